@@ -1,0 +1,832 @@
+"""Pure-Python restatement of the reference's sumcheck / GKR hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (the C-ABI library, its
+C++ host drivers, the ctypes binding) may import or execute this file; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs do, and only as the checker.
+
+This is the *small-case* twin of ``oracle/zk_oracle.c`` (the fast C
+restatement): every function is written with Python integers so that it is an
+independent second statement of the same algorithm.  The two are asserted equal
+in ``tests/test_oracle.py``.
+
+Pinning status
+--------------
+* The Rust reference cannot be built or run here (no cargo/rustc in the image,
+  arkworks/sha3 crates not vendored), so there are no outputs of the reference
+  binary to compare with.
+* Pinned against every known answer held by the reference's own unit tests on
+  this path: see ``tests/test_reference_known_answers.py``.
+* Third-party arithmetic not under /root/reference: ``ark-ff 0.5.0`` /
+  ``ark-bn254 0.5.0`` / ``ark-bls12-381 0.5.0`` (Cargo.lock:45-107) -- results
+  are integers mod p, restated here as ``% p``; ``sha3 0.10.8`` /
+  ``keccak 0.1.5`` (Cargo.lock:559,869) -- Keccak-256 (rate 136, pad 0x01),
+  restated from the published permutation and pinned by the public KATs
+  (keccak256("") and keccak256("abc")).  The reference's own transcript test
+  (fiat_shamir_transcript.rs:45-52) asserts nothing, so transcript *bytes* are
+  "parity unpinned" beyond those KATs.
+
+All ``file:line`` citations are paths under /root/reference/.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Sequence, Tuple
+
+# --------------------------------------------------------------------------
+# Fields.  ark-ff Fp<MontBackend<_,4>>: canonical integers
+# mod p; Montgomery form only matters at the C ABI (R = 2^256).
+# --------------------------------------------------------------------------
+BN254_FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+BN254_FQ = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+BLS12_381_FR = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+FIELD_IDS = {"bn254_fr": 0, "bn254_fq": 1, "bls12_381_fr": 2}
+MODULI = {"bn254_fr": BN254_FR, "bn254_fq": BN254_FQ, "bls12_381_fr": BLS12_381_FR}
+MODULI_BY_ID = {0: BN254_FR, 1: BN254_FQ, 2: BLS12_381_FR}
+R256 = 1 << 256
+
+
+def to_mont(x: int, p: int) -> int:
+    return (x * R256) % p
+
+
+def from_mont(x: int, p: int) -> int:
+    return (x * pow(R256, -1, p)) % p
+
+
+# --------------------------------------------------------------------------
+# Keccak-256 (sha3 0.10.8 `Keccak256`: original Keccak padding 0x01, rate 136)
+# --------------------------------------------------------------------------
+_RC = [
+    0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000,
+    0x000000000000808B, 0x0000000080000001, 0x8000000080008081, 0x8000000000008009,
+    0x000000000000008A, 0x0000000000000088, 0x0000000080008009, 0x000000008000000A,
+    0x000000008000808B, 0x800000000000008B, 0x8000000000008089, 0x8000000000008003,
+    0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+    0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008,
+]
+_ROT = [
+    [0, 36, 3, 41, 18],
+    [1, 44, 10, 45, 2],
+    [62, 6, 43, 15, 61],
+    [28, 55, 25, 21, 56],
+    [27, 20, 39, 8, 14],
+]
+_M64 = (1 << 64) - 1
+
+
+def _rol(x: int, n: int) -> int:
+    n %= 64
+    return ((x << n) | (x >> (64 - n))) & _M64 if n else x
+
+
+def _keccak_f(a: List[List[int]]) -> None:
+    for rnd in range(24):
+        c = [a[x][0] ^ a[x][1] ^ a[x][2] ^ a[x][3] ^ a[x][4] for x in range(5)]
+        d = [c[(x - 1) % 5] ^ _rol(c[(x + 1) % 5], 1) for x in range(5)]
+        for x in range(5):
+            for y in range(5):
+                a[x][y] ^= d[x]
+        b = [[0] * 5 for _ in range(5)]
+        for x in range(5):
+            for y in range(5):
+                b[y][(2 * x + 3 * y) % 5] = _rol(a[x][y], _ROT[x][y])
+        for x in range(5):
+            for y in range(5):
+                a[x][y] = b[x][y] ^ ((~b[(x + 1) % 5][y]) & b[(x + 2) % 5][y])
+        a[0][0] ^= _RC[rnd]
+
+
+def keccak256(data: bytes) -> bytes:
+    rate = 136
+    msg = bytearray(data)
+    msg.append(0x01)
+    while len(msg) % rate:
+        msg.append(0x00)
+    msg[-1] |= 0x80
+    a = [[0] * 5 for _ in range(5)]
+    for off in range(0, len(msg), rate):
+        for i in range(rate // 8):
+            lane = int.from_bytes(msg[off + 8 * i: off + 8 * i + 8], "little")
+            a[i % 5][i // 5] ^= lane
+        _keccak_f(a)
+    out = b"".join(a[i % 5][i // 5].to_bytes(8, "little") for i in range(4))
+    return out
+
+
+# --------------------------------------------------------------------------
+# fiat_shamir/src/fiat_shamir_transcript.rs
+# --------------------------------------------------------------------------
+def fq_vec_to_bytes(values: Sequence[int]) -> bytes:
+    """fiat_shamir_transcript.rs:32-37 -- 32-byte LE canonical per element."""
+    return b"".join(int(v).to_bytes(32, "little") for v in values)
+
+
+class Transcript:
+    """fiat_shamir_transcript.rs:5-30."""
+
+    def __init__(self, p: int):
+        self.p = p
+        self.buf = bytearray()
+
+    def append(self, preimage: bytes) -> None:  # :19-21
+        self.buf += preimage
+
+    def get_random_challenge(self) -> int:  # :23-29
+        digest = keccak256(bytes(self.buf))  # finalize_reset
+        self.buf = bytearray(digest)  # re-seeded with the digest
+        return int.from_bytes(digest, "little") % self.p
+
+
+# --------------------------------------------------------------------------
+# univariate_polynomial/src/univariate_polynomial_dense.rs
+# --------------------------------------------------------------------------
+def _trim(c: List[int]) -> List[int]:  # :14-18
+    c = list(c)
+    while c and c[-1] == 0:
+        c.pop()
+    return c
+
+
+def uni_evaluate(coeffs: Sequence[int], x: int, p: int) -> int:  # :20-26
+    return sum(c * pow(x, i, p) for i, c in enumerate(coeffs)) % p
+
+
+def uni_interpolate(points: Sequence[Tuple[int, int]], p: int) -> List[int]:
+    """:48-74 -- Lagrange interpolation to ascending coefficients, then trim.
+
+    The reference builds each basis polynomial with trimmed intermediates; the
+    result is the (unique) interpolant's coefficient vector with trailing zeros
+    removed, possibly empty.
+    """
+    n = len(points)
+    result = [0]
+    for i in range(n):
+        x_i, y_i = points[i]
+        l_i = [1]
+        for j in range(n):
+            if i == j:
+                continue
+            x_j = points[j][0]
+            inv = pow((x_i - x_j) % p, -1, p)
+            num = _trim([(-x_j * inv) % p, inv % p])  # numerator.scalar_mul(1/denominator)
+            a, b = _trim(l_i), num
+            prod = [0] * (len(a) + len(b) - 1)
+            for ia, ca in enumerate(a):
+                for ib, cb in enumerate(b):
+                    prod[ia + ib] = (prod[ia + ib] + ca * cb) % p
+            l_i = prod
+        term = _trim([(c * y_i) % p for c in l_i])
+        m = max(len(result), len(term))
+        s = [0] * m
+        for k, c in enumerate(result):
+            s[k] = (s[k] + c) % p
+        for k, c in enumerate(term):
+            s[k] = (s[k] + c) % p
+        result = s
+    return _trim(result)
+
+
+# --------------------------------------------------------------------------
+# multilinear_polynomial/src/multilinear_polynomial_evaluation.rs
+# --------------------------------------------------------------------------
+ADD, MUL = 0, 1  # Operation :4-17
+
+
+def op_apply(op: int, a: int, b: int, p: int) -> int:
+    return (a + b) % p if op == ADD else (a * b) % p
+
+
+def _insert_bit(value: int, bit: int) -> int:  # :158-164
+    high = value >> bit
+    low = value & ((1 << bit) - 1)
+    return (high << (bit + 1)) | low
+
+
+class MultilinearPoly:
+    """:19-111.  ``evaluation`` is a list of canonical ints; variable 0 = MSB."""
+
+    def __init__(self, evaluations: Sequence[int], p: int):
+        n = len(evaluations)
+        if n == 0:
+            raise ValueError("ilog2 of zero")  # Rust: panics in ilog2
+        nv = n.bit_length() - 1
+        if n != 1 << nv:
+            raise ValueError("Invalid evaluations")  # :30
+        self.evaluation = [int(e) % p for e in evaluations]
+        self.num_of_vars = nv
+        self.p = p
+
+    def partial_evaluate(self, bit: int, value: int) -> "MultilinearPoly":  # :52-63
+        p, n = self.p, self.num_of_vars
+        inv = n - bit - 1
+        out = []
+        for val in range(1 << (n - 1)):
+            i0 = _insert_bit(val, inv)
+            i1 = i0 | (1 << inv)
+            a, b = self.evaluation[i0], self.evaluation[i1]
+            out.append((a + value * (b - a)) % p)
+        return MultilinearPoly(out, p)
+
+    def multi_partial_evaluate(self, values: Sequence[int]) -> "MultilinearPoly":  # :65-77
+        if len(values) > self.num_of_vars:
+            raise ValueError("Invalid number of values")
+        poly = self
+        for v in values:
+            poly = poly.partial_evaluate(0, v)
+        return poly
+
+    def evaluate(self, values: Sequence[int]) -> int:  # :79-91
+        if len(values) != self.num_of_vars:
+            raise ValueError("Invalid number of values")
+        poly = self
+        for v in values:
+            poly = poly.partial_evaluate(0, v)
+        return poly.evaluation[0]
+
+    def scale(self, value: int) -> "MultilinearPoly":  # :93-97
+        return MultilinearPoly([(e * value) % self.p for e in self.evaluation], self.p)
+
+    @staticmethod
+    def tensor_add_mul_polynomials(a: Sequence[int], b: Sequence[int], op: int, p: int) -> "MultilinearPoly":
+        """:99-111 -- out[i*|b|+j] = a[i] op b[j]."""
+        return MultilinearPoly([op_apply(op, x, y, p) for x in a for y in b], p)
+
+    def add(self, o: "MultilinearPoly") -> "MultilinearPoly":  # :113-126 (zip: shorter length)
+        return MultilinearPoly([(x + y) % self.p for x, y in zip(self.evaluation, o.evaluation)], self.p)
+
+    def mul(self, o: "MultilinearPoly") -> "MultilinearPoly":  # :128-141
+        return MultilinearPoly([(x * y) % self.p for x, y in zip(self.evaluation, o.evaluation)], self.p)
+
+    def sub(self, o: "MultilinearPoly") -> "MultilinearPoly":  # :143-156
+        return MultilinearPoly([(x - y) % self.p for x, y in zip(self.evaluation, o.evaluation)], self.p)
+
+
+# --------------------------------------------------------------------------
+# multilinear_polynomial/src/composed_polynomial.rs
+# --------------------------------------------------------------------------
+class ProductPoly:
+    def __init__(self, evaluations: Sequence[Sequence[int]], p: int):  # :16-29
+        l1 = len(evaluations[0])
+        if any(len(e) != l1 for e in evaluations):
+            raise ValueError("all evaluations must have same length")
+        self.evaluation = [MultilinearPoly(e, p) for e in evaluations]
+        self.p = p
+
+    def evaluate(self, values: Sequence[int]) -> int:  # :31-36
+        r = 1
+        for poly in self.evaluation:
+            r = (r * poly.evaluate(values)) % self.p
+        return r
+
+    def partial_evaluate(self, value: int) -> "ProductPoly":  # :38-50
+        return ProductPoly([m.partial_evaluate(0, value).evaluation for m in self.evaluation], self.p)
+
+    def reduce(self, mode: str = "compat") -> List[int]:
+        """:52-54 -- compat: factors 0 and 1 ONLY (reference quirk).
+        full: the true product of all factors."""
+        if mode == "compat":
+            return self.evaluation[0].mul(self.evaluation[1]).evaluation
+        out = list(self.evaluation[0].evaluation)
+        for m in self.evaluation[1:]:
+            out = [(x * y) % self.p for x, y in zip(out, m.evaluation)]
+        return out
+
+    def get_degree(self) -> int:  # :56-58
+        return len(self.evaluation)
+
+
+class SumPoly:
+    def __init__(self, polys: Sequence[ProductPoly]):  # :62-69
+        d1 = polys[0].get_degree()
+        if any(q.get_degree() != d1 for q in polys):
+            raise ValueError("all product polys must have same degree")
+        self.polys = list(polys)
+        self.p = polys[0].p
+
+    def evaluate(self, values: Sequence[int]) -> int:  # :71-76
+        return sum(q.evaluate(values) for q in self.polys) % self.p
+
+    def partial_evaluate(self, value: int) -> "SumPoly":  # :78-86
+        return SumPoly([q.partial_evaluate(value) for q in self.polys])
+
+    def reduce(self, mode: str = "compat") -> List[int]:
+        """:88-99 -- compat: products 0 and 1 ONLY (IndexError if P<2, as the
+        reference panics).  full: sum over all products."""
+        if mode == "compat":
+            a = self.polys[0].reduce("compat")
+            b = self.polys[1].reduce("compat")
+            return [(x + y) % self.p for x, y in zip(a, b)]
+        acc = self.polys[0].reduce("full")
+        for q in self.polys[1:]:
+            acc = [(x + y) % self.p for x, y in zip(acc, q.reduce("full"))]
+        return acc
+
+    def get_degree(self) -> int:  # :101-103
+        return self.polys[0].get_degree()
+
+
+# --------------------------------------------------------------------------
+# sum_check/src/sum_check_protocol.rs
+# --------------------------------------------------------------------------
+@dataclass
+class Proof:  # :8-12
+    proof_polynomials: List[List[int]]
+    claimed_sum: int
+    challenges: List[int] = field(default_factory=list)  # not in the reference struct; for tests
+
+
+@dataclass
+class GkrSumcheckProof:  # :13-17 (GkrProof)
+    proof_polynomials: List[List[int]]  # trimmed coefficient vectors
+    claimed_sum: int
+    random_challenges: List[int]
+
+
+@dataclass
+class GkrVerify:  # :19-23
+    verified: bool
+    final_claimed_sum: int
+    random_challenges: List[int]
+
+
+def get_round_partial_polynomial_proof(evals: Sequence[int], p: int) -> List[int]:  # :168-175
+    mid = len(evals) // 2
+    return [sum(evals[:mid]) % p, sum(evals[mid:]) % p]
+
+
+def prove(poly: MultilinearPoly) -> Proof:  # :25-52
+    p = poly.p
+    t = Transcript(p)
+    t.append(fq_vec_to_bytes(poly.evaluation))
+    claimed = sum(poly.evaluation) % p
+    t.append(fq_vec_to_bytes([claimed]))
+    cur = poly
+    msgs, chals = [], []
+    for _ in range(poly.num_of_vars):
+        m = get_round_partial_polynomial_proof(cur.evaluation, p)
+        t.append(fq_vec_to_bytes(m))
+        msgs.append(m)
+        r = t.get_random_challenge()
+        chals.append(r)
+        cur = cur.partial_evaluate(0, r)
+    return Proof(msgs, claimed, chals)
+
+
+def verify(poly: MultilinearPoly, proof: Proof) -> bool:  # :54-84
+    p = poly.p
+    t = Transcript(p)
+    t.append(fq_vec_to_bytes(poly.evaluation))
+    t.append(fq_vec_to_bytes([proof.claimed_sum]))
+    chals = []
+    expected = proof.claimed_sum % p
+    for m in proof.proof_polynomials:
+        mp = MultilinearPoly(m, p)
+        if sum(mp.evaluation) % p != expected:
+            return False
+        t.append(fq_vec_to_bytes(mp.evaluation))
+        r = t.get_random_challenge()
+        expected = (mp.evaluation[0] + r * (mp.evaluation[1] - mp.evaluation[0])) % p
+        chals.append(r)
+    return expected == poly.evaluate(chals)
+
+
+def get_round_partial_polynomial_proof_gkr(sp: SumPoly, mode: str = "compat") -> List[int]:  # :152-166
+    p = sp.p
+    d = sp.get_degree()
+    pts = []
+    for i in range(d + 1):
+        part = sp.partial_evaluate(i % p)
+        pts.append((i % p, sum(part.reduce(mode)) % p))
+    return uni_interpolate(pts, p)
+
+
+def gkr_prove(claimed_sum: int, sp: SumPoly, t: Transcript, mode: str = "compat") -> GkrSumcheckProof:  # :86-115
+    n = sp.polys[0].evaluation[0].num_of_vars
+    cur = sp
+    polys, chals = [], []
+    for _ in range(n):
+        c = get_round_partial_polynomial_proof_gkr(cur, mode)
+        t.append(fq_vec_to_bytes(c))
+        polys.append(c)
+        r = t.get_random_challenge()
+        chals.append(r)
+        cur = cur.partial_evaluate(r)
+    return GkrSumcheckProof(polys, claimed_sum, chals)
+
+
+def gkr_verify(round_polys: Sequence[Sequence[int]], claimed_sum: int, t: Transcript) -> GkrVerify:  # :117-150
+    p = t.p
+    chals = []
+    for c in round_polys:
+        if (uni_evaluate(c, 0, p) + uni_evaluate(c, 1, p)) % p != claimed_sum % p:
+            return GkrVerify(False, 0, [0])
+        t.append(fq_vec_to_bytes(c))
+        r = t.get_random_challenge()
+        chals.append(r)
+        claimed_sum = uni_evaluate(c, r, p)
+    return GkrVerify(True, claimed_sum, chals)
+
+
+# --------------------------------------------------------------------------
+# gkr/src/gkr_circuit.rs
+# --------------------------------------------------------------------------
+class Layer:
+    """:25-104.  ``ops[i]`` is gate i's Operation; gate i reads wires 2i, 2i+1."""
+
+    def __init__(self, ops: Sequence[int]):
+        self.ops = list(ops)
+        self.outputs: List[int] = []
+
+    def n_bits(self) -> int:  # get_bits_for_gates :54-65
+        n = len(self.ops)
+        assert n > 0, "There must be at least one gate in the layer."
+        if n == 1:
+            return 3
+        lg = n.bit_length() - 1
+        return lg + 2 * (lg + 1)
+
+    def gate_to_bits(self) -> List[int]:  # :67-104
+        n = len(self.ops)
+        lg = n.bit_length() - 1
+        out = []
+        for idx in range(n):
+            vals = [idx, 2 * idx, 2 * idx + 1]
+            acc = 0
+            for i, v in enumerate(vals):
+                w = 1 if n == 1 else (lg if i == 0 else lg + 1)
+                acc = (acc << w) | v
+            out.append(acc)
+        return out
+
+    def get_add_mul_i(self, op: int, p: int) -> MultilinearPoly:  # :39-52
+        ev = [0] * (1 << self.n_bits())
+        for gv, gop in zip(self.gate_to_bits(), self.ops):
+            if gop == op:
+                ev[gv] = 1
+        return MultilinearPoly(ev, p)
+
+
+class Circuit:
+    """:107-143."""
+
+    def __init__(self, structure: Sequence[Sequence[int]]):
+        self.layers = [Layer(ops) for ops in structure]
+
+    def evaluate(self, inputs: Sequence[int], p: int) -> List[List[int]]:  # :127-143
+        result = []
+        cur = [int(x) % p for x in inputs]
+        for layer in self.layers:
+            outs = []
+            # zip(gates, chunks_exact(2)): stops at the shorter of the two
+            for g, op in enumerate(layer.ops):
+                if 2 * g + 1 >= len(cur):
+                    outs.append(layer.outputs[g] if g < len(layer.outputs) else 0)
+                    continue
+                outs.append(op_apply(op, cur[2 * g], cur[2 * g + 1], p))
+            layer.outputs = outs
+            result.append(list(outs))
+            cur = outs
+        return result
+
+
+# --------------------------------------------------------------------------
+# gkr/src/gkr_protocol.rs  (KZG input opening :92-118 / :157-183 is out of
+# scope -- replaced by a direct evaluate of the input MLE)
+# --------------------------------------------------------------------------
+@dataclass
+class GkrProof:  # :23-29 minus input_proof
+    output_poly: List[int]
+    proof_polynomials: List[List[List[int]]]
+    claimed_evaluations: List[Tuple[int, int]]
+    final_openings: Tuple[int, int]  # (W_in(r_b), W_in(r_c)) -- what the KZG opening would carry
+    final_rb: List[int] = field(default_factory=list)
+    final_rc: List[int] = field(default_factory=list)
+
+
+def initiate_protocol(t: Transcript, output_poly: MultilinearPoly) -> Tuple[int, int]:  # :229-241
+    t.append(fq_vec_to_bytes(output_poly.evaluation))
+    r = t.get_random_challenge()
+    m0 = output_poly.evaluate([r])
+    t.append(fq_vec_to_bytes([m0]))
+    return m0, r
+
+
+def get_fbc_poly(r: int, layer: Layer, w_b: Sequence[int], w_c: Sequence[int], p: int) -> SumPoly:  # :243-263
+    add_i = layer.get_add_mul_i(ADD, p).partial_evaluate(0, r)
+    mul_i = layer.get_add_mul_i(MUL, p).partial_evaluate(0, r)
+    sw = MultilinearPoly.tensor_add_mul_polynomials(w_b, w_c, ADD, p)
+    mw = MultilinearPoly.tensor_add_mul_polynomials(w_b, w_c, MUL, p)
+    return SumPoly([ProductPoly([add_i.evaluation, sw.evaluation], p),
+                    ProductPoly([mul_i.evaluation, mw.evaluation], p)])
+
+
+def get_folded_fbc_poly(layer: Layer, w_b, w_c, r_b, r_c, alpha: int, beta: int, p: int) -> SumPoly:  # :265-292
+    add_i = layer.get_add_mul_i(ADD, p)
+    mul_i = layer.get_add_mul_i(MUL, p)
+    s_add = add_i.multi_partial_evaluate(r_b).scale(alpha).add(add_i.multi_partial_evaluate(r_c).scale(beta))
+    s_mul = mul_i.multi_partial_evaluate(r_b).scale(alpha).add(mul_i.multi_partial_evaluate(r_c).scale(beta))
+    sw = MultilinearPoly.tensor_add_mul_polynomials(w_b, w_c, ADD, p)
+    mw = MultilinearPoly.tensor_add_mul_polynomials(w_b, w_c, MUL, p)
+    return SumPoly([ProductPoly([s_add.evaluation, sw.evaluation], p),
+                    ProductPoly([s_mul.evaluation, mw.evaluation], p)])
+
+
+def gkr_protocol_prove_dense(circuit: Circuit, inputs: Sequence[int], p: int) -> GkrProof:
+    """gkr_protocol.rs:31-91 with the dense add_i/mul_i tables, exactly as the
+    reference builds them (only feasible for tiny circuits)."""
+    t = Transcript(p)
+    inputs = [int(x) % p for x in inputs]
+    evals = circuit.evaluate(inputs, p)
+    w0 = list(evals[-1])
+    if len(w0) == 1:
+        w0.append(0)
+    out_poly = MultilinearPoly(w0, p)
+    claimed, r0 = initiate_protocol(t, out_poly)
+    nl = len(circuit.layers)
+    proofs, claimed_evals = [], []
+    rb: List[int] = []
+    rc: List[int] = []
+    alpha = beta = 0
+    evals_rev = list(reversed(evals))
+    layers_rev = list(reversed(circuit.layers))
+    o1 = o2 = 0
+    for idx, layer in enumerate(layers_rev):
+        w_i = inputs if idx == nl - 1 else evals_rev[idx + 1]
+        if idx == 0:
+            fbc = get_fbc_poly(r0, layer, w_i, w_i, p)
+        else:
+            fbc = get_folded_fbc_poly(layer, w_i, w_i, rb, rc, alpha, beta, p)
+        sc = gkr_prove(claimed, fbc, t, "compat")
+        proofs.append(sc.proof_polynomials)
+        nxt = MultilinearPoly(w_i, p)
+        mid = len(sc.random_challenges) // 2
+        rb, rc = sc.random_challenges[:mid], sc.random_challenges[mid:]
+        o1, o2 = nxt.evaluate(rb), nxt.evaluate(rc)
+        if idx < nl - 1:
+            t.append(fq_vec_to_bytes([o1]))
+            alpha = t.get_random_challenge()
+            t.append(fq_vec_to_bytes([o2]))
+            beta = t.get_random_challenge()
+            claimed = (alpha * o1 + beta * o2) % p
+            claimed_evals.append((o1, o2))
+    return GkrProof(w0, proofs, claimed_evals, (o1, o2), list(rb), list(rc))
+
+
+def gkr_protocol_verify_dense(proof: GkrProof, circuit: Circuit, inputs: Sequence[int], p: int) -> bool:
+    """gkr_protocol.rs:128-227 with dense wiring tables.  The KZG check of the
+    input opening (:157-183) is replaced by evaluating the input MLE directly."""
+    t = Transcript(p)
+    claim, r0 = initiate_protocol(t, MultilinearPoly(proof.output_poly, p))
+    alpha = beta = 0
+    prev: List[int] = []
+    layers = list(reversed(circuit.layers))
+    nl = len(layers)
+    in_poly = MultilinearPoly(inputs, p)
+    for i, layer in enumerate(layers):
+        v = gkr_verify(proof.proof_polynomials[i], claim, t)
+        if not v.verified:
+            return False
+        cur = v.random_challenges
+        if i == nl - 1:
+            mid = len(cur) // 2
+            o1, o2 = in_poly.evaluate(cur[:mid]), in_poly.evaluate(cur[mid:])
+            if (o1, o2) != tuple(proof.final_openings):
+                return False
+        else:
+            o1, o2 = proof.claimed_evaluations[i]
+        if i == 0:  # get_verifier_claim :294-314
+            allr = [r0] + list(cur)
+            a_r = layer.get_add_mul_i(ADD, p).evaluate(allr)
+            m_r = layer.get_add_mul_i(MUL, p).evaluate(allr)
+        else:  # get_folded_verifier_claim :316-341
+            mid = len(prev) // 2
+            prb, prc = prev[:mid], prev[mid:]
+            add_i = layer.get_add_mul_i(ADD, p)
+            mul_i = layer.get_add_mul_i(MUL, p)
+            sa = add_i.multi_partial_evaluate(prb).scale(alpha).add(add_i.multi_partial_evaluate(prc).scale(beta))
+            sm = mul_i.multi_partial_evaluate(prb).scale(alpha).add(mul_i.multi_partial_evaluate(prc).scale(beta))
+            a_r, m_r = sa.evaluate(cur), sm.evaluate(cur)
+        expected = (a_r * (o1 + o2) + m_r * (o1 * o2)) % p
+        if expected != v.final_claimed_sum:
+            return False
+        prev = cur
+        t.append(fq_vec_to_bytes([o1]))
+        alpha = t.get_random_challenge()
+        t.append(fq_vec_to_bytes([o2]))
+        beta = t.get_random_challenge()
+        claim = (alpha * o1 + beta * o2) % p
+    return True
+
+
+# --------------------------------------------------------------------------
+# Sparse ("two-phase", linear-time) restatement of the same per-layer sumcheck.
+# The dense tables above are the MLEs of the add/mul wiring predicates and of
+# W(b)+W(c), W(b)*W(c), so the round polynomials are identical;
+# tests assert equality with gkr_protocol_prove_dense on small circuits.
+# --------------------------------------------------------------------------
+def eq_table(r: Sequence[int], p: int) -> List[int]:
+    """eq(r, x) for x in {0,1}^len(r), variable 0 = MSB of x."""
+    t = [1]
+    for rv in r:
+        nt = []
+        for e in t:
+            hi = (e * rv) % p
+            nt.append((e - hi) % p)
+            nt.append(hi)
+        t = nt
+    return t
+
+
+def _sumcheck_xy_z(X: List[int], Y: List[int], Z: List[int], t: Transcript, p: int):
+    """Sumcheck of sum_x X(x)*Y(x) + Z(x), degree 2, messages as trimmed
+    coefficient vectors (same wire format as gkr_prove :96-108)."""
+    n = (len(X)).bit_length() - 1
+    polys, chals = [], []
+    for _ in range(n):
+        h = len(X) // 2
+        pts = []
+        for tt in range(3):
+            s = 0
+            for i in range(h):
+                x = X[i] + tt * (X[i + h] - X[i])
+                y = Y[i] + tt * (Y[i + h] - Y[i])
+                z = Z[i] + tt * (Z[i + h] - Z[i])
+                s += x * y + z
+            pts.append((tt, s % p))
+        c = uni_interpolate(pts, p)
+        t.append(fq_vec_to_bytes(c))
+        polys.append(c)
+        r = t.get_random_challenge()
+        chals.append(r)
+        X = [(X[i] + r * (X[i + h] - X[i])) % p for i in range(h)]
+        Y = [(Y[i] + r * (Y[i + h] - Y[i])) % p for i in range(h)]
+        Z = [(Z[i] + r * (Z[i + h] - Z[i])) % p for i in range(h)]
+    return polys, chals, X[0], Y[0], Z[0]
+
+
+def gkr_layer_coef(layer_ops: Sequence[int], idx: int, r0: int, rb, rc, alpha: int, beta: int, p: int) -> List[int]:
+    """coef[g] = weight of gate g in the bound wiring predicate.
+
+    idx == 0 (get_fbc_poly :249-254): ONE `a` variable bound with r0; the output
+    layer has 1 or 2 gates, `a` is 1 bit wide in both cases.
+    idx  > 0 (get_folded_fbc_poly :277-281): alpha*eq(r_b,g) + beta*eq(r_c,g),
+    where `a` is log2(G) bits wide (G>1).  multi_partial_evaluate binds
+    len(r_b) leading variables; for G>1, len(r_b) = log2(G_prev)+1 = log2(G).
+    """
+    G = len(layer_ops)
+    if idx == 0:
+        e = eq_table([r0], p)
+        return [e[g] for g in range(G)]
+    ea, eb = eq_table(rb, p), eq_table(rc, p)
+    return [(alpha * ea[g] + beta * eb[g]) % p for g in range(G)]
+
+
+def gkr_protocol_prove_sparse(circuit: Circuit, inputs: Sequence[int], p: int) -> GkrProof:
+    t = Transcript(p)
+    inputs = [int(x) % p for x in inputs]
+    evals = circuit.evaluate(inputs, p)
+    w0 = list(evals[-1])
+    if len(w0) == 1:
+        w0.append(0)
+    claimed, r0 = initiate_protocol(t, MultilinearPoly(w0, p))
+    nl = len(circuit.layers)
+    proofs, claimed_evals = [], []
+    rb: List[int] = []
+    rc: List[int] = []
+    alpha = beta = 0
+    evals_rev = list(reversed(evals))
+    layers_rev = list(reversed(circuit.layers))
+    o1 = o2 = 0
+    for idx, layer in enumerate(layers_rev):
+        W = list(inputs if idx == nl - 1 else evals_rev[idx + 1])
+        G = len(layer.ops)
+        nw = len(W)  # = 2G
+        coef = gkr_layer_coef(layer.ops, idx, r0, rb, rc, alpha, beta, p)
+        # phase 1 over b: W(b)*(hA(b)+hM(b)) + hA2(b)
+        H1 = [0] * nw
+        HA2 = [0] * nw
+        for g, op in enumerate(layer.ops):
+            b, c = 2 * g, 2 * g + 1
+            if op == ADD:
+                H1[b] = (H1[b] + coef[g]) % p
+                HA2[b] = (HA2[b] + coef[g] * W[c]) % p
+            else:
+                H1[b] = (H1[b] + coef[g] * W[c]) % p
+        polys1, u, Wu, _, _ = _sumcheck_xy_z(list(W), H1, HA2, t, p)
+        # phase 2 over c: W(c)*(A2(c) + Wu*M2(c)) + Wu*A2(c)
+        eu = eq_table(u, p)
+        A2 = [0] * nw
+        M2 = [0] * nw
+        for g, op in enumerate(layer.ops):
+            b, c = 2 * g, 2 * g + 1
+            v = (coef[g] * eu[b]) % p
+            if op == ADD:
+                A2[c] = (A2[c] + v) % p
+            else:
+                M2[c] = (M2[c] + v) % p
+        C = [(A2[i] + Wu * M2[i]) % p for i in range(nw)]
+        D = [(Wu * A2[i]) % p for i in range(nw)]
+        polys2, v, Wv, _, _ = _sumcheck_xy_z(list(W), C, D, t, p)
+        proofs.append(polys1 + polys2)
+        rb, rc = u, v
+        o1, o2 = Wu, Wv
+        if idx < nl - 1:
+            t.append(fq_vec_to_bytes([o1]))
+            alpha = t.get_random_challenge()
+            t.append(fq_vec_to_bytes([o2]))
+            beta = t.get_random_challenge()
+            claimed = (alpha * o1 + beta * o2) % p
+            claimed_evals.append((o1, o2))
+    return GkrProof(w0, proofs, claimed_evals, (o1, o2), list(rb), list(rc))
+
+
+def gkr_protocol_verify_sparse(proof: GkrProof, circuit: Circuit, inputs: Sequence[int], p: int) -> bool:
+    """Verifier with O(G) wiring-predicate evaluation through eq tables
+    (same acceptance predicate as gkr_protocol.rs:128-227)."""
+    t = Transcript(p)
+    claim, r0 = initiate_protocol(t, MultilinearPoly(proof.output_poly, p))
+    alpha = beta = 0
+    prb: List[int] = []
+    prc: List[int] = []
+    layers = list(reversed(circuit.layers))
+    nl = len(layers)
+    in_poly = MultilinearPoly(inputs, p)
+    for i, layer in enumerate(layers):
+        v = gkr_verify(proof.proof_polynomials[i], claim, t)
+        if not v.verified:
+            return False
+        cur = v.random_challenges
+        mid = len(cur) // 2
+        u, w = cur[:mid], cur[mid:]
+        if i == nl - 1:
+            o1, o2 = in_poly.evaluate(u), in_poly.evaluate(w)
+            if (o1, o2) != tuple(proof.final_openings):
+                return False
+        else:
+            o1, o2 = proof.claimed_evaluations[i]
+        coef = gkr_layer_coef(layer.ops, i, r0, prb, prc, alpha, beta, p)
+        eu, ew = eq_table(u, p), eq_table(w, p)
+        a_r = m_r = 0
+        for g, op in enumerate(layer.ops):
+            term = coef[g] * eu[2 * g] % p * ew[2 * g + 1] % p
+            if op == ADD:
+                a_r = (a_r + term) % p
+            else:
+                m_r = (m_r + term) % p
+        if (a_r * (o1 + o2) + m_r * (o1 * o2)) % p != v.final_claimed_sum:
+            return False
+        prb, prc = u, w
+        t.append(fq_vec_to_bytes([o1]))
+        alpha = t.get_random_challenge()
+        t.append(fq_vec_to_bytes([o2]))
+        beta = t.get_random_challenge()
+        claim = (alpha * o1 + beta * o2) % p
+    return True
+
+
+# --------------------------------------------------------------------------
+# "full"-mode composed sumcheck in evaluation form (what the GPU computes):
+# (d+1) evaluations per round, used to cross-check the fused kernels without
+# the reference's (d+2) folds.
+# --------------------------------------------------------------------------
+def round_evals_full(tables: Sequence[Sequence[Sequence[int]]], p: int) -> List[int]:
+    """tables[prod][factor][i]; returns s(0..d) with s(t)=sum_i sum_prod prod_f."""
+    d = len(tables[0])
+    h = len(tables[0][0]) // 2
+    out = []
+    for tt in range(d + 1):
+        s = 0
+        for prod in tables:
+            for i in range(h):
+                m = 1
+                for f in prod:
+                    m = (m * (f[i] + tt * (f[i + h] - f[i]))) % p
+                s += m
+        out.append(s % p)
+    return out
+
+
+# --------------------------------------------------------------------------
+# Synthetic inputs: entry i of table t from SplitMix64.
+# --------------------------------------------------------------------------
+def splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def synth_entry(seed: int, table: int, i: int, field_id: int = 0) -> int:
+    """Canonical value < 2^253 (2^254 for BLS12-381 Fr): limbs are
+    SplitMix64(base + limb) with base = SplitMix64(seed ^ (table << 48)) + 4*i."""
+    base = (splitmix64((seed ^ (table << 48)) & _M64) + 4 * i) & _M64
+    limbs = [splitmix64((base + k) & _M64) for k in range(4)]
+    limbs[3] &= (1 << (62 if field_id == 2 else 61)) - 1
+    return limbs[0] | (limbs[1] << 64) | (limbs[2] << 128) | (limbs[3] << 192)
+
+
+def synth_table(seed: int, table: int, n_vars: int, field_id: int = 0) -> List[int]:
+    return [synth_entry(seed, table, i, field_id) for i in range(1 << n_vars)]

@@ -1,0 +1,944 @@
+/*
+ * zk_oracle.c -- CPU restatement (plain C11) of the reference's sumcheck / GKR
+ * hot path.  TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library, and
+ * only as the checker / the timed CPU baseline.  The product (libzkb200.so and
+ * everything under zk-research-implementations_b200/) never links or calls it.
+ *
+ * Pinning status: the Rust reference cannot be compiled here (no cargo/rustc;
+ * arkworks + sha3 crates are crates.io dependencies, not vendored), so this is
+ * a restatement, not the reference binary.  It is pinned against every known
+ * answer in the reference's own unit tests for this path (SURVEY.md section 4;
+ * tests/test_reference_known_answers.py) and against the independent
+ * pure-Python twin oracle/pyref.py (tests/test_oracle.py).  Transcript bytes
+ * are "parity unpinned" beyond the public Keccak-256 KATs, because the
+ * reference's only transcript test asserts nothing
+ * (fiat_shamir/src/fiat_shamir_transcript.rs:45-52).
+ *
+ * Third-party algorithms restated (not under /root/reference):
+ *   ark-ff 0.5.0 Fp<MontBackend<_,4>> (Cargo.lock:89-107): 4x64-bit Montgomery,
+ *     R = 2^256; ark-bn254 0.5.0 Fr/Fq, ark-bls12-381 0.5.0 Fr moduli.
+ *   sha3 0.10.8 Keccak256 / keccak 0.1.5 (Cargo.lock:559,869): Keccak-f[1600],
+ *     rate 136, padding 0x01 .. 0x80.
+ *
+ * The loops deliberately follow the reference's SCHEDULE (a fresh allocation
+ * per fold, (d+2) folds of every table per composed round, clone per call) so
+ * that timing this file is a fair stand-in for the reference's CPU path.
+ * All file:line citations are paths under /root/reference/.
+ *
+ * ABI: field elements cross as uint64_t[4] little-endian limbs of the CANONICAL
+ * integer (not Montgomery) unless a function says otherwise.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+typedef uint8_t u8;
+
+/* ------------------------------------------------------------------ fields */
+typedef struct {
+    u64 p[4];
+    u64 r2[4];  /* R^2 mod p */
+    u64 one[4]; /* R mod p   */
+    u64 inv;    /* -p^{-1} mod 2^64 */
+} fctx;
+
+static const fctx FIELDS[3] = {
+    /* BN254 Fr */
+    {{0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
+     {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL},
+     {0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL},
+     0xc2e1f593efffffffULL},
+    /* BN254 Fq */
+    {{0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
+     {0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL},
+     {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL},
+     0x87d20782e4866389ULL},
+    /* BLS12-381 Fr */
+    {{0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL},
+     {0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL, 0x05d314967254398fULL, 0x0748d9d99f59ff11ULL},
+     {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL},
+     0xfffffffeffffffffULL},
+};
+
+typedef struct { u64 v[4]; } fe; /* Montgomery residue, fully reduced */
+
+static inline int ge_p(const u64 a[4], const u64 p[4]) {
+    for (int i = 3; i >= 0; --i) {
+        if (a[i] > p[i]) return 1;
+        if (a[i] < p[i]) return 0;
+    }
+    return 1;
+}
+static inline void sub_p(u64 a[4], const u64 p[4]) {
+    u128 b = 0;
+    for (int i = 0; i < 4; ++i) {
+        u128 d = (u128)a[i] - p[i] - (u64)b;
+        a[i] = (u64)d;
+        b = (d >> 64) & 1;
+    }
+}
+static inline fe f_add(const fctx* F, fe a, fe b) {
+    fe r;
+    u128 c = 0;
+    for (int i = 0; i < 4; ++i) {
+        c += (u128)a.v[i] + b.v[i];
+        r.v[i] = (u64)c;
+        c >>= 64;
+    }
+    if (c || ge_p(r.v, F->p)) sub_p(r.v, F->p);
+    return r;
+}
+static inline fe f_sub(const fctx* F, fe a, fe b) {
+    fe r;
+    u128 bw = 0;
+    for (int i = 0; i < 4; ++i) {
+        u128 d = (u128)a.v[i] - b.v[i] - (u64)bw;
+        r.v[i] = (u64)d;
+        bw = (d >> 64) & 1;
+    }
+    if (bw) {
+        u128 c = 0;
+        for (int i = 0; i < 4; ++i) {
+            c += (u128)r.v[i] + F->p[i];
+            r.v[i] = (u64)c;
+            c >>= 64;
+        }
+    }
+    return r;
+}
+static inline fe f_mul(const fctx* F, fe a, fe b) {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        u128 c = 0;
+        for (int j = 0; j < 4; ++j) {
+            c += (u128)a.v[j] * b.v[i] + t[j];
+            t[j] = (u64)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (u64)c;
+        t[5] = (u64)(c >> 64);
+        u64 m = t[0] * F->inv;
+        c = (u128)m * F->p[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; ++j) {
+            c += (u128)m * F->p[j] + t[j];
+            t[j - 1] = (u64)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (u64)c;
+        t[4] = t[5] + (u64)(c >> 64);
+    }
+    fe r = {{t[0], t[1], t[2], t[3]}};
+    if (t[4] || ge_p(r.v, F->p)) sub_p(r.v, F->p);
+    return r;
+}
+static inline fe f_zero(void) { fe r = {{0, 0, 0, 0}}; return r; }
+static inline fe f_one(const fctx* F) { fe r; memcpy(r.v, F->one, 32); return r; }
+static inline int f_is_zero(fe a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+static inline int f_eq(fe a, fe b) { return memcmp(a.v, b.v, 32) == 0; }
+static inline fe f_to_mont(const fctx* F, const u64 c[4]) {
+    fe a, r2;
+    memcpy(a.v, c, 32);
+    while (ge_p(a.v, F->p)) sub_p(a.v, F->p);
+    memcpy(r2.v, F->r2, 32);
+    return f_mul(F, a, r2);
+}
+static inline void f_from_mont(const fctx* F, fe a, u64 out[4]) {
+    fe o = {{1, 0, 0, 0}};
+    fe r = f_mul(F, a, o);
+    memcpy(out, r.v, 32);
+}
+static inline fe f_from_u64(const fctx* F, u64 x) {
+    u64 c[4] = {x, 0, 0, 0};
+    return f_to_mont(F, c);
+}
+static fe f_pow(const fctx* F, fe a, const u64 e[4]) {
+    fe r = f_one(F);
+    for (int i = 255; i >= 0; --i) {
+        r = f_mul(F, r, r);
+        if ((e[i / 64] >> (i % 64)) & 1) r = f_mul(F, r, a);
+    }
+    return r;
+}
+static fe f_inv(const fctx* F, fe a) { /* Fermat: a^(p-2) */
+    u64 e[4];
+    memcpy(e, F->p, 32);
+    e[0] -= 2; /* p is odd and p[0] >= 2 for all three moduli */
+    return f_pow(F, a, e);
+}
+
+/* ------------------------------------------------------------------ keccak */
+static const u64 KRC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+static const int KROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+static const int KPIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+#define ROL64(x, n) (((x) << (n)) | ((x) >> (64 - (n))))
+
+static void keccak_f(u64 st[25]) {
+    u64 bc[5], t;
+    for (int r = 0; r < 24; ++r) {
+        for (int i = 0; i < 5; ++i) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+        for (int i = 0; i < 5; ++i) {
+            t = bc[(i + 4) % 5] ^ ROL64(bc[(i + 1) % 5], 1);
+            for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+        }
+        t = st[1];
+        for (int i = 0; i < 24; ++i) {
+            int j = KPIL[i];
+            bc[0] = st[j];
+            st[j] = ROL64(t, KROT[i]);
+            t = bc[0];
+        }
+        for (int j = 0; j < 25; j += 5) {
+            for (int i = 0; i < 5; ++i) bc[i] = st[j + i];
+            for (int i = 0; i < 5; ++i) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+        }
+        st[0] ^= KRC[r];
+    }
+}
+
+typedef struct {
+    u64 st[25];
+    u8 buf[136];
+    size_t fill;
+} keccak_t;
+static void keccak_init(keccak_t* k) { memset(k, 0, sizeof *k); }
+static void keccak_absorb_block(keccak_t* k, const u8* blk) {
+    for (int i = 0; i < 17; ++i) {
+        u64 lane;
+        memcpy(&lane, blk + 8 * i, 8); /* little-endian host */
+        k->st[i] ^= lane;
+    }
+    keccak_f(k->st);
+}
+static void keccak_update(keccak_t* k, const u8* d, size_t n) {
+    if (k->fill) {
+        size_t take = 136 - k->fill;
+        if (take > n) take = n;
+        memcpy(k->buf + k->fill, d, take);
+        k->fill += take;
+        d += take;
+        n -= take;
+        if (k->fill == 136) {
+            keccak_absorb_block(k, k->buf);
+            k->fill = 0;
+        }
+    }
+    while (n >= 136) {
+        keccak_absorb_block(k, d);
+        d += 136;
+        n -= 136;
+    }
+    if (n) {
+        memcpy(k->buf, d, n);
+        k->fill = n;
+    }
+}
+static void keccak_final(keccak_t* k, u8 out[32]) {
+    memset(k->buf + k->fill, 0, 136 - k->fill);
+    k->buf[k->fill] ^= 0x01;
+    k->buf[135] ^= 0x80;
+    keccak_absorb_block(k, k->buf);
+    memcpy(out, k->st, 32);
+}
+void zko_keccak256(const u8* data, size_t len, u8 out[32]) {
+    keccak_t k;
+    keccak_init(&k);
+    keccak_update(&k, data, len);
+    keccak_final(&k, out);
+}
+
+/* -------------------------------------------------------------- transcript */
+/* fiat_shamir_transcript.rs:5-30 */
+typedef struct {
+    const fctx* F;
+    keccak_t h;
+} zko_transcript;
+
+zko_transcript* zko_transcript_new(int field) {
+    zko_transcript* t = (zko_transcript*)malloc(sizeof *t);
+    t->F = &FIELDS[field];
+    keccak_init(&t->h);
+    return t;
+}
+void zko_transcript_free(zko_transcript* t) { free(t); }
+void zko_transcript_append(zko_transcript* t, const u8* d, size_t n) { keccak_update(&t->h, d, n); } /* :19-21 */
+static void tr_append_fe(zko_transcript* t, const fe* v, size_t n) { /* fq_vec_to_bytes :32-37 */
+    for (size_t i = 0; i < n; ++i) {
+        u64 c[4];
+        f_from_mont(t->F, v[i], c);
+        keccak_update(&t->h, (const u8*)c, 32);
+    }
+}
+static fe tr_challenge(zko_transcript* t) { /* :23-29 */
+    u8 dg[32];
+    keccak_final(&t->h, dg);
+    keccak_init(&t->h);
+    keccak_update(&t->h, dg, 32);
+    /* from_le_bytes_mod_order: 256-bit LE integer mod p */
+    u64 c[4];
+    memcpy(c, dg, 32);
+    return f_to_mont(t->F, c); /* f_to_mont reduces c below p first */
+}
+void zko_transcript_challenge(zko_transcript* t, u64 out[4]) {
+    fe r = tr_challenge(t);
+    f_from_mont(t->F, r, out);
+}
+
+/* --------------------------------------------------------- misc conversions */
+int zko_field_info(int field, u64 p[4], u64 r2[4], u64 one[4], u64* inv) {
+    if (field < 0 || field > 2) return -1;
+    memcpy(p, FIELDS[field].p, 32);
+    memcpy(r2, FIELDS[field].r2, 32);
+    memcpy(one, FIELDS[field].one, 32);
+    *inv = FIELDS[field].inv;
+    return 0;
+}
+void zko_to_mont(int field, const u64* in, u64* out, size_t n) {
+    const fctx* F = &FIELDS[field];
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        fe r = f_to_mont(F, in + 4 * i);
+        memcpy(out + 4 * i, r.v, 32);
+    }
+}
+void zko_from_mont(int field, const u64* in, u64* out, size_t n) {
+    const fctx* F = &FIELDS[field];
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        fe a;
+        memcpy(a.v, in + 4 * i, 32);
+        f_from_mont(F, a, out + 4 * i);
+    }
+}
+void zko_set_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n > 0 ? n : 1);
+#else
+    (void)n;
+#endif
+}
+int zko_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------- synthetic inputs (8d) */
+static inline u64 splitmix64(u64 x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    u64 z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+/* canonical entry i of synthetic table `table` (same rule in pyref.synth_entry
+ * and in the device generator) */
+static inline void synth_entry(int field, u64 seed, u64 table, u64 i, u64 out[4]) {
+    u64 base = splitmix64(seed ^ (table << 48)) + 4 * i;
+    for (int k = 0; k < 4; ++k) out[k] = splitmix64(base + (u64)k);
+    out[3] &= ((1ULL << (field == 2 ? 62 : 61)) - 1);
+}
+void zko_synth_table(int field, u64 seed, u64 table, uint32_t n_vars, u64 first, u64 stride, u64 count, u64* out) {
+    /* entries first, first+stride, ... (count of them) of the 2^n_vars table */
+    (void)n_vars;
+#pragma omp parallel for schedule(static)
+    for (u64 k = 0; k < count; ++k) synth_entry(field, seed, table, first + k * stride, out + 4 * k);
+}
+
+/* ------------------------------------------------------- MultilinearPoly */
+/* multilinear_polynomial_evaluation.rs:52-63, general `bit`; fresh allocation
+ * per call exactly as the reference's Vec::new()+push. */
+static fe* mle_fold(const fctx* F, const fe* in, uint32_t n_vars, uint32_t bit, fe r) {
+    size_t half = (size_t)1 << (n_vars - 1);
+    fe* out = (fe*)malloc(half * sizeof(fe));
+    uint32_t inv = n_vars - bit - 1;
+    size_t lowmask = ((size_t)1 << inv) - 1;
+#pragma omp parallel for schedule(static)
+    for (size_t v = 0; v < half; ++v) {
+        size_t i0 = ((v >> inv) << (inv + 1)) | (v & lowmask); /* insert_bit :158-164 */
+        size_t i1 = i0 | ((size_t)1 << inv);
+        fe a = in[i0], b = in[i1];
+        out[v] = f_add(F, a, f_mul(F, r, f_sub(F, b, a))); /* a + v*(b-a) :59 */
+    }
+    return out;
+}
+static fe* load_table(const fctx* F, const u64* canon, size_t n) {
+    fe* t = (fe*)malloc(n * sizeof(fe));
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) t[i] = f_to_mont(F, canon + 4 * i);
+    return t;
+}
+static void store_table(const fctx* F, const fe* t, size_t n, u64* canon) {
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) f_from_mont(F, t[i], canon + 4 * i);
+}
+static fe sum_range(const fctx* F, const fe* t, size_t n) {
+    fe s = f_zero();
+#ifdef _OPENMP
+    int nt = omp_get_max_threads();
+    if (nt > 1 && n >= 4096) {
+        fe* part = (fe*)calloc((size_t)nt, sizeof(fe));
+#pragma omp parallel
+        {
+            int id = omp_get_thread_num();
+            fe a = f_zero();
+#pragma omp for schedule(static)
+            for (size_t i = 0; i < n; ++i) a = f_add(F, a, t[i]);
+            part[id] = a;
+        }
+        for (int k = 0; k < nt; ++k) s = f_add(F, s, part[k]);
+        free(part);
+        return s;
+    }
+#endif
+    for (size_t i = 0; i < n; ++i) s = f_add(F, s, t[i]);
+    return s;
+}
+
+int zko_mle_partial_evaluate(int field, const u64* in, uint32_t n_vars, uint32_t bit, const u64 r[4], u64* out) {
+    const fctx* F = &FIELDS[field];
+    if (n_vars == 0 || bit >= n_vars) return -1;
+    size_t n = (size_t)1 << n_vars;
+    fe* t = load_table(F, in, n);
+    fe* o = mle_fold(F, t, n_vars, bit, f_to_mont(F, r));
+    store_table(F, o, n / 2, out);
+    free(t);
+    free(o);
+    return 0;
+}
+/* evaluate :79-91 -- clone, then n folds on variable 0 */
+static fe mle_evaluate(const fctx* F, const fe* in, uint32_t n_vars, const fe* rs) {
+    size_t n = (size_t)1 << n_vars;
+    fe* cur = (fe*)malloc(n * sizeof(fe));
+    memcpy(cur, in, n * sizeof(fe)); /* self.clone() :84 */
+    for (uint32_t k = 0; k < n_vars; ++k) {
+        fe* nx = mle_fold(F, cur, n_vars - k, 0, rs[k]);
+        free(cur);
+        cur = nx;
+    }
+    fe r = cur[0];
+    free(cur);
+    return r;
+}
+int zko_mle_evaluate(int field, const u64* in, uint32_t n_vars, const u64* rs, u64 out[4]) {
+    const fctx* F = &FIELDS[field];
+    size_t n = (size_t)1 << n_vars;
+    fe* t = load_table(F, in, n);
+    fe* r = (fe*)malloc((n_vars ? n_vars : 1) * sizeof(fe));
+    for (uint32_t k = 0; k < n_vars; ++k) r[k] = f_to_mont(F, rs + 4 * k);
+    fe v = mle_evaluate(F, t, n_vars, r);
+    f_from_mont(F, v, out);
+    free(t);
+    free(r);
+    return 0;
+}
+
+/* ------------------------------------------------------------- univariate */
+/* univariate_polynomial_dense.rs:48-74: coefficients (ascending) of the
+ * interpolant through (xs[i], ys[i]), trailing zeros trimmed (:14-18,:71).
+ * Returns the trimmed length (0..n). */
+static int uni_interpolate(const fctx* F, const fe* xs, const fe* ys, int n, fe* coeff) {
+    fe acc[8], li[8], tmp[8];
+    for (int k = 0; k < n; ++k) acc[k] = f_zero();
+    for (int i = 0; i < n; ++i) {
+        int deg = 0;
+        li[0] = f_one(F);
+        fe denom = f_one(F);
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            /* li *= (x - x_j) */
+            fe nx = f_sub(F, f_zero(), xs[j]);
+            for (int k = 0; k <= deg + 1; ++k) tmp[k] = f_zero();
+            for (int k = 0; k <= deg; ++k) {
+                tmp[k] = f_add(F, tmp[k], f_mul(F, li[k], nx));
+                tmp[k + 1] = f_add(F, tmp[k + 1], li[k]);
+            }
+            ++deg;
+            for (int k = 0; k <= deg; ++k) li[k] = tmp[k];
+            denom = f_mul(F, denom, f_sub(F, xs[i], xs[j]));
+        }
+        fe s = f_mul(F, ys[i], f_inv(F, denom));
+        for (int k = 0; k <= deg; ++k) acc[k] = f_add(F, acc[k], f_mul(F, li[k], s));
+    }
+    int len = n;
+    while (len > 0 && f_is_zero(acc[len - 1])) --len;
+    for (int k = 0; k < len; ++k) coeff[k] = acc[k];
+    return len;
+}
+static fe uni_evaluate(const fctx* F, const fe* c, int len, fe x) { /* :20-26 */
+    fe s = f_zero(), xp = f_one(F);
+    for (int i = 0; i < len; ++i) {
+        s = f_add(F, s, f_mul(F, c[i], xp));
+        xp = f_mul(F, xp, x);
+    }
+    return s;
+}
+int zko_uni_interpolate(int field, const u64* xs, const u64* ys, int n, u64* coeff) {
+    const fctx* F = &FIELDS[field];
+    if (n > 8) return -1;
+    fe x[8], y[8], c[8];
+    for (int i = 0; i < n; ++i) {
+        x[i] = f_to_mont(F, xs + 4 * i);
+        y[i] = f_to_mont(F, ys + 4 * i);
+    }
+    int len = uni_interpolate(F, x, y, n, c);
+    for (int i = 0; i < len; ++i) f_from_mont(F, c[i], coeff + 4 * i);
+    return len;
+}
+
+/* ------------------------------------------------ sum_check_protocol.rs */
+/* prove :25-52.  msgs: n_vars x 2 elements; chals: n_vars elements.
+ * absorb_table = 1 follows the reference (the whole table is hashed, :27);
+ * absorb_table = 0 is the "seeded-transcript prover core" of SURVEY F9. */
+int zko_sumcheck_prove(int field, const u64* table, uint32_t n_vars, int absorb_table,
+                       u64 claimed[4], u64* msgs, u64* chals) {
+    const fctx* F = &FIELDS[field];
+    size_t n = (size_t)1 << n_vars;
+    zko_transcript* t = zko_transcript_new(field);
+    fe* poly = load_table(F, table, n);
+    if (absorb_table) keccak_update(&t->h, (const u8*)table, n * 32); /* canonical LE bytes */
+    fe cs = sum_range(F, poly, n); /* :29 */
+    tr_append_fe(t, &cs, 1);
+    f_from_mont(F, cs, claimed);
+    fe* cur = (fe*)malloc(n * sizeof(fe));
+    memcpy(cur, poly, n * sizeof(fe)); /* polynomial.clone() :34 */
+    for (uint32_t k = 0; k < n_vars; ++k) {
+        size_t len = n >> k, mid = len / 2;
+        fe m[2] = {sum_range(F, cur, mid), sum_range(F, cur + mid, mid)}; /* :168-175 */
+        tr_append_fe(t, m, 2);
+        f_from_mont(F, m[0], msgs + 8 * k);
+        f_from_mont(F, m[1], msgs + 8 * k + 4);
+        fe r = tr_challenge(t);
+        f_from_mont(F, r, chals + 4 * k);
+        fe* nx = mle_fold(F, cur, n_vars - k, 0, r);
+        free(cur);
+        cur = nx;
+    }
+    free(cur);
+    free(poly);
+    zko_transcript_free(t);
+    return 0;
+}
+/* verify :54-84 (including the redundant per-round fold :76 when
+ * redundant_fold != 0).  Returns 1 = accepted, 0 = rejected. */
+int zko_sumcheck_verify(int field, const u64* table, uint32_t n_vars, int absorb_table, int redundant_fold,
+                        const u64 claimed[4], const u64* msgs, uint32_t n_msgs) {
+    const fctx* F = &FIELDS[field];
+    size_t n = (size_t)1 << n_vars;
+    zko_transcript* t = zko_transcript_new(field);
+    fe* poly = load_table(F, table, n);
+    if (absorb_table) keccak_update(&t->h, (const u8*)table, n * 32);
+    fe expected = f_to_mont(F, claimed);
+    tr_append_fe(t, &expected, 1);
+    fe* cur = NULL;
+    if (redundant_fold) {
+        cur = (fe*)malloc(n * sizeof(fe));
+        memcpy(cur, poly, n * sizeof(fe));
+    }
+    fe* ch = (fe*)malloc((n_msgs ? n_msgs : 1) * sizeof(fe));
+    int ok = 1;
+    for (uint32_t k = 0; k < n_msgs; ++k) {
+        fe m0 = f_to_mont(F, msgs + 8 * k), m1 = f_to_mont(F, msgs + 8 * k + 4);
+        if (!f_eq(f_add(F, m0, m1), expected)) {
+            ok = 0;
+            break;
+        }
+        fe m[2] = {m0, m1};
+        tr_append_fe(t, m, 2);
+        fe r = tr_challenge(t);
+        expected = f_add(F, m0, f_mul(F, r, f_sub(F, m1, m0)));
+        if (cur && k < n_vars) {
+            fe* nx = mle_fold(F, cur, n_vars - k, 0, r);
+            free(cur);
+            cur = nx;
+        }
+        ch[k] = r;
+    }
+    if (ok) {
+        if (n_msgs != n_vars) ok = 0; /* evaluate() panics on wrong arity (:81) */
+        else ok = f_eq(expected, mle_evaluate(F, poly, n_vars, ch));
+    }
+    free(ch);
+    free(cur);
+    free(poly);
+    zko_transcript_free(t);
+    return ok;
+}
+
+/* Composed polynomial: tables[p*d + f] (composed_polynomial.rs). */
+typedef struct {
+    int P, d;
+    uint32_t n_vars;
+    fe** t; /* P*d tables of 2^n_vars */
+} sumpoly;
+static sumpoly sp_fold(const fctx* F, const sumpoly* s, fe r) { /* SumPoly::partial_evaluate :78-86 */
+    sumpoly o = {s->P, s->d, s->n_vars - 1, (fe**)malloc(sizeof(fe*) * (size_t)(s->P * s->d))};
+    for (int k = 0; k < s->P * s->d; ++k) o.t[k] = mle_fold(F, s->t[k], s->n_vars, 0, r);
+    return o;
+}
+static void sp_free(sumpoly* s) {
+    for (int k = 0; k < s->P * s->d; ++k) free(s->t[k]);
+    free(s->t);
+}
+/* SumPoly::reduce :88-99 + .iter().sum() (sum_check_protocol.rs:161).
+ * mode 0 = compat (factors 0,1 of products 0,1 only), 1 = full. */
+static fe sp_reduce_sum(const fctx* F, const sumpoly* s, int mode) {
+    size_t n = (size_t)1 << s->n_vars;
+    int P = mode == 0 ? 2 : s->P, d = mode == 0 ? 2 : s->d;
+    fe total = f_zero();
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+        fe loc = f_zero();
+#pragma omp for schedule(static)
+        for (size_t i = 0; i < n; ++i) {
+            fe acc = f_zero();
+            for (int p = 0; p < P; ++p) {
+                fe m = s->t[p * s->d][i];
+                for (int f = 1; f < d; ++f) m = f_mul(F, m, s->t[p * s->d + f][i]);
+                acc = f_add(F, acc, m);
+            }
+            loc = f_add(F, loc, acc);
+        }
+#pragma omp critical
+        total = f_add(F, total, loc);
+    }
+#else
+    for (size_t i = 0; i < n; ++i) {
+        fe acc = f_zero();
+        for (int p = 0; p < P; ++p) {
+            fe m = s->t[p * s->d][i];
+            for (int f = 1; f < d; ++f) m = f_mul(F, m, s->t[p * s->d + f][i]);
+            acc = f_add(F, acc, m);
+        }
+        total = f_add(F, total, acc);
+    }
+#endif
+    return total;
+}
+/* get_round_partial_polynomial_proof_gkr :152-166 */
+static int sp_round_poly(const fctx* F, const sumpoly* s, int mode, fe* coeff, fe* evals_out) {
+    fe xs[8], ys[8];
+    for (int i = 0; i <= s->d; ++i) {
+        xs[i] = f_from_u64(F, (u64)i);
+        sumpoly part = sp_fold(F, s, xs[i]);
+        ys[i] = sp_reduce_sum(F, &part, mode);
+        sp_free(&part);
+        if (evals_out) evals_out[i] = ys[i];
+    }
+    return uni_interpolate(F, xs, ys, s->d + 1, coeff);
+}
+
+/* gkr_prove :86-115.  tables: P*d pointers to canonical tables (p-major).
+ * coeffs: n_vars x (d+1) slots (unused slots zero), lens: trimmed lengths,
+ * evals (optional, may be NULL): n_vars x (d+1) raw evaluations s(0..d),
+ * final_vals (optional): the P*d fully folded table values. */
+int zko_gkr_sumcheck_prove(zko_transcript* t, int mode, int P, int d, const u64* const* tables, uint32_t n_vars,
+                           u64* coeffs, int32_t* lens, u64* chals, u64* evals, u64* final_vals) {
+    const fctx* F = t->F;
+    if (d + 1 > 8 || P < 1 || d < 1) return -1;
+    if (mode == 0 && (P < 2 || d < 2)) return -2; /* reference panics: polys[1] / evaluation[1] out of range */
+    size_t n = (size_t)1 << n_vars;
+    sumpoly cur = {P, d, n_vars, (fe**)malloc(sizeof(fe*) * (size_t)(P * d))};
+    for (int k = 0; k < P * d; ++k) cur.t[k] = load_table(F, tables[k], n); /* composed_polynomial.clone() :94 */
+    for (uint32_t k = 0; k < n_vars; ++k) {
+        fe c[8], ev[8];
+        int len = sp_round_poly(F, &cur, mode, c, ev);
+        tr_append_fe(t, c, (size_t)len);
+        memset(coeffs + (size_t)k * (size_t)(d + 1) * 4, 0, (size_t)(d + 1) * 32);
+        for (int i = 0; i < len; ++i) f_from_mont(F, c[i], coeffs + ((size_t)k * (size_t)(d + 1) + (size_t)i) * 4);
+        lens[k] = len;
+        if (evals)
+            for (int i = 0; i <= d; ++i) f_from_mont(F, ev[i], evals + ((size_t)k * (size_t)(d + 1) + (size_t)i) * 4);
+        fe r = tr_challenge(t);
+        f_from_mont(F, r, chals + 4 * (size_t)k);
+        sumpoly nx = sp_fold(F, &cur, r);
+        sp_free(&cur);
+        cur = nx;
+    }
+    if (final_vals)
+        for (int k = 0; k < P * d; ++k) f_from_mont(F, cur.t[k][0], final_vals + 4 * k);
+    sp_free(&cur);
+    return 0;
+}
+/* gkr_verify :117-150.  Returns 1/0; final_claim and chals filled on accept
+ * (on reject: final_claim = 0 and one zero challenge, as :129-133). */
+int zko_gkr_sumcheck_verify(zko_transcript* t, int n_rounds, int slots, const u64* coeffs, const int32_t* lens,
+                            const u64 claimed[4], u64 final_claim[4], u64* chals) {
+    const fctx* F = t->F;
+    fe claim = f_to_mont(F, claimed);
+    for (int k = 0; k < n_rounds; ++k) {
+        fe c[8];
+        int len = lens[k];
+        for (int i = 0; i < len; ++i) c[i] = f_to_mont(F, coeffs + ((size_t)k * (size_t)slots + (size_t)i) * 4);
+        fe s0 = uni_evaluate(F, c, len, f_zero()), s1 = uni_evaluate(F, c, len, f_one(F));
+        if (!f_eq(f_add(F, s0, s1), claim)) {
+            memset(final_claim, 0, 32);
+            memset(chals, 0, 32);
+            return 0;
+        }
+        tr_append_fe(t, c, (size_t)len);
+        fe r = tr_challenge(t);
+        f_from_mont(F, r, chals + 4 * (size_t)k);
+        claim = uni_evaluate(F, c, len, r);
+    }
+    f_from_mont(F, claim, final_claim);
+    return 1;
+}
+
+/* ------------------------------------------------------ gkr_circuit.rs */
+/* Circuit::evaluate :127-143.  ops: concatenated per layer, input side first;
+ * gate i of each layer reads wires 2i, 2i+1 of the layer below (:132).
+ * out: concatenated layer outputs (canonical).  0 = Add, 1 = Mul. */
+static void circuit_eval(const fctx* F, int n_layers, const uint32_t* gates, const u8* ops, const fe* inputs,
+                         size_t n_inputs, fe** layer_out) {
+    const fe* cur = inputs;
+    size_t ncur = n_inputs, off = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        size_t G = gates[l];
+        fe* o = (fe*)malloc((G ? G : 1) * sizeof(fe));
+#pragma omp parallel for schedule(static)
+        for (size_t g = 0; g < G; ++g) {
+            if (2 * g + 1 < ncur) {
+                fe a = cur[2 * g], b = cur[2 * g + 1];
+                o[g] = ops[off + g] ? f_mul(F, a, b) : f_add(F, a, b);
+            } else {
+                o[g] = f_zero(); /* gate keeps Gate::new(0,0,op).output = 0 (:118) */
+            }
+        }
+        layer_out[l] = o;
+        cur = o;
+        ncur = G;
+        off += G;
+    }
+}
+int zko_circuit_evaluate(int field, int n_layers, const uint32_t* gates, const u8* ops, const u64* inputs,
+                         size_t n_inputs, u64* out) {
+    const fctx* F = &FIELDS[field];
+    fe* in = load_table(F, inputs, n_inputs);
+    fe** lo = (fe**)malloc(sizeof(fe*) * (size_t)n_layers);
+    circuit_eval(F, n_layers, gates, ops, in, n_inputs, lo);
+    size_t off = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        store_table(F, lo[l], gates[l], out + 4 * off);
+        off += gates[l];
+        free(lo[l]);
+    }
+    free(lo);
+    free(in);
+    return 0;
+}
+
+/* eq(r, x), variable 0 = MSB of x */
+static fe* eq_table(const fctx* F, const fe* r, int n) {
+    fe* t = (fe*)malloc(((size_t)1 << n) * sizeof(fe));
+    t[0] = f_one(F);
+    for (int k = 0; k < n; ++k) {
+        size_t len = (size_t)1 << k;
+        for (size_t i = len; i-- > 0;) {
+            fe hi = f_mul(F, t[i], r[k]);
+            t[2 * i] = f_sub(F, t[i], hi);
+            t[2 * i + 1] = hi;
+        }
+    }
+    return t;
+}
+
+/* sumcheck of sum_x X(x)*Y(x) + Z(x) (degree 2), reference wire format */
+static void sumcheck_xy_z(zko_transcript* t, fe* X, fe* Y, fe* Z, int n, u64* coeffs, int32_t* lens, u64* chals,
+                          fe* rs, fe* x_final) {
+    const fctx* F = t->F;
+    fe xs[3] = {f_zero(), f_one(F), f_from_u64(F, 2)};
+    size_t len = (size_t)1 << n;
+    for (int k = 0; k < n; ++k) {
+        size_t h = len / 2;
+        fe s0 = f_zero(), s1 = f_zero(), s2 = f_zero();
+        for (size_t i = 0; i < h; ++i) {
+            fe x0 = X[i], x1 = X[i + h], y0 = Y[i], y1 = Y[i + h], z0 = Z[i], z1 = Z[i + h];
+            fe x2 = f_sub(F, f_add(F, x1, x1), x0), y2 = f_sub(F, f_add(F, y1, y1), y0),
+               z2 = f_sub(F, f_add(F, z1, z1), z0);
+            s0 = f_add(F, s0, f_add(F, f_mul(F, x0, y0), z0));
+            s1 = f_add(F, s1, f_add(F, f_mul(F, x1, y1), z1));
+            s2 = f_add(F, s2, f_add(F, f_mul(F, x2, y2), z2));
+        }
+        fe ys[3] = {s0, s1, s2}, c[3];
+        int cl = uni_interpolate(F, xs, ys, 3, c);
+        tr_append_fe(t, c, (size_t)cl);
+        memset(coeffs + (size_t)k * 12, 0, 96);
+        for (int i = 0; i < cl; ++i) f_from_mont(F, c[i], coeffs + (size_t)k * 12 + 4 * (size_t)i);
+        lens[k] = cl;
+        fe r = tr_challenge(t);
+        rs[k] = r;
+        f_from_mont(F, r, chals + 4 * (size_t)k);
+        for (size_t i = 0; i < h; ++i) {
+            X[i] = f_add(F, X[i], f_mul(F, r, f_sub(F, X[i + h], X[i])));
+            Y[i] = f_add(F, Y[i], f_mul(F, r, f_sub(F, Y[i + h], Y[i])));
+            Z[i] = f_add(F, Z[i], f_mul(F, r, f_sub(F, Z[i + h], Z[i])));
+        }
+        len = h;
+    }
+    *x_final = X[0];
+}
+
+static int ilog2u(size_t x) {
+    int r = 0;
+    while (x > 1) {
+        x >>= 1;
+        ++r;
+    }
+    return r;
+}
+
+/* gkr_protocol::prove :31-91 (KZG :92-118 out of scope), sparse two-phase
+ * restatement (see oracle/pyref.py gkr_protocol_prove_sparse, which is asserted
+ * equal to the dense reference construction on small circuits).
+ *
+ * Outputs (canonical): w0[2]; per layer (output side first) 2*(g+1) rounds:
+ * coeffs[round][3], lens[round], chals[round]; claimed[(L-1)][2]; final[2].
+ * Returns the total number of rounds, or <0 on a malformed circuit. */
+int zko_gkr_prove(int field, int n_layers, const uint32_t* gates, const u8* ops, const u64* inputs, size_t n_inputs,
+                  u64 w0_out[8], u64* coeffs, int32_t* lens, u64* chals, u64* claimed, u64 final_out[8]) {
+    const fctx* F = &FIELDS[field];
+    /* reference-legal shape: every layer has 2x the gates of the next, output layer 1 or 2 gates */
+    if (n_layers < 1) return -1;
+    if (gates[n_layers - 1] != 1 && gates[n_layers - 1] != 2) return -2;
+    for (int l = 0; l + 1 < n_layers; ++l)
+        if (gates[l] != 2 * gates[l + 1]) return -3;
+    if (n_inputs != 2 * (size_t)gates[0]) return -4;
+
+    zko_transcript* t = zko_transcript_new(field);
+    fe* in = load_table(F, inputs, n_inputs);
+    fe** lo = (fe**)malloc(sizeof(fe*) * (size_t)n_layers);
+    circuit_eval(F, n_layers, gates, ops, in, n_inputs, lo);
+    size_t* opoff = (size_t*)malloc(sizeof(size_t) * (size_t)n_layers);
+    {
+        size_t off = 0;
+        for (int l = 0; l < n_layers; ++l) {
+            opoff[l] = off;
+            off += gates[l];
+        }
+    }
+    /* w_0, padded (:34-39); initiate_protocol :229-241 */
+    fe w0[2] = {lo[n_layers - 1][0], gates[n_layers - 1] == 2 ? lo[n_layers - 1][1] : f_zero()};
+    f_from_mont(F, w0[0], w0_out);
+    f_from_mont(F, w0[1], w0_out + 4);
+    tr_append_fe(t, w0, 2);
+    fe r0 = tr_challenge(t);
+    fe m0 = f_add(F, w0[0], f_mul(F, r0, f_sub(F, w0[1], w0[0])));
+    tr_append_fe(t, &m0, 1);
+
+    fe alpha = f_zero(), beta = f_zero();
+    fe rb[40], rc[40];
+    int nrb = 0;
+    int round_base = 0;
+    fe o1 = f_zero(), o2 = f_zero();
+    for (int idx = 0; idx < n_layers; ++idx) {
+        int l = n_layers - 1 - idx; /* circuit layer index (input side = 0) */
+        size_t G = gates[l], nw = 2 * G;
+        const u8* lops = ops + opoff[l];
+        const fe* W = (l == 0) ? in : lo[l - 1];
+        int nb = ilog2u(nw); /* bits of b (= bits of c) */
+        /* coef[g] */
+        fe* coef = (fe*)malloc(G * sizeof(fe));
+        if (idx == 0) {
+            fe e1 = r0, e0 = f_sub(F, f_one(F), r0);
+            coef[0] = e0;
+            if (G == 2) coef[1] = e1;
+        } else {
+            fe* ea = eq_table(F, rb, nrb);
+            fe* eb = eq_table(F, rc, nrb);
+            if (((size_t)1 << nrb) != G) return -5;
+            for (size_t g = 0; g < G; ++g) coef[g] = f_add(F, f_mul(F, alpha, ea[g]), f_mul(F, beta, eb[g]));
+            free(ea);
+            free(eb);
+        }
+        fe* X = (fe*)malloc(nw * sizeof(fe));
+        fe* H1 = (fe*)calloc(nw, sizeof(fe));
+        fe* HA2 = (fe*)calloc(nw, sizeof(fe));
+        memcpy(X, W, nw * sizeof(fe));
+        for (size_t g = 0; g < G; ++g) {
+            size_t b = 2 * g, c = 2 * g + 1;
+            if (lops[g] == 0) {
+                H1[b] = coef[g];
+                HA2[b] = f_mul(F, coef[g], W[c]);
+            } else {
+                H1[b] = f_mul(F, coef[g], W[c]);
+            }
+        }
+        fe u[40], v[40], Wu, Wv;
+        sumcheck_xy_z(t, X, H1, HA2, nb, coeffs + (size_t)round_base * 12, lens + round_base,
+                      chals + (size_t)round_base * 4, u, &Wu);
+        fe* eu = eq_table(F, u, nb);
+        fe* C = (fe*)calloc(nw, sizeof(fe));
+        fe* D = (fe*)calloc(nw, sizeof(fe));
+        memcpy(X, W, nw * sizeof(fe));
+        for (size_t g = 0; g < G; ++g) {
+            size_t b = 2 * g, c = 2 * g + 1;
+            fe val = f_mul(F, coef[g], eu[b]);
+            if (lops[g] == 0) {
+                C[c] = val;               /* A2(c) */
+                D[c] = f_mul(F, Wu, val); /* Wu*A2(c) */
+            } else {
+                C[c] = f_mul(F, Wu, val); /* Wu*M2(c) */
+            }
+        }
+        sumcheck_xy_z(t, X, C, D, nb, coeffs + (size_t)(round_base + nb) * 12, lens + round_base + nb,
+                      chals + (size_t)(round_base + nb) * 4, v, &Wv);
+        round_base += 2 * nb;
+        free(eu);
+        free(C);
+        free(D);
+        free(X);
+        free(H1);
+        free(HA2);
+        free(coef);
+        memcpy(rb, u, sizeof(fe) * (size_t)nb);
+        memcpy(rc, v, sizeof(fe) * (size_t)nb);
+        nrb = nb;
+        o1 = Wu;
+        o2 = Wv;
+        if (idx < n_layers - 1) { /* :80-89 */
+            tr_append_fe(t, &o1, 1);
+            alpha = tr_challenge(t);
+            tr_append_fe(t, &o2, 1);
+            beta = tr_challenge(t);
+            f_from_mont(F, o1, claimed + (size_t)idx * 8);
+            f_from_mont(F, o2, claimed + (size_t)idx * 8 + 4);
+        }
+    }
+    f_from_mont(F, o1, final_out);
+    f_from_mont(F, o2, final_out + 4);
+    for (int l = 0; l < n_layers; ++l) free(lo[l]);
+    free(lo);
+    free(opoff);
+    free(in);
+    zko_transcript_free(t);
+    return round_base;
+}
+
+/* Elementwise field ops for checking device helpers: op 0 add, 1 sub, 2 mul */
+void zko_vec_op(int field, int op, const u64* a, const u64* b, u64* out, size_t n) {
+    const fctx* F = &FIELDS[field];
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; ++i) {
+        fe x = f_to_mont(F, a + 4 * i), y = f_to_mont(F, b + 4 * i), r;
+        r = op == 0 ? f_add(F, x, y) : op == 1 ? f_sub(F, x, y) : f_mul(F, x, y);
+        f_from_mont(F, r, out + 4 * i);
+    }
+}
