@@ -1,0 +1,203 @@
+/*
+ * zkb200.h -- C ABI of libzkb200.so: the B200-native sumcheck / GKR prover
+ * engine that sits behind the crate API of obah/zk-research-implementations.
+ *
+ * The reference has no FFI of its own (pure Rust); this header IS
+ * the drop-in boundary.  Every entry point names the reference item it replaces
+ * (paths under /root/reference/).  The Rust side binds these through the thin
+ * `zkb200-sys` crate shown in INTEGRATION.md; nothing but plain pointers and
+ * sizes crosses the boundary.
+ *
+ * Conventions
+ *  - Field elements cross as `uint64_t[4]`: the little-endian limbs of the
+ *    MONTGOMERY residue (R = 2^256), i.e. byte-for-byte ark-ff 0.5's
+ *    `Fp<MontBackend<_,4>>` (`.0.0`), so a `Vec<F>` is passed as `*const u64`
+ *    with no conversion.  Canonical 32-byte little-endian encodings appear only
+ *    where the reference serialises (`fq_vec_to_bytes`,
+ *    fiat_shamir/src/fiat_shamir_transcript.rs:32-37).
+ *  - Every function returns 0 on success or a negative zkb_status; nothing
+ *    unwinds across the boundary.  The reference's panics map to error codes
+ *    (the Rust shim re-raises the same panic strings).
+ *  - A ctx owns one CUDA device, one stream and its scratch memory; it is not
+ *    internally synchronised: one ctx per host thread.  Calls return after
+ *    their (tiny) results are in host memory.
+ *  - There is NO CPU fallback: creating a ctx without a usable CUDA device
+ *    fails with ZKB_ERR_CUDA.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_transcript zkb_transcript;
+typedef uint64_t zkb_mle;  /* opaque handle of a device-resident MultilinearPoly */
+typedef uint64_t zkb_sp;   /* opaque handle of a device-resident SumPoly        */
+typedef uint64_t zkb_circ; /* opaque handle of a device-resident Circuit        */
+
+typedef enum {
+    ZKB_OK = 0,
+    ZKB_ERR_BAD_ARG = -1,
+    ZKB_ERR_NOT_POW2 = -2,        /* panic "Invalid evaluations"                    multilinear_polynomial_evaluation.rs:30 */
+    ZKB_ERR_ARITY = -3,           /* panic "Invalid number of values"               :67, :81 */
+    ZKB_ERR_LENGTH_MISMATCH = -4, /* panic "all evaluations must have same length"  composed_polynomial.rs:20 */
+    ZKB_ERR_DEGREE_MISMATCH = -5, /* panic "all product polys must have same degree" :65 */
+    ZKB_ERR_CUDA = -6,
+    ZKB_ERR_NCCL = -7,
+    ZKB_ERR_OOM = -8,
+    ZKB_ERR_UNSUPPORTED = -9,     /* shape outside the instantiated kernels (degree > 4, > 16 tables) */
+    ZKB_ERR_COMPAT_SHAPE = -10,   /* compat mode needs >= 2 products of >= 2 factors: the reference indexes
+                                     polys[1] / evaluation[1] and panics otherwise (composed_polynomial.rs:53,90) */
+    ZKB_ERR_CIRCUIT_SHAPE = -11   /* layer sizes the reference's fixed wiring cannot express */
+} zkb_status;
+
+enum { ZKB_FIELD_BN254_FR = 0, ZKB_FIELD_BN254_FQ = 1, ZKB_FIELD_BLS12_381_FR = 2 };
+/* SumPoly::reduce semantics: COMPAT reproduces the reference exactly (only factors 0,1 of products 0,1
+ * contribute, composed_polynomial.rs:52-54,88-99); FULL is the true sum of products. */
+enum { ZKB_MODE_COMPAT = 0, ZKB_MODE_FULL = 1 };
+enum { ZKB_OP_ADD = 0, ZKB_OP_MUL = 1, ZKB_OP_SUB = 2 }; /* Operation, multilinear_polynomial_evaluation.rs:4-17 */
+
+const char* zkb_strerror(int32_t status);
+const char* zkb_version(void);
+
+/* ------------------------------------------------------------------ context */
+int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx** out);
+int32_t zkb_ctx_destroy(zkb_ctx* ctx);
+const char* zkb_ctx_last_error(const zkb_ctx* ctx);
+/* The ctx's CUDA stream (cudaStream_t) for callers that time with CUDA events. */
+void* zkb_ctx_stream(const zkb_ctx* ctx);
+/* Number of this library's kernels launched through ctx so far (bench.py's `gpu_launches`). */
+uint64_t zkb_ctx_launch_count(const zkb_ctx* ctx);
+int32_t zkb_ctx_sync(zkb_ctx* ctx);
+
+/* Multi-GPU (one process per GPU).  The table is sharded on LOW index bits: rank j of 2^g holds entries
+ * i with i mod 2^g == j, so both halves of every bound variable stay local.  Per round the
+ * (d+1) partial sums are combined with one ncclAllReduce over widened limbs.  `unique_id` is the
+ * 128-byte ncclUniqueId produced by zkb_comm_unique_id on rank 0 and broadcast by the launcher. */
+int32_t zkb_comm_unique_id(uint8_t out[128]);
+int32_t zkb_ctx_comm_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8_t unique_id[128]);
+int32_t zkb_ctx_set_gather_threshold(zkb_ctx* ctx, uint32_t log2_local_entries);
+
+/* --------------------------------------------- MultilinearPoly (device table) */
+/* MultilinearPoly::new (multilinear_polynomial_evaluation.rs:26-37): `len` must be a power of two. */
+int32_t zkb_mle_upload(zkb_ctx* ctx, const uint64_t* aos_mont, uint64_t len, zkb_mle* out);
+/* Rank-local shard of a host table that every rank holds in full (strided gather on upload). */
+int32_t zkb_mle_upload_shard(zkb_ctx* ctx, const uint64_t* aos_mont_full, uint64_t len_full, zkb_mle* out);
+/* Synthetic table generated on the device (bench inputs).  With a communicator attached the
+ * call creates this rank's shard of the 2^n_vars-entry global table. */
+int32_t zkb_mle_generate(zkb_ctx* ctx, uint64_t seed, uint64_t table_id, uint32_t n_vars, zkb_mle* out);
+int32_t zkb_mle_download(zkb_ctx* ctx, zkb_mle m, uint64_t* aos_mont);
+/* canonical 32-byte LE encodings, the bytes fq_vec_to_bytes would produce */
+int32_t zkb_mle_download_canonical(zkb_ctx* ctx, zkb_mle m, uint8_t* bytes);
+int32_t zkb_mle_clone(zkb_ctx* ctx, zkb_mle m, zkb_mle* out);
+int32_t zkb_mle_free(zkb_ctx* ctx, zkb_mle m);
+int32_t zkb_mle_num_vars(zkb_ctx* ctx, zkb_mle m, uint32_t* n_vars); /* local shard size */
+/* partial_evaluate(bit, value) :52-63 */
+int32_t zkb_mle_partial_evaluate(zkb_ctx* ctx, zkb_mle in, uint32_t bit, const uint64_t value[4], zkb_mle* out);
+/* multi_partial_evaluate(values) :65-77 */
+int32_t zkb_mle_multi_partial_evaluate(zkb_ctx* ctx, zkb_mle in, const uint64_t* values, uint32_t k, zkb_mle* out);
+/* evaluate(values) :79-91 */
+int32_t zkb_mle_evaluate(zkb_ctx* ctx, zkb_mle m, const uint64_t* values, uint32_t k, uint64_t out[4]);
+/* [sum of low half, sum of high half]: get_round_partial_polynomial_proof, sum_check_protocol.rs:168-175 */
+int32_t zkb_mle_sum_halves(zkb_ctx* ctx, zkb_mle m, uint64_t out[8]);
+/* scale :93-97 */
+int32_t zkb_mle_scale(zkb_ctx* ctx, zkb_mle in, const uint64_t value[4], zkb_mle* out);
+/* impl Add / Mul / Sub :113-156 (op = ZKB_OP_*) */
+int32_t zkb_mle_binary(zkb_ctx* ctx, zkb_mle a, zkb_mle b, int32_t op, zkb_mle* out);
+/* tensor_add_mul_polynomials :99-111 (op = ZKB_OP_ADD | ZKB_OP_MUL) */
+int32_t zkb_mle_tensor(zkb_ctx* ctx, zkb_mle a, zkb_mle b, int32_t op, zkb_mle* out);
+
+/* ------------------------------------------ ProductPoly / SumPoly (composed) */
+/* SumPoly::new over ProductPoly::new (composed_polynomial.rs:16-29,62-69): `tables` holds n_products *
+ * degree handles, product-major.  The SumPoly takes its own copy of nothing: it references the tables
+ * read-only and folds into private scratch, so the caller's tables stay intact (the reference clones). */
+int32_t zkb_sumpoly_create(zkb_ctx* ctx, const zkb_mle* tables, uint32_t n_products, uint32_t degree, zkb_sp* out);
+int32_t zkb_sumpoly_free(zkb_ctx* ctx, zkb_sp sp);
+/* ProductPoly/SumPoly::evaluate (:31-36, :71-76): sum of products of the factors' evaluations. */
+int32_t zkb_sumpoly_evaluate(zkb_ctx* ctx, zkb_sp sp, const uint64_t* values, uint32_t k, uint64_t out[4]);
+/* Step API of the composed sumcheck (the body of gkr_prove's loop, sum_check_protocol.rs:96-108):
+ *   round_evals : s(0..d) of the current round          (get_round_partial_polynomial_proof_gkr :152-166)
+ *   bind_and_next: fold every table with r and return the next round's s(0..d) in ONE pass over HBM
+ *   final_values: the n_products*degree fully bound table values after the last bind                */
+int32_t zkb_sc_round_evals(zkb_ctx* ctx, zkb_sp sp, uint64_t* evals /* (d+1)*4 */);
+int32_t zkb_sc_bind_and_next(zkb_ctx* ctx, zkb_sp sp, const uint64_t r[4], uint64_t* evals /* (d+1)*4, NULL on the last bind */);
+int32_t zkb_sc_final_values(zkb_ctx* ctx, zkb_sp sp, uint64_t* values /* T*4 */);
+
+/* ------------------------------------------------ Transcript (host, Keccak-256) */
+/* fiat_shamir/src/fiat_shamir_transcript.rs:5-37 */
+int32_t zkb_transcript_new(int32_t field_id, zkb_transcript** out);
+int32_t zkb_transcript_free(zkb_transcript* t);
+int32_t zkb_transcript_append(zkb_transcript* t, const uint8_t* bytes, size_t len);
+int32_t zkb_transcript_append_elements(zkb_transcript* t, const uint64_t* mont, size_t n); /* append(&fq_vec_to_bytes(..)) */
+int32_t zkb_transcript_challenge(zkb_transcript* t, uint64_t out_mont[4]);
+int32_t zkb_keccak256(const uint8_t* bytes, size_t len, uint8_t out[32]);
+
+/* ------------------------------------------------ UnivariatePoly (host, tiny) */
+/* interpolate + trim (univariate_polynomial_dense.rs:48-74,14-18): returns the trimmed length in *len. */
+int32_t zkb_uni_interpolate(int32_t field_id, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint64_t* coeffs,
+                            uint32_t* len);
+/* evaluate :20-26 */
+int32_t zkb_uni_evaluate(int32_t field_id, const uint64_t* coeffs, uint32_t len, const uint64_t x[4], uint64_t out[4]);
+
+/* -------------------------------------------------------- sum_check_protocol */
+/* prove (sum_check_protocol.rs:25-52).  msgs: n_vars x 2 elements; challenges: n_vars elements (not part
+ * of the reference's Proof, returned for callers that want them; may be NULL).
+ * flags bit 0: absorb the whole table into the transcript first, as the reference does (:27).  Clear it
+ * for the "seeded-transcript prover core" (SURVEY F9); the reference-faithful setting is 1. */
+int32_t zkb_sumcheck_prove(zkb_ctx* ctx, zkb_mle poly, uint32_t flags, uint64_t claimed_sum[4], uint64_t* msgs,
+                           uint64_t* challenges);
+/* verify (:54-84): *accepted = 1/0. */
+int32_t zkb_sumcheck_verify(zkb_ctx* ctx, zkb_mle poly, uint32_t flags, const uint64_t claimed_sum[4],
+                            const uint64_t* msgs, uint32_t n_msgs, int32_t* accepted);
+/* gkr_prove (:86-115).  coeffs: n_vars x (d+1) slots, lens[k] = trimmed length of round k's coefficient
+ * vector (possibly 0); challenges: n_vars; final_values (may be NULL): the T bound table values. */
+int32_t zkb_gkr_sumcheck_prove(zkb_ctx* ctx, zkb_transcript* t, const uint64_t claimed_sum[4], zkb_sp sp,
+                               uint64_t* coeffs, int32_t* lens, uint64_t* challenges, uint64_t* final_values);
+/* gkr_verify (:117-150).  slots = stride (in elements) between rounds in coeffs.  On rejection
+ * final_claim = 0 and challenges[0] = 0 (:129-133). */
+int32_t zkb_gkr_sumcheck_verify(zkb_transcript* t, uint32_t n_rounds, uint32_t slots, const uint64_t* coeffs,
+                                const int32_t* lens, const uint64_t claimed_sum[4], int32_t* accepted,
+                                uint64_t final_claim[4], uint64_t* challenges);
+
+/* --------------------------------------------------------- gkr_circuit / gkr */
+/* Circuit::new (gkr_circuit.rs:113-125): layers listed input side first; gate i of a layer reads wires
+ * 2i, 2i+1 of the layer below (:76-78,132).  ops: concatenated ZKB_OP_ADD/ZKB_OP_MUL bytes. */
+int32_t zkb_circuit_create(zkb_ctx* ctx, uint32_t n_layers, const uint32_t* gates_per_layer, const uint8_t* ops,
+                           zkb_circ* out);
+int32_t zkb_circuit_free(zkb_ctx* ctx, zkb_circ c);
+/* Circuit::evaluate (:127-143): layer outputs stay on the device; `outputs` (may be NULL) receives them
+ * concatenated, input-side layer first. */
+int32_t zkb_circuit_evaluate(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, uint64_t n_inputs,
+                             uint64_t* outputs_mont);
+/* gkr_protocol::prove (gkr_protocol.rs:31-91; the KZG input opening :92-118 is out of scope).
+ * Outputs: w0[2] (output_poly); per layer (output side first) 2*(log2(2G)) rounds of 3 coefficient slots
+ * with trimmed lengths; claimed[(L-1)][2] (claimed_evaluations); final_openings[2] = the input MLE at
+ * (r_b, r_c) -- what the input-layer commitment opens; challenges (may be NULL).  *n_rounds receives the
+ * total number of sumcheck rounds. */
+int32_t zkb_gkr_prove(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, uint64_t n_inputs, uint64_t w0[8],
+                      uint64_t* coeffs, int32_t* lens, uint64_t* challenges, uint64_t* claimed, uint64_t final_openings[8],
+                      uint32_t* n_rounds);
+/* gkr_protocol::verify (:128-227) with the input opening replaced by a direct evaluation of the input
+ * MLE on the device and the wiring predicates evaluated in O(G) through eq tables. */
+int32_t zkb_gkr_verify(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, uint64_t n_inputs, const uint64_t w0[8],
+                       const uint64_t* coeffs, const int32_t* lens, const uint64_t* claimed, const uint64_t final_openings[8],
+                       int32_t* accepted);
+uint32_t zkb_gkr_total_rounds(uint32_t n_layers, const uint32_t* gates_per_layer);
+
+/* ------------------------------------------------------------ microbenchmarks */
+/* Device-timed multiplier throughput (fills the IMAD-roofline denominator).
+ * variant: 0/1 = IMAD.WIDE multiplier with 1/2 independent chains per thread, 2/3 = 32-bit lo/hi
+ * multiplier.  Returns modmuls per second. */
+int32_t zkb_bench_modmul(zkb_ctx* ctx, int32_t variant, uint32_t iters, double* modmuls_per_s);
+/* mode 0 IMAD, 1 IMAD.HI, 2 mad.wide, 3 IMAD.WIDE.X carry chain; returns multiply instructions/s */
+int32_t zkb_bench_imad(zkb_ctx* ctx, int32_t mode, uint32_t iters, double* ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

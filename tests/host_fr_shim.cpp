@@ -1,0 +1,31 @@
+// Host build of zk-research-implementations_b200/csrc/fr.cuh (carry flag emulated) so the
+// exact limb algorithms the kernels run can be checked on a machine with no GPU.
+#include <cstddef>
+#include <cstring>
+#include "fr.cuh"
+using namespace zkb;
+
+template <class F>
+static void run(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        Fe x, y, r;
+        memcpy(x.l, a + 8 * i, 32);
+        memcpy(y.l, b + 8 * i, 32);
+        switch (op) {
+            case 0: r = Field<F>::add(x, y); break;
+            case 1: r = Field<F>::sub(x, y); break;
+            case 2: r = Field<F>::mul(x, y); break;
+            case 3: r = Field<F>::mul_split(x, y); break;
+            case 4: r = Field<F>::to_mont(x); break;
+            case 5: r = Field<F>::from_mont(x); break;
+            case 6: r = Field<F>::fold(x, y, Field<F>::to_mont(y)); break;
+            default: r = Field<F>::zero();
+        }
+        memcpy(out + 8 * i, r.l, 32);
+    }
+}
+extern "C" void host_fr_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+    if (field == 0) run<Bn254Fr>(op, a, b, out, n);
+    else if (field == 1) run<Bn254Fq>(op, a, b, out, n);
+    else run<Bls12381Fr>(op, a, b, out, n);
+}

@@ -1,0 +1,100 @@
+// field_impl.cuh -- included once per field TU with ZKB_FIELD / ZKB_FIELD_FN set.
+#include "launch.h"
+
+namespace zkb {
+namespace {
+typedef ZKB_FIELD FT;
+
+// (kind, D, npts) instantiations: PROD(1,2) plain sumcheck; PROD(2,3) the GKR /
+// compat shape; PROD(2,4), PROD(2,5) compat with 3 or 4 declared factors
+// (reference quirk: only factors 0,1 multiply); PROD(3,4), PROD(4,5)
+// full products; XYZ(2,3) two-phase GKR.
+#define ZKB_SC_CASES(X) \
+    X(KIND_PROD, 1, 2) X(KIND_PROD, 2, 3) X(KIND_PROD, 2, 4) X(KIND_PROD, 2, 5) X(KIND_PROD, 3, 4) X(KIND_PROD, 4, 5) \
+    X(KIND_XYZ, 2, 3)
+
+bool l_sc_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { k_sc_eval<FT, K, DD, NP><<<grid, BLOCK, 0, s>>>(a); return true; }
+    ZKB_SC_CASES(X)
+#undef X
+    return false;
+}
+bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { k_sc_fold_eval<FT, K, DD, NP><<<grid, BLOCK, 0, s>>>(a); return true; }
+    ZKB_SC_CASES(X)
+#undef X
+    return false;
+}
+int l_sc_occupancy(int fused, int kind, int D, int npts) {
+    int nb = 0;
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { \
+        if (fused) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_fold_eval<FT, K, DD, NP>, BLOCK, 0); \
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_eval<FT, K, DD, NP>, BLOCK, 0); \
+        return nb; \
+    }
+    ZKB_SC_CASES(X)
+#undef X
+    return 0;
+}
+void l_fold_tables(const FoldTablesArgs& a, int grid, cudaStream_t s) { k_fold_tables<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const Fe& r, int grid, cudaStream_t s) {
+    k_fold<FT><<<grid, BLOCK, 0, s>>>(in, out, n_out, shift, r);
+}
+void l_aos_to_planar(const void* aos, TabRef out, uint64_t n, uint64_t first, uint64_t stride, int conv, int grid, cudaStream_t s) {
+    k_aos_to_planar<FT><<<grid, BLOCK, 0, s>>>((const uint4*)aos, out, n, first, stride, conv);
+}
+void l_planar_to_aos(TabRef in, void* aos, uint64_t n, int conv, int grid, cudaStream_t s) {
+    k_planar_to_aos<FT><<<grid, BLOCK, 0, s>>>(in, (uint4*)aos, n, conv);
+}
+void l_interleave(TabRef g, uint64_t pitch, TabRef out, uint64_t n_local, uint32_t log2g, int grid, cudaStream_t s) {
+    k_interleave_shards<FT><<<grid, BLOCK, 0, s>>>(g, pitch, out, n_local, log2g);
+}
+void l_generate(TabRef out, uint64_t n, uint64_t seed, uint64_t table, uint64_t first, uint64_t stride, int grid, cudaStream_t s) {
+    k_generate<FT><<<grid, BLOCK, 0, s>>>(out, n, seed, table, first, stride);
+}
+void l_vec_op(TabRef x, TabRef y, TabRef out, uint64_t n, int op, int grid, cudaStream_t s) {
+    k_vec_op<FT><<<grid, BLOCK, 0, s>>>(x, y, out, n, op);
+}
+void l_axpby(TabRef x, TabRef y, TabRef out, uint64_t n, const Fe& al, const Fe& be, int grid, cudaStream_t s) {
+    k_axpby<FT><<<grid, BLOCK, 0, s>>>(x, y, out, n, al, be);
+}
+void l_tensor(TabRef x, TabRef y, TabRef out, uint64_t na, uint64_t nb, int op, int grid, cudaStream_t s) {
+    k_tensor<FT><<<grid, BLOCK, 0, s>>>(x, y, out, na, nb, op);
+}
+void l_layer_eval(TabRef in, TabRef out, const uint8_t* ops, uint64_t n_gates, int grid, cudaStream_t s) {
+    k_layer_eval<FT><<<grid, BLOCK, 0, s>>>(in, out, ops, n_gates);
+}
+void l_eq_split(const ChalList& r, int n, int n_hi, TabRef hi, TabRef lo, int grid, cudaStream_t s) {
+    k_eq_split<FT><<<grid, BLOCK, 0, s>>>(r, n, n_hi, hi, lo);
+}
+void l_gkr_phase1(const GkrP1Args& a, int grid, cudaStream_t s) { k_gkr_phase1<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_gkr_phase2(const GkrP2Args& a, int grid, cudaStream_t s) { k_gkr_phase2<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_gkr_wiring(const GkrWiringArgs& a, int grid, cudaStream_t s) { k_gkr_wiring<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_bench_mul(int variant, Fe* out, uint32_t iters, int grid, cudaStream_t s) {
+    Fe seed = Field<FT>::r2();
+    if (variant == 0) k_bench_mul<FT, 1, false><<<grid, BLOCK, 0, s>>>(out, iters, seed);
+    else if (variant == 1) k_bench_mul<FT, 2, false><<<grid, BLOCK, 0, s>>>(out, iters, seed);
+    else if (variant == 2) k_bench_mul<FT, 1, true><<<grid, BLOCK, 0, s>>>(out, iters, seed);
+    else k_bench_mul<FT, 2, true><<<grid, BLOCK, 0, s>>>(out, iters, seed);
+}
+void h_add(const Fe& a, const Fe& b, Fe& r) { r = Field<FT>::add(a, b); }
+void h_sub(const Fe& a, const Fe& b, Fe& r) { r = Field<FT>::sub(a, b); }
+void h_mul(const Fe& a, const Fe& b, Fe& r) { r = Field<FT>::mul(a, b); }
+void h_to_mont(const Fe& a, Fe& r) { r = Field<FT>::to_mont(a); }
+void h_from_mont(const Fe& a, Fe& r) { r = Field<FT>::from_mont(a); }
+void h_modulus(Fe& p) {
+    for (int i = 0; i < 8; ++i) p.l[i] = FT::P(i);
+}
+
+const FieldKernels TABLE = {
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_occupancy, l_fold_tables, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_eq_split,     l_gkr_phase1,
+    l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
+};
+}  // namespace
+
+const FieldKernels* ZKB_FIELD_FN() { return &TABLE; }
+}  // namespace zkb

@@ -1,0 +1,342 @@
+// fr.cuh -- 256-bit prime-field arithmetic for sm_100a: 8 x 32-bit limbs,
+// Montgomery form with R = 2^256 (bit-compatible with ark-ff's
+// Fp<MontBackend<_,4>>: the same residues, the same little-endian limb order,
+// so a host `Vec<F>` uploads without conversion).
+//
+// Replaces (as the arithmetic under every table kernel) the ark-ff operators
+// the reference uses through `F: PrimeField`
+// (multilinear_polynomial/src/multilinear_polynomial_evaluation.rs:13-14,59,94).
+//
+// The multiplier is a row-wise (CIOS) Montgomery product with the partial
+// products kept in two interleaved accumulators ("even"/"odd" limb columns) so
+// that every 32x32->64 product lands on a 64-bit-aligned limb pair and ptxas
+// can fuse each `mad.lo.cc / madc.hi.cc` pair into ONE `IMAD.WIDE.U32.X` with a
+// predicate carry: 136 wide multiply-accumulates per product, no carry-save
+// shuffling.  The same source compiles for the host with the carry flag
+// emulated, which is how the limb algorithm is unit-tested without a GPU
+// (tests/test_fr_host.py).
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ZK_HD __host__ __device__ __forceinline__
+#define ZK_D __device__ __forceinline__
+#else
+#define ZK_HD inline
+#define ZK_D inline
+#endif
+
+namespace zkb {
+
+// ---------------------------------------------------------------- carry ops
+// Device: PTX carry-flag instructions (asm volatile keeps their order).
+// Host: the flag is a thread-local variable.
+#if defined(__CUDA_ARCH__)
+#define ZK_ASM asm volatile
+ZK_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; ZK_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZK_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZK_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZK_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; ZK_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+ZK_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+ZK_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// 32x32->64 multiply + 64-bit add with carry: each block is ONE IMAD.WIDE.U32(.X)
+// with a predicate carry after ptxas (checked with cuobjdump -sass).
+ZK_D uint64_t mul_wide(uint32_t a, uint32_t b) { uint64_t r; ZK_ASM("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+ZK_D uint64_t madw_cc(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; ZK_ASM("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %1, %2;\n\tadd.cc.u64 %0, %3, p;\n\t}" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+ZK_D uint64_t madwc_cc(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; ZK_ASM("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %1, %2;\n\taddc.cc.u64 %0, %3, p;\n\t}" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+ZK_D uint64_t madwc(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; ZK_ASM("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %1, %2;\n\taddc.u64 %0, %3, p;\n\t}" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+#else
+namespace detail { inline uint32_t& cf() { static thread_local uint32_t f = 0; return f; } }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; detail::cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + detail::cf(); detail::cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + detail::cf(); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; detail::cf() = (uint32_t)((t >> 32) & 1); return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - detail::cf(); detail::cf() = (uint32_t)((t >> 32) & 1); return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - detail::cf(); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc((uint32_t)((uint64_t)a * b), c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc((uint32_t)((uint64_t)a * b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc((uint32_t)(((uint64_t)a * b) >> 32), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc((uint32_t)(((uint64_t)a * b) >> 32), c); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint64_t mul_wide(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
+inline uint64_t madw_cc(uint32_t a, uint32_t b, uint64_t c) { unsigned __int128 t = (unsigned __int128)c + (uint64_t)a * b; detail::cf() = (uint32_t)(t >> 64); return (uint64_t)t; }
+inline uint64_t madwc_cc(uint32_t a, uint32_t b, uint64_t c) { unsigned __int128 t = (unsigned __int128)c + (uint64_t)a * b + detail::cf(); detail::cf() = (uint32_t)(t >> 64); return (uint64_t)t; }
+inline uint64_t madwc(uint32_t a, uint32_t b, uint64_t c) { return c + (uint64_t)a * b + detail::cf(); }
+#endif
+ZK_HD uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+ZK_HD uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
+ZK_HD uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// ------------------------------------------------------------ field params
+// SURVEY.md App. B.  P = modulus, R2 = R^2 mod p, ONE = R mod p,
+// INV = -p^{-1} mod 2^32.  All as 8 x u32, little-endian.
+struct Bn254Fr {
+    static constexpr int ID = 0;
+    static constexpr uint32_t INV = 0xefffffffu;
+    ZK_HD static constexpr uint32_t P(int i) {
+        constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    ZK_HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return v[i];
+    }
+    ZK_HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+};
+struct Bn254Fq {
+    static constexpr int ID = 1;
+    static constexpr uint32_t INV = 0xe4866389u;
+    ZK_HD static constexpr uint32_t P(int i) {
+        constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    ZK_HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+    ZK_HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+};
+struct Bls12381Fr {
+    static constexpr int ID = 2;
+    static constexpr uint32_t INV = 0xffffffffu;
+    ZK_HD static constexpr uint32_t P(int i) {
+        constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return v[i];
+    }
+    ZK_HD static constexpr uint32_t R2(int i) {
+        constexpr uint32_t v[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return v[i];
+    }
+    ZK_HD static constexpr uint32_t ONE(int i) {
+        constexpr uint32_t v[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return v[i];
+    }
+};
+
+// ------------------------------------------------------------ the element
+struct alignas(16) Fe {
+    uint32_t l[8];
+};
+
+template <class F>
+struct Field {
+    ZK_HD static Fe zero() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = 0;
+        return r;
+    }
+    ZK_HD static Fe one() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = F::ONE(i);
+        return r;
+    }
+    ZK_HD static Fe r2() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = F::R2(i);
+        return r;
+    }
+    ZK_HD static bool is_zero(const Fe& a) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o |= a.l[i];
+        return o == 0;
+    }
+
+    // r = a - p if a >= p else a   (a < 2p)
+    ZK_HD static Fe reduce_once(const Fe& a) {
+        Fe t;
+        t.l[0] = sub_cc(a.l[0], F::P(0));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t.l[i] = subc_cc(a.l[i], F::P(i));
+        uint32_t borrow = subc(0u, 0u);  // 0xffffffff if a < p
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = borrow ? a.l[i] : t.l[i];
+        return r;
+    }
+    // a + b mod p (a, b < p; 2p < 2^256 for all three moduli so no carry-out)
+    ZK_HD static Fe add(const Fe& a, const Fe& b) {
+        Fe s;
+        s.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) s.l[i] = addc_cc(a.l[i], b.l[i]);
+        s.l[7] = addc(a.l[7], b.l[7]);
+        return reduce_once(s);
+    }
+    // a - b mod p
+    ZK_HD static Fe sub(const Fe& a, const Fe& b) {
+        Fe d;
+        d.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) d.l[i] = subc_cc(a.l[i], b.l[i]);
+        uint32_t m = subc(0u, 0u);  // all ones if a < b
+        Fe r;
+        r.l[0] = add_cc(d.l[0], F::P(0) & m);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = addc_cc(d.l[i], F::P(i) & m);
+        r.l[7] = addc(d.l[7], F::P(7) & m);
+        return r;
+    }
+    ZK_HD static Fe neg(const Fe& a) { return sub(zero(), a); }
+    // 2a mod p
+    ZK_HD static Fe dbl(const Fe& a) { return add(a, a); }
+
+    // ---- Montgomery product, a*b*R^-1 mod p, fully reduced ----------------
+    // acc[0..7] += x[0,2,4,6] * y at 64-bit aligned limb pairs, one carry chain;
+    // leaves the carry flag set for the caller.
+    ZK_HD static void cmad(uint32_t* acc, const uint32_t* x, uint32_t y) {
+        acc[0] = mad_lo_cc(x[0], y, acc[0]);
+        acc[1] = madc_hi_cc(x[0], y, acc[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            acc[j] = madc_lo_cc(x[j], y, acc[j]);
+            acc[j + 1] = madc_hi_cc(x[j], y, acc[j + 1]);
+        }
+    }
+    // same with the modulus' limbs (compile-time constants -> immediates)
+    template <int OFF>
+    ZK_HD static void cmad_p(uint32_t* acc, uint32_t y) {
+        acc[0] = mad_lo_cc(F::P(OFF), y, acc[0]);
+        acc[1] = madc_hi_cc(F::P(OFF), y, acc[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            acc[j] = madc_lo_cc(F::P(OFF + j), y, acc[j]);
+            acc[j + 1] = madc_hi_cc(F::P(OFF + j), y, acc[j + 1]);
+        }
+    }
+    // One CIOS row.  On entry T = ev + (od << 32) where od[] is the PREVIOUS
+    // row's "even" accumulator whose limb 0 is zero, limb 1 is a stray limb to
+    // be folded into ev[0], and limbs 2..7 are the shifted-down content.
+    ZK_HD static void row(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi, bool first) {
+        if (first) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                od[j] = mul_lo(a[j + 1], bi);
+                od[j + 1] = mul_hi(a[j + 1], bi);
+                ev[j] = mul_lo(a[j], bi);
+                ev[j + 1] = mul_hi(a[j], bi);
+            }
+        } else {
+            ev[0] = add_cc(ev[0], od[1]);
+            // od = (od >> 64) + a_odd * bi (+ carry of the stray-limb add)
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) {
+                od[j] = madc_lo_cc(a[j + 1], bi, od[j + 2]);
+                od[j + 1] = madc_hi_cc(a[j + 1], bi, od[j + 3]);
+            }
+            od[6] = madc_lo_cc(a[7], bi, 0u);
+            od[7] = madc_hi(a[7], bi, 0u);
+            cmad(ev, a, bi);
+            od[7] = addc(od[7], 0u);
+        }
+        uint32_t m = mul_lo(ev[0], F::INV);
+        cmad_p<1>(od, m);
+        cmad_p<0>(ev, m);
+        od[7] = addc(od[7], 0u);
+    }
+    // 32-bit-limb variant (kept for the IMAD vs IMAD.WIDE microbenchmark)
+    ZK_HD static Fe mul_split(const Fe& a, const Fe& b) {
+        uint32_t ev[8], od[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            row(ev, od, a.l, b.l[i], i == 0);
+            row(od, ev, a.l, b.l[i + 1], false);
+        }
+        // result = ev + (od >> 32)
+        Fe r;
+        r.l[0] = add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = addc_cc(ev[i], od[i + 1]);
+        r.l[7] = addc(ev[7], 0u);
+        return reduce_once(r);
+    }
+    // ---- the same rows on 4 x u64 accumulators (default multiplier) ---------
+    // ev/od hold limb PAIRS: ev[k] = limbs (2k, 2k+1) of the even column sum,
+    // od[k] = limbs (2k+1, 2k+2) of the odd one (T = ev + (od << 32)).
+    template <int OFF>
+    ZK_HD static void cmadw_p(uint64_t* acc, uint32_t m) {
+        acc[0] = madw_cc(F::P(OFF), m, acc[0]);
+        acc[1] = madwc_cc(F::P(OFF + 2), m, acc[1]);
+        acc[2] = madwc_cc(F::P(OFF + 4), m, acc[2]);
+        acc[3] = madwc_cc(F::P(OFF + 6), m, acc[3]);
+    }
+    ZK_HD static void roww(uint64_t* ev, uint64_t* od, const uint32_t* a, uint32_t bi, bool first) {
+        if (first) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                od[k] = mul_wide(a[2 * k + 1], bi);
+                ev[k] = mul_wide(a[2 * k], bi);
+            }
+        } else {
+            // od is the previous row's even accumulator: limb 0 is zero, limb 1
+            // (hi32(od[0])) is the stray limb; its carry feeds the od chain.
+            uint32_t e0 = add_cc(lo32(ev[0]), hi32(od[0]));
+            od[0] = madwc_cc(a[1], bi, od[1]);
+            od[1] = madwc_cc(a[3], bi, od[2]);
+            od[2] = madwc_cc(a[5], bi, od[3]);
+            od[3] = madwc(a[7], bi, 0ull);
+            ev[0] = pack64(e0, hi32(ev[0]));
+            ev[0] = madw_cc(a[0], bi, ev[0]);
+            ev[1] = madwc_cc(a[2], bi, ev[1]);
+            ev[2] = madwc_cc(a[4], bi, ev[2]);
+            ev[3] = madwc_cc(a[6], bi, ev[3]);
+            od[3] = pack64(lo32(od[3]), addc(hi32(od[3]), 0u));
+        }
+        uint32_t m = mul_lo(lo32(ev[0]), F::INV);
+        cmadw_p<1>(od, m);  // carry-out provably zero: od << 32 <= T < 2^288
+        cmadw_p<0>(ev, m);
+        od[3] = pack64(lo32(od[3]), addc(hi32(od[3]), 0u));
+    }
+    ZK_HD static Fe mul(const Fe& a, const Fe& b) {
+        uint64_t ev[4], od[4];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            roww(ev, od, a.l, b.l[i], i == 0);
+            roww(od, ev, a.l, b.l[i + 1], false);
+        }
+        Fe r;  // ev + (od >> 32); od's limb 0 is zero
+        r.l[0] = add_cc(lo32(ev[0]), hi32(od[0]));
+        r.l[1] = addc_cc(hi32(ev[0]), lo32(od[1]));
+        r.l[2] = addc_cc(lo32(ev[1]), hi32(od[1]));
+        r.l[3] = addc_cc(hi32(ev[1]), lo32(od[2]));
+        r.l[4] = addc_cc(lo32(ev[2]), hi32(od[2]));
+        r.l[5] = addc_cc(hi32(ev[2]), lo32(od[3]));
+        r.l[6] = addc_cc(lo32(ev[3]), hi32(od[3]));
+        r.l[7] = addc(hi32(ev[3]), 0u);
+        return reduce_once(r);
+    }
+    ZK_HD static Fe sqr(const Fe& a) { return mul(a, a); }
+
+    ZK_HD static Fe to_mont(const Fe& canon) { return mul(canon, r2()); }
+    ZK_HD static Fe from_mont(const Fe& m) {
+        Fe o = zero();
+        o.l[0] = 1;
+        return mul(m, o);
+    }
+    // small unsigned integer -> Montgomery form
+    ZK_HD static Fe from_u32(uint32_t x) {
+        Fe c = zero();
+        c.l[0] = x;
+        return to_mont(c);
+    }
+    // a + r*(b - a): the fold of multilinear_polynomial_evaluation.rs:59
+    ZK_HD static Fe fold(const Fe& a, const Fe& b, const Fe& r) { return add(a, mul(r, sub(b, a))); }
+};
+
+}  // namespace zkb

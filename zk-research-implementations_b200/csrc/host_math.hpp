@@ -1,0 +1,302 @@
+// host_math.hpp -- the host-resident part of the path: the Fiat-Shamir
+// transcript (Keccak-256), canonical serialisation, and the <=5-point
+// univariate interpolation of round messages.  These stay on the host by
+// design (BASELINE.json north_star): per round only (d+1) field elements come
+// back from the GPU and one challenge goes out as a kernel argument.
+//
+// Mirrors fiat_shamir/src/fiat_shamir_transcript.rs:5-37 and
+// univariate_polynomial/src/univariate_polynomial_dense.rs:14-26,48-74.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "launch.h"
+
+namespace zkb {
+
+// ------------------------------------------------------------- Keccak-256
+// sha3 0.10.8 `Keccak256` = Keccak[r=1088,c=512] with the ORIGINAL 0x01 padding
+// (not SHA3's 0x06).  Sponge state is 25 lanes; absorption is sequential.
+class Keccak256 {
+  public:
+    Keccak256() { reset(); }
+    void reset() {
+        std::memset(st_, 0, sizeof st_);
+        fill_ = 0;
+    }
+    void update(const uint8_t* d, size_t n) {
+        while (n) {
+            if (fill_ == 0 && n >= RATE) {  // whole blocks straight from the input
+                absorb(d);
+                d += RATE;
+                n -= RATE;
+                continue;
+            }
+            size_t take = RATE - fill_;
+            if (take > n) take = n;
+            std::memcpy(buf_ + fill_, d, take);
+            fill_ += take;
+            d += take;
+            n -= take;
+            if (fill_ == RATE) {
+                absorb(buf_);
+                fill_ = 0;
+            }
+        }
+    }
+    // finalize_reset(): digest of everything absorbed, then a fresh sponge
+    void finalize_reset(uint8_t out[32]) {
+        std::memset(buf_ + fill_, 0, RATE - fill_);
+        buf_[fill_] ^= 0x01;
+        buf_[RATE - 1] ^= 0x80;
+        absorb(buf_);
+        std::memcpy(out, st_, 32);
+        reset();
+    }
+
+  private:
+    static constexpr size_t RATE = 136;
+    uint64_t st_[25];
+    uint8_t buf_[RATE];
+    size_t fill_;
+
+    static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+    void absorb(const uint8_t* blk) {
+        for (size_t i = 0; i < RATE / 8; ++i) {
+            uint64_t lane;
+            std::memcpy(&lane, blk + 8 * i, 8);
+            st_[i] ^= lane;
+        }
+        permute();
+    }
+    void permute() {
+        static const uint64_t RC[24] = {
+            0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
+            0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+            0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
+            0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
+            0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+            0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+        // rho offsets indexed [x + 5y]
+        static const int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+        uint64_t* a = st_;
+        for (int rnd = 0; rnd < 24; ++rnd) {
+            uint64_t c[5], b[25];
+            for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+            for (int x = 0; x < 5; ++x) {
+                uint64_t d = c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1);
+                for (int y = 0; y < 25; y += 5) a[y + x] ^= d;
+            }
+            for (int x = 0; x < 5; ++x)
+                for (int y = 0; y < 5; ++y) {
+                    int r = RHO[x + 5 * y];
+                    uint64_t v = a[x + 5 * y];
+                    b[y + 5 * ((2 * x + 3 * y) % 5)] = r ? rotl(v, r) : v;
+                }
+            for (int y = 0; y < 25; y += 5)
+                for (int x = 0; x < 5; ++x) a[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
+            a[0] ^= RC[rnd];
+        }
+    }
+};
+
+// ------------------------------------------------------- host field helper
+// Montgomery-residue arithmetic on the host through the per-field table
+// (fr.cuh compiled for the host; the very same limb code the kernels run).
+struct HostField {
+    const FieldKernels* K;
+    Fe zero() const {
+        Fe z;
+        for (int i = 0; i < 8; ++i) z.l[i] = 0;
+        return z;
+    }
+    Fe add(const Fe& a, const Fe& b) const { Fe r; K->h_add(a, b, r); return r; }
+    Fe sub(const Fe& a, const Fe& b) const { Fe r; K->h_sub(a, b, r); return r; }
+    Fe mul(const Fe& a, const Fe& b) const { Fe r; K->h_mul(a, b, r); return r; }
+    Fe to_mont(const Fe& a) const { Fe r; K->h_to_mont(a, r); return r; }
+    Fe from_mont(const Fe& a) const { Fe r; K->h_from_mont(a, r); return r; }
+    Fe from_u64(uint64_t x) const {
+        Fe c = zero();
+        c.l[0] = (uint32_t)x;
+        c.l[1] = (uint32_t)(x >> 32);
+        return to_mont(c);
+    }
+    Fe one() const { return from_u64(1); }
+    bool is_zero(const Fe& a) const {
+        uint32_t o = 0;
+        for (int i = 0; i < 8; ++i) o |= a.l[i];
+        return o == 0;
+    }
+    bool eq(const Fe& a, const Fe& b) const { return std::memcmp(a.l, b.l, 32) == 0; }
+    Fe modulus() const { Fe p; K->h_modulus(p); return p; }
+    // a^(p-2)
+    Fe inv(const Fe& a) const {
+        Fe e = modulus();
+        e.l[0] -= 2;  // all three moduli end in ...01 or ...47: no borrow
+        Fe r = one();
+        for (int i = 255; i >= 0; --i) {
+            r = mul(r, r);
+            if ((e.l[i / 32] >> (i % 32)) & 1) r = mul(r, a);
+        }
+        return r;
+    }
+    // 256-bit little-endian integer mod p -> Montgomery (from_le_bytes_mod_order)
+    Fe from_le_bytes_mod_order(const uint8_t b[32]) const {
+        Fe c;
+        std::memcpy(c.l, b, 32);
+        Fe p = modulus();
+        // value < 2^256 < 6p (BN254) / 3p (BLS): subtract p while >= p
+        for (;;) {
+            bool ge = true;
+            for (int i = 7; i >= 0; --i) {
+                if (c.l[i] > p.l[i]) break;
+                if (c.l[i] < p.l[i]) { ge = false; break; }
+            }
+            if (!ge) break;
+            uint64_t bw = 0;
+            for (int i = 0; i < 8; ++i) {
+                uint64_t d = (uint64_t)c.l[i] - p.l[i] - bw;
+                c.l[i] = (uint32_t)d;
+                bw = (d >> 32) & 1;
+            }
+        }
+        return to_mont(c);
+    }
+    // Sum of up to 2^32 canonical-range residues delivered as 8 zero-extended u64 limbs
+    // (the NCCL allreduce operand): carry-propagate, then reduce mod p.
+    Fe from_wide_limbs(const unsigned long long w[8]) const {
+        uint32_t v[10] = {0};
+        unsigned __int128 carry = 0;
+        for (int i = 0; i < 8; ++i) {
+            carry += w[i];
+            v[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        v[8] = (uint32_t)carry;
+        v[9] = (uint32_t)(carry >> 32);
+        Fe p = modulus();
+        for (;;) {  // v < world * p: at most world-1 subtractions
+            bool ge = (v[8] | v[9]) != 0;
+            if (!ge) {
+                ge = true;
+                for (int i = 7; i >= 0; --i) {
+                    if (v[i] > p.l[i]) break;
+                    if (v[i] < p.l[i]) { ge = false; break; }
+                }
+            }
+            if (!ge) break;
+            uint64_t bw = 0;
+            for (int i = 0; i < 10; ++i) {
+                uint64_t d = (uint64_t)v[i] - (i < 8 ? p.l[i] : 0u) - bw;
+                v[i] = (uint32_t)d;
+                bw = (d >> 32) & 1;
+            }
+        }
+        Fe r;
+        for (int i = 0; i < 8; ++i) r.l[i] = v[i];
+        return r;
+    }
+};
+
+// -------------------------------------------------------------- Transcript
+// fiat_shamir_transcript.rs:5-30
+struct TranscriptImpl {
+    HostField H;
+    Keccak256 hasher;
+    void append(const uint8_t* d, size_t n) { hasher.update(d, n); }  // :19-21
+    // append(&fq_vec_to_bytes(values)) -- 32-byte LE canonical per element (:32-37)
+    void append_elements(const Fe* v, size_t n) {
+        for (size_t i = 0; i < n; ++i) {
+            Fe c = H.from_mont(v[i]);
+            hasher.update(reinterpret_cast<const uint8_t*>(c.l), 32);
+        }
+    }
+    Fe challenge() {  // :23-29
+        uint8_t dg[32];
+        hasher.finalize_reset(dg);
+        hasher.update(dg, 32);  // the new sponge is seeded with the digest (:25)
+        return H.from_le_bytes_mod_order(dg);
+    }
+};
+
+// ---------------------------------------------------------- UnivariatePoly
+// interpolate (univariate_polynomial_dense.rs:48-74) for the nodes 0..n-1 that
+// get_round_partial_polynomial_proof_gkr uses (sum_check_protocol.rs:157-160),
+// with the per-node factors 1/prod_{j!=i}(i-j) precomputed once per ctx.
+struct RoundInterpolator {
+    HostField H;
+    int n = 0;
+    std::vector<Fe> basis;  // basis[i*n + k] = coefficient k of the i-th Lagrange basis polynomial
+
+    void init(const HostField& h, int npts) {
+        H = h;
+        n = npts;
+        basis.assign((size_t)n * n, H.zero());
+        std::vector<Fe> xs(n);
+        for (int i = 0; i < n; ++i) xs[i] = H.from_u64((uint64_t)i);
+        for (int i = 0; i < n; ++i) {
+            std::vector<Fe> li(1, H.one());
+            Fe denom = H.one();
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                std::vector<Fe> nx(li.size() + 1, H.zero());
+                Fe neg = H.sub(H.zero(), xs[j]);
+                for (size_t k = 0; k < li.size(); ++k) {
+                    nx[k] = H.add(nx[k], H.mul(li[k], neg));
+                    nx[k + 1] = H.add(nx[k + 1], li[k]);
+                }
+                li.swap(nx);
+                denom = H.mul(denom, H.sub(xs[i], xs[j]));
+            }
+            Fe w = H.inv(denom);
+            for (int k = 0; k < n; ++k) basis[(size_t)i * n + k] = H.mul(li[k], w);
+        }
+    }
+    // ys[0..n) -> ascending coefficients; returns the trimmed length (:14-18,:71)
+    int interpolate(const Fe* ys, Fe* coeffs) const {
+        for (int k = 0; k < n; ++k) coeffs[k] = H.zero();
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) coeffs[k] = H.add(coeffs[k], H.mul(basis[(size_t)i * n + k], ys[i]));
+        int len = n;
+        while (len > 0 && H.is_zero(coeffs[len - 1])) --len;
+        return len;
+    }
+};
+
+// General-node Lagrange interpolation (the public UnivariatePoly::interpolate).
+inline int uni_interpolate(const HostField& H, const Fe* xs, const Fe* ys, int n, Fe* coeffs) {
+    std::vector<Fe> acc(n, H.zero());
+    for (int i = 0; i < n; ++i) {
+        std::vector<Fe> li(1, H.one());
+        Fe denom = H.one();
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            std::vector<Fe> nx(li.size() + 1, H.zero());
+            Fe neg = H.sub(H.zero(), xs[j]);
+            for (size_t k = 0; k < li.size(); ++k) {
+                nx[k] = H.add(nx[k], H.mul(li[k], neg));
+                nx[k + 1] = H.add(nx[k + 1], li[k]);
+            }
+            li.swap(nx);
+            denom = H.mul(denom, H.sub(xs[i], xs[j]));
+        }
+        Fe s = H.mul(ys[i], H.inv(denom));
+        for (int k = 0; k < n; ++k) acc[k] = H.add(acc[k], H.mul(li[k], s));
+    }
+    int len = n;
+    while (len > 0 && H.is_zero(acc[len - 1])) --len;
+    for (int k = 0; k < len; ++k) coeffs[k] = acc[k];
+    return len;
+}
+// evaluate (:20-26): sum c_i x^i
+inline Fe uni_evaluate(const HostField& H, const Fe* c, int len, const Fe& x) {
+    Fe s = H.zero(), xp = H.one();
+    for (int i = 0; i < len; ++i) {
+        s = H.add(s, H.mul(c[i], xp));
+        xp = H.mul(xp, x);
+    }
+    return s;
+}
+
+}  // namespace zkb

@@ -1,0 +1,654 @@
+// kernels.cuh -- the table kernels of the sumcheck / GKR hot path (sm_100a).
+//
+// Data layout in HBM ("planar", limb-interleaved): a table of N field elements
+// is two planes of N uint4 each -- plane 0 holds limbs 0..3 (the low 128 bits)
+// of every element, plane 1 holds limbs 4..7.  Consecutive threads read
+// consecutive uint4 of one plane, so every 128-bit load of a warp is one
+// contiguous 512-byte request.  Values are Montgomery residues (R = 2^256),
+// i.e. exactly ark-ff's in-memory representation re-ordered.
+//
+// Index convention of the reference (multilinear_polynomial_evaluation.rs:39-50,
+// :158-164): variable 0 is the MOST significant index bit, so binding variable 0
+// pairs entry i with entry i + N/2.
+//
+// Kernel inventory (SURVEY.md section 2.2 numbering):
+//   K1  k_fold            partial_evaluate, any `bit`
+//   K2/K7  k_sc_eval      round-0 evaluations  (plain sumcheck = PROD<D=1>)
+//   K8  k_sc_fold_eval    fused: bind the previous challenge in all tables,
+//                         write the folded tables once, and accumulate the next
+//                         round's evaluations from the freshly folded values
+//   K9  (in-kernel)       last-block-done second-stage reduction
+//   K3  k_fold_tables     fold a list of (small) tables; final bind
+//   K4  k_vec_op / k_scale, K5 k_tensor, K6 k_aos_to_planar / k_planar_to_aos
+//   K10 k_layer_eval, K11 k_eq_split, K12 k_gkr_phase1, K13 k_gkr_phase2,
+//   K14 = k_sc_* with KIND_XYZ.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "fr.cuh"
+
+namespace zkb {
+
+constexpr int MAXT = 16;      // tables per composed polynomial
+constexpr int MAXPTS = 5;     // evaluation points per round (degree <= 4)
+constexpr int BLOCK = 256;    // threads per CTA for every table kernel
+constexpr int MAXCHAL = 40;   // challenges per eq table
+
+struct TabRef {
+    uint4* base;       // plane 0; plane 1 starts at base + stride
+    uint64_t stride;   // in uint4 units
+};
+
+// Where a reducing kernel leaves its NPTS sums.
+struct FinishArgs {
+    Fe* partials;      // [gridDim.x][NPTS] scratch
+    unsigned int* ticket;
+    Fe* result;        // [NPTS] Montgomery (device or mapped host memory)
+    unsigned long long* result_wide;  // optional [NPTS][8] limbs zero-extended to u64 (NCCL sum operand)
+};
+
+struct ScArgs {
+    TabRef in[MAXT];
+    TabRef out[MAXT];
+    int n_tables;      // tables to fold (product-major: table = p*D + f)
+    int n_products;    // P (KIND_PROD)
+    uint64_t n_out;    // entries per table AFTER the fold (k_sc_fold_eval) / table size (k_sc_eval)
+    Fe r;              // challenge being bound (k_sc_fold_eval)
+    FinishArgs fin;
+};
+
+struct ChalList {
+    Fe r[MAXCHAL];
+};
+
+enum { KIND_PROD = 0, KIND_XYZ = 1 };
+
+// ----------------------------------------------------------- load / store
+__device__ __forceinline__ Fe ld_fe(const TabRef& t, uint64_t i) {
+    uint4 a = t.base[i];
+    uint4 b = t.base[t.stride + i];
+    Fe r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fe(const TabRef& t, uint64_t i, const Fe& v) {
+    t.base[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    t.base[t.stride + i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// ------------------------------------------------------------- reductions
+template <class F>
+__device__ __forceinline__ Fe warp_sum(Fe v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Fe o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.l[k] = __shfl_down_sync(0xffffffffu, v.l[k], off);
+        v = Field<F>::add(v, o);
+    }
+    return v;
+}
+
+// Sum NPTS accumulators over the CTA; valid in thread 0.
+template <class F, int NPTS>
+__device__ __forceinline__ void block_sum(Fe* acc, Fe (*smem)[NPTS]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int p = 0; p < NPTS; ++p) {
+        acc[p] = warp_sum<F>(acc[p]);
+        if (lane == 0) smem[warp][p] = acc[p];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < NPTS; ++p) {
+            Fe v = (lane < BLOCK / 32) ? smem[lane][p] : Field<F>::zero();
+            acc[p] = warp_sum<F>(v);
+        }
+    }
+    __syncthreads();
+}
+
+// Per-CTA partials -> global; the last CTA to arrive reduces them all and
+// publishes the round's NPTS evaluations (K9 folded into the producer).
+template <class F, int NPTS>
+__device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a) {
+    __shared__ Fe smem[BLOCK / 32][NPTS];
+    __shared__ bool is_last;
+    block_sum<F, NPTS>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int p = 0; p < NPTS; ++p) a.partials[(uint64_t)blockIdx.x * NPTS + p] = acc[p];
+        __threadfence();
+        unsigned int t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Fe tot[NPTS];
+#pragma unroll
+    for (int p = 0; p < NPTS; ++p) tot[p] = Field<F>::zero();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += BLOCK) {
+#pragma unroll
+        for (int p = 0; p < NPTS; ++p) {
+            const Fe* src = a.partials + (uint64_t)b * NPTS + p;
+            Fe v;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4 x = __ldcg(s4), y = __ldcg(s4 + 1);
+            v.l[0] = x.x; v.l[1] = x.y; v.l[2] = x.z; v.l[3] = x.w;
+            v.l[4] = y.x; v.l[5] = y.y; v.l[6] = y.z; v.l[7] = y.w;
+            tot[p] = Field<F>::add(tot[p], v);
+        }
+    }
+    block_sum<F, NPTS>(tot, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int p = 0; p < NPTS; ++p) {
+            a.result[p] = tot[p];
+            if (a.result_wide) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a.result_wide[p * 8 + k] = tot[p].l[k];
+            }
+        }
+        *a.ticket = 0u;
+        __threadfence_system();
+    }
+}
+
+// --------------------------------------------- round-polynomial evaluation
+// Adds this pair position's contribution to the NPTS accumulators.
+// KIND_PROD: sum over products p of prod_f (lo_f + t*(hi_f-lo_f)), t = 0..NPTS-1
+//            (get_round_partial_polynomial_proof_gkr, sum_check_protocol.rs:152-166,
+//             without materialising the (d+1) folded copies it builds).
+// KIND_XYZ : X(t)*Y(t) + Z(t) -- the two-phase GKR integrand.
+template <class F, int D, int NPTS>
+__device__ __forceinline__ void eval_product(const Fe* lo, const Fe* hi, Fe* acc) {
+    typedef Field<F> Fd;
+    if (D == 1) {
+        acc[0] = Fd::add(acc[0], lo[0]);
+        acc[1] = Fd::add(acc[1], hi[0]);
+        Fe cur = hi[0];
+        Fe dl = Fd::sub(hi[0], lo[0]);
+#pragma unroll
+        for (int t = 2; t < NPTS; ++t) {
+            cur = Fd::add(cur, dl);
+            acc[t] = Fd::add(acc[t], cur);
+        }
+        return;
+    }
+    Fe m0 = lo[0], m1 = hi[0];
+#pragma unroll
+    for (int f = 1; f < D; ++f) {
+        m0 = Fd::mul(m0, lo[f]);
+        m1 = Fd::mul(m1, hi[f]);
+    }
+    acc[0] = Fd::add(acc[0], m0);
+    acc[1] = Fd::add(acc[1], m1);
+    Fe cur[D], dl[D];
+#pragma unroll
+    for (int f = 0; f < D; ++f) {
+        dl[f] = Fd::sub(hi[f], lo[f]);
+        cur[f] = hi[f];
+    }
+#pragma unroll
+    for (int t = 2; t < NPTS; ++t) {
+#pragma unroll
+        for (int f = 0; f < D; ++f) cur[f] = Fd::add(cur[f], dl[f]);
+        Fe m = cur[0];
+#pragma unroll
+        for (int f = 1; f < D; ++f) m = Fd::mul(m, cur[f]);
+        acc[t] = Fd::add(acc[t], m);
+    }
+}
+
+template <class F>
+__device__ __forceinline__ void eval_xyz(const Fe* lo, const Fe* hi, Fe* acc) {
+    typedef Field<F> Fd;
+    acc[0] = Fd::add(acc[0], Fd::add(Fd::mul(lo[0], lo[1]), lo[2]));
+    acc[1] = Fd::add(acc[1], Fd::add(Fd::mul(hi[0], hi[1]), hi[2]));
+    Fe x2 = Fd::sub(Fd::dbl(hi[0]), lo[0]);
+    Fe y2 = Fd::sub(Fd::dbl(hi[1]), lo[1]);
+    Fe z2 = Fd::sub(Fd::dbl(hi[2]), lo[2]);
+    acc[2] = Fd::add(acc[2], Fd::add(Fd::mul(x2, y2), z2));
+}
+
+// K7: evaluations of the first round (no challenge to bind yet).
+template <class F, int KIND, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK) k_sc_eval(const ScArgs a) {
+    typedef Field<F> Fd;
+    Fe acc[NPTS];
+#pragma unroll
+    for (int p = 0; p < NPTS; ++p) acc[p] = Fd::zero();
+    const uint64_t half = a.n_out >> 1;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+        if (KIND == KIND_XYZ) {
+            Fe lo[3], hi[3];
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                lo[f] = ld_fe(a.in[f], j);
+                hi[f] = ld_fe(a.in[f], j + half);
+            }
+            eval_xyz<F>(lo, hi, acc);
+        } else {
+            for (int p = 0; p < a.n_products; ++p) {
+                Fe lo[D], hi[D];
+#pragma unroll
+                for (int f = 0; f < D; ++f) {
+                    lo[f] = ld_fe(a.in[p * D + f], j);
+                    hi[f] = ld_fe(a.in[p * D + f], j + half);
+                }
+                eval_product<F, D, NPTS>(lo, hi, acc);
+            }
+        }
+    }
+    finish_round<F, NPTS>(acc, a.fin);
+}
+
+// K8: one HBM pass per round.  Thread j owns the quad
+//   (j, j + n_out/2, j + n_out, j + n_out + n_out/2) of every input table
+// (input size 2*n_out): it folds (j, j+n_out) -> new[j] and
+// (j+n_out/2, j+n_out+n_out/2) -> new[j+n_out/2], stores both, and the pair
+// (new[j], new[j+n_out/2]) is exactly the next round's (lo, hi).
+// In-place operation (out == in) is safe: a thread only overwrites entries
+// that no other thread reads.
+template <class F, int KIND, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK) k_sc_fold_eval(const ScArgs a) {
+    typedef Field<F> Fd;
+    Fe acc[NPTS];
+#pragma unroll
+    for (int p = 0; p < NPTS; ++p) acc[p] = Fd::zero();
+    const uint64_t n_out = a.n_out, half = n_out >> 1;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const Fe r = a.r;
+    for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+        if (KIND == KIND_XYZ) {
+            Fe lo[3], hi[3];
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                Fe x0 = ld_fe(a.in[f], j), x1 = ld_fe(a.in[f], j + n_out);
+                Fe y0 = ld_fe(a.in[f], j + half), y1 = ld_fe(a.in[f], j + half + n_out);
+                lo[f] = Fd::fold(x0, x1, r);
+                hi[f] = Fd::fold(y0, y1, r);
+                st_fe(a.out[f], j, lo[f]);
+                st_fe(a.out[f], j + half, hi[f]);
+            }
+            eval_xyz<F>(lo, hi, acc);
+        } else {
+            for (int p = 0; p < a.n_products; ++p) {
+                Fe lo[D], hi[D];
+#pragma unroll
+                for (int f = 0; f < D; ++f) {
+                    const TabRef& ti = a.in[p * D + f];
+                    Fe x0 = ld_fe(ti, j), x1 = ld_fe(ti, j + n_out);
+                    Fe y0 = ld_fe(ti, j + half), y1 = ld_fe(ti, j + half + n_out);
+                    lo[f] = Fd::fold(x0, x1, r);
+                    hi[f] = Fd::fold(y0, y1, r);
+                    st_fe(a.out[p * D + f], j, lo[f]);
+                    st_fe(a.out[p * D + f], j + half, hi[f]);
+                }
+                eval_product<F, D, NPTS>(lo, hi, acc);
+            }
+        }
+    }
+    finish_round<F, NPTS>(acc, a.fin);
+}
+
+// K3/K1 for lists: fold variable 0 of n_tables tables of 2*n_out entries.
+struct FoldTablesArgs {
+    TabRef in[MAXT];
+    TabRef out[MAXT];
+    int n_tables;
+    uint64_t n_out;
+    Fe r;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_fold_tables(const FoldTablesArgs a) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t total = a.n_out * (uint64_t)a.n_tables;
+    for (uint64_t w = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; w < total; w += step) {
+        const int t = (int)(w / a.n_out);
+        const uint64_t j = w - (uint64_t)t * a.n_out;
+        Fe x0 = ld_fe(a.in[t], j), x1 = ld_fe(a.in[t], j + a.n_out);
+        st_fe(a.out[t], j, Field<F>::fold(x0, x1, a.r));
+    }
+}
+
+// K1: partial_evaluate(bit, v) (multilinear_polynomial_evaluation.rs:52-63).
+// `shift` = n_vars - 1 - bit: output index v pairs inputs insert_bit(v, shift)
+// and that | (1 << shift).
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, Fe r) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t lowmask = (1ull << shift) - 1;
+    for (uint64_t v = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; v < n_out; v += step) {
+        const uint64_t i0 = ((v >> shift) << (shift + 1)) | (v & lowmask);
+        const uint64_t i1 = i0 | (1ull << shift);
+        st_fe(out, v, Field<F>::fold(ld_fe(in, i0), ld_fe(in, i1), r));
+    }
+}
+
+// K6: layout conversion.  AoS = ark-ff Vec<Fp>: 32 bytes per element.
+// conv: 0 = none, 1 = to Montgomery (input canonical), 2 = from Montgomery.
+template <class F>
+__device__ __forceinline__ Fe apply_conv(const Fe& v, int conv) {
+    if (conv == 1) return Field<F>::to_mont(v);
+    if (conv == 2) return Field<F>::from_mont(v);
+    return v;
+}
+// Element i of the planar table <- AoS element (first + i*stride_elems).
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_aos_to_planar(const uint4* __restrict__ aos, TabRef out, uint64_t n,
+                                                        uint64_t first, uint64_t stride_elems, int conv) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += step) {
+        const uint64_t s = first + i * stride_elems;
+        uint4 a = aos[2 * s], b = aos[2 * s + 1];
+        Fe v;
+        v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w;
+        v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+        st_fe(out, i, apply_conv<F>(v, conv));
+    }
+}
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_planar_to_aos(TabRef in, uint4* __restrict__ aos, uint64_t n, int conv) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += step) {
+        Fe v = apply_conv<F>(ld_fe(in, i), conv);
+        aos[2 * i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        aos[2 * i + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+}
+// Interleave G per-rank shards (each n_local entries, planar, concatenated in
+// `gathered` rank-major) into the global order i = local*G + rank (C2).
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_interleave_shards(TabRef gathered, uint64_t shard_pitch, TabRef out,
+                                                            uint64_t n_local, uint32_t log2g) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t n = n_local << log2g;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += step) {
+        const uint64_t rank = i & ((1ull << log2g) - 1), loc = i >> log2g;
+        // each shard is its own planar block: plane 0 at rank*pitch, plane 1 at rank*pitch + n_local
+        TabRef src;
+        src.base = gathered.base + rank * shard_pitch;
+        src.stride = n_local;
+        st_fe(out, i, ld_fe(src, loc));
+    }
+}
+
+// Synthetic table (same rule as oracle synth_entry): canonical limbs
+// from SplitMix64, top limb masked, converted to Montgomery form on the fly.
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_generate(TabRef out, uint64_t n, uint64_t seed, uint64_t table,
+                                                   uint64_t first, uint64_t stride_elems) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t base0 = splitmix64(seed ^ (table << 48));
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += step) {
+        const uint64_t gi = first + i * stride_elems;
+        const uint64_t base = base0 + 4 * gi;
+        Fe v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint64_t w = splitmix64(base + (uint64_t)k);
+            if (k == 3) w &= (1ull << (F::ID == 2 ? 62 : 61)) - 1;
+            v.l[2 * k] = (uint32_t)w;
+            v.l[2 * k + 1] = (uint32_t)(w >> 32);
+        }
+        st_fe(out, i, Field<F>::to_mont(v));
+    }
+}
+
+// K4: elementwise.  op: 0 add, 1 sub, 2 mul (Add/Sub/Mul impls :113-156).
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_vec_op(TabRef x, TabRef y, TabRef out, uint64_t n, int op) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += step) {
+        Fe a = ld_fe(x, i), b = ld_fe(y, i), r;
+        if (op == 0) r = Field<F>::add(a, b);
+        else if (op == 1) r = Field<F>::sub(a, b);
+        else r = Field<F>::mul(a, b);
+        st_fe(out, i, r);
+    }
+}
+// out = alpha*x (+ beta*y when y.base != nullptr): scale (:93-97) and the
+// alpha/beta merge of gkr_protocol.rs:277-281.
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_axpby(TabRef x, TabRef y, TabRef out, uint64_t n, Fe alpha, Fe beta) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += step) {
+        Fe r = Field<F>::mul(alpha, ld_fe(x, i));
+        if (y.base) r = Field<F>::add(r, Field<F>::mul(beta, ld_fe(y, i)));
+        st_fe(out, i, r);
+    }
+}
+// K5: out[i*nb + j] = a[i] (op) b[j]  (tensor_add_mul_polynomials :99-111)
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_tensor(TabRef x, TabRef y, TabRef out, uint64_t na, uint64_t nb, int op) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t w = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; w < na * nb; w += step) {
+        Fe a = ld_fe(x, w / nb), b = ld_fe(y, w % nb);
+        st_fe(out, w, op == 0 ? Field<F>::add(a, b) : Field<F>::mul(a, b));
+    }
+}
+
+// K10: one circuit layer (Circuit::evaluate, gkr_circuit.rs:127-143):
+// out[g] = in[2g] (op[g]) in[2g+1].
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_layer_eval(TabRef in, TabRef out, const uint8_t* __restrict__ ops,
+                                                     uint64_t n_gates) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < n_gates; g += step) {
+        Fe a = ld_fe(in, 2 * g), b = ld_fe(in, 2 * g + 1);
+        st_fe(out, g, ops[g] ? Field<F>::mul(a, b) : Field<F>::add(a, b));
+    }
+}
+
+// K11: eq(r, .) in split form.  r has n challenges (variable 0 = MSB).  The
+// table over the first n_hi variables goes to `hi` (2^n_hi entries), the one
+// over the remaining n - n_hi to `lo`; eq(r, x) = hi[x >> n_lo] * lo[x & mask].
+// One thread per entry, <= 20 multiplications each; both tables are tiny.
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_eq_split(const ChalList r, int n, int n_hi, TabRef hi, TabRef lo) {
+    typedef Field<F> Fd;
+    const int n_lo = n - n_hi;
+    const uint64_t nh = 1ull << n_hi, nl = 1ull << n_lo;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t w = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; w < nh + nl; w += step) {
+        const bool is_hi = w < nh;
+        const uint64_t x = is_hi ? w : w - nh;
+        const int cnt = is_hi ? n_hi : n_lo, off = is_hi ? 0 : n_hi;
+        Fe v = Fd::one();
+        for (int k = 0; k < cnt; ++k) {
+            const Fe rk = r.r[off + k];
+            const bool bit = (x >> (cnt - 1 - k)) & 1;
+            v = Fd::mul(v, bit ? rk : Fd::sub(Fd::one(), rk));
+        }
+        st_fe(is_hi ? hi : lo, x, v);
+    }
+}
+template <class F>
+__device__ __forceinline__ Fe eq_lookup(const TabRef& hi, const TabRef& lo, int n_lo, uint64_t x) {
+    return Field<F>::mul(ld_fe(hi, x >> n_lo), ld_fe(lo, x & ((1ull << n_lo) - 1)));
+}
+
+// K12: phase-1 tables of the two-phase GKR layer sumcheck (sparse restatement
+// of get_fbc_poly / get_folded_fbc_poly, gkr_protocol.rs:243-292).
+//   coef[g] = first layer : eq((r0), g)                       (one `a` variable)
+//             otherwise   : alpha*eq(r_b, g) + beta*eq(r_c, g)
+//   gate g reads wires b = 2g, c = 2g+1 (gkr_circuit.rs:76-78):
+//   Add: H1[b] = coef, HA2[b] = coef*W[c];   Mul: H1[b] = coef*W[c], HA2[b] = 0;
+//   odd b: zero.  Round polynomial of phase 1: sum_b W(b)*H1(b) + HA2(b).
+struct GkrP1Args {
+    TabRef W, H1, HA2, coef;
+    TabRef eb_hi, eb_lo, ec_hi, ec_lo;  // split eq tables of r_b, r_c (unused for the first layer)
+    int n_lo;
+    const uint8_t* ops;
+    uint64_t n_gates;
+    int first_layer;
+    Fe r0, alpha, beta;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_phase1(const GkrP1Args a) {
+    typedef Field<F> Fd;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.n_gates; g += step) {
+        Fe c;
+        if (a.first_layer) {
+            c = g ? a.r0 : Fd::sub(Fd::one(), a.r0);
+        } else {
+            Fe eb = eq_lookup<F>(a.eb_hi, a.eb_lo, a.n_lo, g);
+            Fe ec = eq_lookup<F>(a.ec_hi, a.ec_lo, a.n_lo, g);
+            c = Fd::add(Fd::mul(a.alpha, eb), Fd::mul(a.beta, ec));
+        }
+        st_fe(a.coef, g, c);
+        Fe wc = ld_fe(a.W, 2 * g + 1);
+        Fe cw = Fd::mul(c, wc);
+        const bool is_mul = a.ops[g] != 0;
+        st_fe(a.H1, 2 * g, is_mul ? cw : c);
+        st_fe(a.HA2, 2 * g, is_mul ? Fd::zero() : cw);
+        st_fe(a.H1, 2 * g + 1, Fd::zero());
+        st_fe(a.HA2, 2 * g + 1, Fd::zero());
+    }
+}
+// K13: phase-2 tables, b bound to u: with v = coef[g]*eq(u, 2g), Wu = W(u):
+//   Add: C[c] = v, D[c] = Wu*v;   Mul: C[c] = Wu*v, D[c] = 0;   even c: zero.
+// Round polynomial of phase 2: sum_c W(c)*C(c) + D(c).
+struct GkrP2Args {
+    TabRef C, D, coef;
+    TabRef eu_hi, eu_lo;
+    int n_lo;
+    const uint8_t* ops;
+    uint64_t n_gates;
+    Fe Wu;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_phase2(const GkrP2Args a) {
+    typedef Field<F> Fd;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.n_gates; g += step) {
+        Fe v = Fd::mul(ld_fe(a.coef, g), eq_lookup<F>(a.eu_hi, a.eu_lo, a.n_lo, 2 * g));
+        Fe wv = Fd::mul(a.Wu, v);
+        const bool is_mul = a.ops[g] != 0;
+        st_fe(a.C, 2 * g + 1, is_mul ? wv : v);
+        st_fe(a.D, 2 * g + 1, is_mul ? Fd::zero() : wv);
+        st_fe(a.C, 2 * g, Fd::zero());
+        st_fe(a.D, 2 * g, Fd::zero());
+    }
+}
+
+// Element `idx` of each listed table -> out[t] (final bound values, openings).
+struct GatherArgs {
+    TabRef t[MAXT];
+    int n;
+    uint64_t idx;
+    Fe* out;
+};
+__global__ void k_gather_elems(const GatherArgs a) {
+    int t = threadIdx.x;
+    if (t < a.n) a.out[t] = ld_fe(a.t[t], a.idx);
+}
+
+// Verifier side of a GKR layer (get_verifier_claim / get_folded_verifier_claim,
+// gkr_protocol.rs:294-341) in O(G): the wiring predicates at the random point,
+//   a_r = sum_{g: Add} coef[g]*eq(u,2g)*eq(w,2g+1),   m_r likewise for Mul,
+// with coef as in k_gkr_phase1.  result[0] = a_r, result[1] = m_r.
+struct GkrWiringArgs {
+    TabRef eb_hi, eb_lo, ec_hi, ec_lo;  // split eq of the previous r_b, r_c
+    int n_lo_a;
+    TabRef eu_hi, eu_lo, ew_hi, ew_lo;  // split eq of this layer's r_b (u) and r_c (w)
+    int n_lo_w;
+    const uint8_t* ops;
+    uint64_t n_gates;
+    int first_layer;
+    Fe r0, alpha, beta;
+    FinishArgs fin;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_wiring(const GkrWiringArgs a) {
+    typedef Field<F> Fd;
+    Fe acc[2] = {Fd::zero(), Fd::zero()};
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.n_gates; g += step) {
+        Fe c;
+        if (a.first_layer) {
+            c = g ? a.r0 : Fd::sub(Fd::one(), a.r0);
+        } else {
+            Fe eb = eq_lookup<F>(a.eb_hi, a.eb_lo, a.n_lo_a, g);
+            Fe ec = eq_lookup<F>(a.ec_hi, a.ec_lo, a.n_lo_a, g);
+            c = Fd::add(Fd::mul(a.alpha, eb), Fd::mul(a.beta, ec));
+        }
+        Fe t = Fd::mul(c, Fd::mul(eq_lookup<F>(a.eu_hi, a.eu_lo, a.n_lo_w, 2 * g),
+                                  eq_lookup<F>(a.ew_hi, a.ew_lo, a.n_lo_w, 2 * g + 1)));
+        if (a.ops[g]) acc[1] = Fd::add(acc[1], t);
+        else acc[0] = Fd::add(acc[0], t);
+    }
+    finish_round<F, 2>(acc, a.fin);
+}
+
+// ------------------------------------------------------- microbenchmarks
+// Register-resident multiplier throughput (fills the IMAD-roofline number the
+// driver does not measure): each thread runs `iters` dependent products on
+// ILP independent chains.
+template <class F, int ILP, bool SPLIT>
+__global__ void __launch_bounds__(BLOCK) k_bench_mul(Fe* out, uint32_t iters, Fe seed) {
+    Fe x[ILP], y = seed;
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) {
+        x[k] = seed;
+        x[k].l[0] += threadIdx.x + k;
+    }
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) x[k] = SPLIT ? Field<F>::mul_split(x[k], y) : Field<F>::mul(x[k], y);
+    }
+    Fe s = x[0];
+#pragma unroll
+    for (int k = 1; k < ILP; ++k) s = Field<F>::add(s, x[k]);
+    if (s.l[0] == 0x12345678u && s.l[7] == 0x9abcdef0u) out[blockIdx.x * BLOCK + threadIdx.x] = s;  // keep the loop alive
+}
+// Raw multiply-pipe rate: MODE 0 = IMAD (32-bit mad.lo), 1 = IMAD.HI, 2 = mad.wide (64-bit accumulate,
+// no carry), 3 = the multiplier's own chain: mul.wide + addc.cc.u64 -> IMAD.WIDE.U32.X with predicate carry
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) k_bench_imad(uint64_t* out, uint32_t iters, uint32_t a, uint32_t b) {
+    uint64_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = threadIdx.x + k;
+    uint32_t x = a + threadIdx.x, y = b;
+    for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (MODE == 0) {
+                    uint32_t lo = (uint32_t)acc[k];
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(x), "r"(y));
+                    acc[k] = lo;
+                } else if (MODE == 1) {
+                    uint32_t lo = (uint32_t)acc[k];
+                    asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(x), "r"(y));
+                    acc[k] = lo;
+                } else if (MODE == 2) {
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+                } else {
+                    acc[k] = (k & 3) == 0 ? madw_cc(x, y, acc[k]) : madwc_cc(x, y, acc[k]);
+                }
+            }
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    if (s == 0x123456789abcdef0ull) out[blockIdx.x * BLOCK + threadIdx.x] = s;
+}
+
+}  // namespace zkb

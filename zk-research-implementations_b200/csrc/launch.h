@@ -1,0 +1,48 @@
+// launch.h -- per-field launcher table.  Each field (BN254 Fr, BN254 Fq,
+// BLS12-381 Fr) is one translation unit instantiating kernels.cuh with its
+// modulus as compile-time immediates; the host driver picks a table by id.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace zkb {
+
+struct FieldKernels {
+    int field_id;
+    // composed-sumcheck kernels; kind/D/npts select the instantiation. Return false if unsupported.
+    bool (*sc_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
+    bool (*sc_fold_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
+    // resident CTAs per SM for that instantiation (0 = unsupported)
+    int (*sc_occupancy)(int fused, int kind, int D, int npts);
+    void (*fold_tables)(const FoldTablesArgs& a, int grid, cudaStream_t s);
+    void (*fold)(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const Fe& r, int grid, cudaStream_t s);
+    void (*aos_to_planar)(const void* aos, TabRef out, uint64_t n, uint64_t first, uint64_t stride, int conv, int grid, cudaStream_t s);
+    void (*planar_to_aos)(TabRef in, void* aos, uint64_t n, int conv, int grid, cudaStream_t s);
+    void (*interleave_shards)(TabRef gathered, uint64_t pitch, TabRef out, uint64_t n_local, uint32_t log2g, int grid, cudaStream_t s);
+    void (*generate)(TabRef out, uint64_t n, uint64_t seed, uint64_t table, uint64_t first, uint64_t stride, int grid, cudaStream_t s);
+    void (*vec_op)(TabRef x, TabRef y, TabRef out, uint64_t n, int op, int grid, cudaStream_t s);
+    void (*axpby)(TabRef x, TabRef y, TabRef out, uint64_t n, const Fe& alpha, const Fe& beta, int grid, cudaStream_t s);
+    void (*tensor)(TabRef x, TabRef y, TabRef out, uint64_t na, uint64_t nb, int op, int grid, cudaStream_t s);
+    void (*layer_eval)(TabRef in, TabRef out, const uint8_t* ops, uint64_t n_gates, int grid, cudaStream_t s);
+    void (*eq_split)(const ChalList& r, int n, int n_hi, TabRef hi, TabRef lo, int grid, cudaStream_t s);
+    void (*gkr_phase1)(const GkrP1Args& a, int grid, cudaStream_t s);
+    void (*gkr_phase2)(const GkrP2Args& a, int grid, cudaStream_t s);
+    void (*gkr_wiring)(const GkrWiringArgs& a, int grid, cudaStream_t s);
+    void (*bench_mul)(int variant, Fe* out, uint32_t iters, int grid, cudaStream_t s);
+    // host-side arithmetic on Montgomery residues (fr.cuh compiled for the host)
+    void (*h_add)(const Fe& a, const Fe& b, Fe& r);
+    void (*h_sub)(const Fe& a, const Fe& b, Fe& r);
+    void (*h_mul)(const Fe& a, const Fe& b, Fe& r);
+    void (*h_to_mont)(const Fe& a, Fe& r);
+    void (*h_from_mont)(const Fe& a, Fe& r);
+    void (*h_modulus)(Fe& p);
+};
+
+const FieldKernels* field_kernels_bn254_fr();
+const FieldKernels* field_kernels_bn254_fq();
+const FieldKernels* field_kernels_bls12_381_fr();
+void launch_gather_elems(const GatherArgs& a, cudaStream_t s);
+void launch_bench_imad(int mode, uint64_t* out, uint32_t iters, int grid, cudaStream_t s);
+
+}  // namespace zkb
