@@ -136,6 +136,13 @@ int32_t zkb_transcript_append(zkb_transcript* t, const uint8_t* bytes, size_t le
 int32_t zkb_transcript_append_elements(zkb_transcript* t, const uint64_t* mont, size_t n); /* append(&fq_vec_to_bytes(..)) */
 int32_t zkb_transcript_challenge(zkb_transcript* t, uint64_t out_mont[4]);
 int32_t zkb_keccak256(const uint8_t* bytes, size_t len, uint8_t out[32]);
+/* Host conversion between canonical little-endian limbs and the Montgomery residues that cross this ABI
+ * (what ark-ff's `F::from(BigInt)` / `into_bigint()` do; used by non-Rust callers). */
+int32_t zkb_fe_to_mont(int32_t field_id, const uint64_t* canonical, uint64_t* mont, size_t n);
+int32_t zkb_fe_from_mont(int32_t field_id, const uint64_t* mont, uint64_t* canonical, size_t n);
+/* The host half of the per-round multi-GPU combine (C1): `wide` holds, for each of n values, the 8 32-bit limbs
+ * of the ranks' residues summed as plain integers in 8 uint64 slots; carry-propagate and reduce mod p. */
+int32_t zkb_fe_reduce_wide(int32_t field_id, const uint64_t* wide, uint64_t* out, size_t n);
 
 /* ------------------------------------------------ UnivariatePoly (host, tiny) */
 /* interpolate + trim (univariate_polynomial_dense.rs:48-74,14-18): returns the trimmed length in *len. */

@@ -1,3 +1,4 @@
+import importlib
 import os
 import sys
 
@@ -6,6 +7,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+PKG = "zk-research-implementations_b200"
 
 
 def pytest_configure(config):
@@ -18,3 +21,25 @@ def oracle():
 
     c_oracle.build()
     return c_oracle
+
+
+@pytest.fixture(scope="session")
+def zkb():
+    """The product package (hyphenated directory name -> importlib)."""
+    return importlib.import_module(PKG)
+
+
+@pytest.fixture(scope="session")
+def ctxs(zkb):
+    """One device context per (field, mode), created lazily on cuda:0.  Fails loudly without a GPU."""
+    cache = {}
+
+    def get(field=0, mode=0):
+        key = (field, mode)
+        if key not in cache:
+            cache[key] = zkb.Context(field, 0, mode)
+        return cache[key]
+
+    yield get
+    for c in cache.values():
+        c.close()

@@ -1,0 +1,133 @@
+"""CPU-side checks of the drop-in boundary: libzkb200.so loads without a GPU,
+exports every symbol include/zkb200.h declares, its host-resident parts
+(transcript, interpolation, Montgomery conversion, wide-limb reduction, the
+composed-sumcheck verifier) agree with the oracle, and the device entry points
+fail loudly -- never fall back -- when there is no CUDA device."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pyref as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIELDS = [(0, R.BN254_FR), (1, R.BN254_FQ), (2, R.BLS12_381_FR)]
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "zkb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(zkb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(zkb):
+    lib = zkb.engine.lib()
+    syms = header_symbols()
+    assert len(syms) >= 50
+    for s in syms:
+        assert hasattr(lib, s), f"libzkb200.so does not export {s}"
+    assert b"sm_100a" in lib.zkb_version()
+
+
+def test_no_cpu_fallback(zkb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(zkb.ZkbError) as ei:
+        zkb.Context(0, 0, 0)
+    assert ei.value.status == -6  # ZKB_ERR_CUDA
+
+
+def test_keccak_and_transcript(zkb, oracle):
+    assert zkb.engine.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert zkb.engine.keccak256(b"abc").hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    rng = random.Random(5)
+    for n in (0, 1, 135, 136, 137, 272, 1000):
+        data = bytes(rng.randrange(256) for _ in range(n))
+        assert zkb.engine.keccak256(data) == oracle.keccak256(data) == R.keccak256(data)
+    for fid, p in FIELDS:
+        t, o = zkb.fiat_shamir.Transcript(fid), oracle.Transcript(fid)
+        for k in range(6):
+            chunk = bytes(rng.randrange(256) for _ in range(rng.randrange(0, 300)))
+            t.append(chunk)
+            o.append(chunk)
+            assert t.get_random_challenge() == o.challenge()
+    # SURVEY App. C vector (fiat_shamir_transcript.rs:47 input)
+    t = zkb.fiat_shamir.Transcript(0)
+    t.append(b"zero knowledge")
+    assert t.get_random_challenge() == 0x020D8026E5DCCBCA38647E1D8C0B31759149BF792F36122704566AF81A460761
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_montgomery_conversion_and_wide_reduce(zkb, oracle, fid, p):
+    E = zkb.engine
+    rng = random.Random(fid)
+    vals = [0, 1, p - 1, (1 << 256) % p] + [rng.randrange(p) for _ in range(100)]
+    m = E.to_mont(fid, E.ints_to_limbs(vals))
+    assert E.limbs_to_ints(m) == [R.to_mont(v, p) for v in vals]
+    assert E.limbs_to_ints(E.from_mont(fid, m)) == vals
+    # C1: sum of up to 8 ranks' residues on zero-extended 32-bit limbs
+    for world in (1, 2, 4, 8):
+        parts = [[rng.choice([p - 1, rng.randrange(p)]) for _ in range(5)] for _ in range(world)]
+        wide = np.zeros((5, 8), dtype=np.uint64)
+        for part in parts:
+            for i, v in enumerate(part):
+                for k in range(8):
+                    wide[i, k] += (v >> (32 * k)) & 0xFFFFFFFF
+        out = np.zeros((5, 4), dtype=np.uint64)
+        assert E.lib().zkb_fe_reduce_wide(fid, wide.ctypes.data_as(E.u64p), out.ctypes.data_as(E.u64p), 5) == 0
+        assert E.limbs_to_ints(out) == [sum(part[i] for part in parts) % p for i in range(5)]
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_univariate(zkb, fid, p):
+    U = zkb.univariate_polynomial.UnivariatePoly
+    assert U.interpolate([(0, 2), (1, 4), (2, 6)], fid).coefficients == [2, 2]  # univariate_polynomial_dense.rs test
+    assert U.interpolate([(0, 20), (1, 68), (2, 156)], fid).coefficients == [20, 28, 20]  # sum_check_protocol.rs:236-244
+    assert U.interpolate([(0, 0), (1, 0), (2, 0)], fid).coefficients == []  # trimmed to empty
+    rng = random.Random(9 + fid)
+    for n in (1, 2, 3, 4, 5):
+        pts = [(rng.randrange(p), rng.randrange(p)) for _ in range(n)]
+        q = U.interpolate(pts, fid)
+        assert q.coefficients == R.uni_interpolate(pts, p)
+        x = rng.randrange(p)
+        assert q.evaluate(x) == R.uni_evaluate(q.coefficients, x, p)
+        for px, py in pts:
+            assert q.evaluate(px) == py
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_host_composed_verifier_against_oracle_proofs(zkb, oracle, fid, p):
+    """gkr_verify (sum_check_protocol.rs:117-150) is host code in libzkb200: feed it the oracle's proofs."""
+    from oracle.c_oracle import ints_to_arr
+
+    S = zkb.sum_check_protocol
+    U = zkb.univariate_polynomial.UnivariatePoly
+    rng = random.Random(77 + fid)
+    for n in (1, 3, 6):
+        tabs = [[rng.randrange(p) for _ in range(1 << n)] for _ in range(4)]
+        pr = oracle.gkr_sumcheck_prove(oracle.Transcript(fid), 0, 2, 2, [ints_to_arr(t) for t in tabs])
+        claim = sum(a * b + c * d for a, b, c, d in zip(*tabs)) % p
+        polys = [U(c, fid) for c in pr["coeffs"]]
+        v = S.gkr_verify(polys, claim, zkb.fiat_shamir.Transcript(fid))
+        assert v.verified and v.random_challenges == pr["challenges"]
+        fv = pr["final_vals"]
+        assert v.final_claimed_sum == (fv[0] * fv[1] + fv[2] * fv[3]) % p
+        ok_o, fin_o, ch_o = oracle.gkr_sumcheck_verify(oracle.Transcript(fid), pr["coeffs"], claim)
+        assert ok_o and fin_o == v.final_claimed_sum and ch_o == v.random_challenges
+        bad = S.gkr_verify(polys, (claim + 1) % p, zkb.fiat_shamir.Transcript(fid))
+        assert (bad.verified, bad.final_claimed_sum, bad.random_challenges) == (False, 0, [0])  # :129-133
+
+
+def test_error_codes_map_to_reference_panics(zkb):
+    E = zkb.engine
+    assert E.lib().zkb_strerror(-2) == b"Invalid evaluations"
+    assert E.lib().zkb_strerror(-3) == b"Invalid number of values"
+    assert E.lib().zkb_strerror(-4) == b"all evaluations must have same length"
+    assert E.lib().zkb_strerror(-5) == b"all product polys must have same degree"
+    with pytest.raises(ValueError, match="Invalid evaluations"):
+        E._ck(None, -2)

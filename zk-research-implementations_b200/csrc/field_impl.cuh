@@ -40,6 +40,9 @@ int l_sc_occupancy(int fused, int kind, int D, int npts) {
     return 0;
 }
 void l_fold_tables(const FoldTablesArgs& a, int grid, cudaStream_t s) { k_fold_tables<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_final_bind(const FoldTablesArgs& a, Fe* out, volatile unsigned int* flag, unsigned int seq, cudaStream_t s) {
+    k_final_bind<FT><<<1, 32, 0, s>>>(a, out, flag, seq);
+}
 void l_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const Fe& r, int grid, cudaStream_t s) {
     k_fold<FT><<<grid, BLOCK, 0, s>>>(in, out, n_out, shift, r);
 }
@@ -90,7 +93,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_occupancy, l_fold_tables, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_occupancy, l_fold_tables, l_final_bind, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

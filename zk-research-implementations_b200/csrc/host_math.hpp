@@ -133,7 +133,12 @@ struct HostField {
     // a^(p-2)
     Fe inv(const Fe& a) const {
         Fe e = modulus();
-        e.l[0] -= 2;  // all three moduli end in ...01 or ...47: no borrow
+        uint64_t bw = 2;  // e = p - 2 with borrow propagation (BLS12-381 Fr's low limb is 1)
+        for (int i = 0; i < 8 && bw; ++i) {
+            uint64_t d = (uint64_t)e.l[i] - bw;
+            e.l[i] = (uint32_t)d;
+            bw = (d >> 32) & 1;
+        }
         Fe r = one();
         for (int i = 255; i >= 0; --i) {
             r = mul(r, r);

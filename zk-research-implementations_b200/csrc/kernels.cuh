@@ -46,6 +46,8 @@ struct FinishArgs {
     unsigned int* ticket;
     Fe* result;        // [NPTS] Montgomery (device or mapped host memory)
     unsigned long long* result_wide;  // optional [NPTS][8] limbs zero-extended to u64 (NCCL sum operand)
+    volatile unsigned int* flag;      // optional mailbox flag (mapped host memory): set to `seq` after `result`
+    unsigned int seq;
 };
 
 struct ScArgs {
@@ -155,6 +157,7 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a) {
         }
         *a.ticket = 0u;
         __threadfence_system();
+        if (a.flag) *a.flag = a.seq;
     }
 }
 
@@ -315,6 +318,21 @@ __global__ void __launch_bounds__(BLOCK) k_fold_tables(const FoldTablesArgs a) {
         Fe x0 = ld_fe(a.in[t], j), x1 = ld_fe(a.in[t], j + a.n_out);
         st_fe(a.out[t], j, Field<F>::fold(x0, x1, a.r));
     }
+}
+
+// Last bind of a sumcheck: every table has 2 entries left; fold them, keep the
+// value in the table (entry 0) and publish all n_tables values to the mailbox.
+template <class F>
+__global__ void k_final_bind(const FoldTablesArgs a, Fe* out, volatile unsigned int* flag, unsigned int seq) {
+    const int t = threadIdx.x;
+    if (t < a.n_tables) {
+        Fe v = Field<F>::fold(ld_fe(a.in[t], 0), ld_fe(a.in[t], 1), a.r);
+        st_fe(a.out[t], 0, v);
+        out[t] = v;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t == 0 && flag) *flag = seq;
 }
 
 // K1: partial_evaluate(bit, v) (multilinear_polynomial_evaluation.rs:52-63).
@@ -553,7 +571,7 @@ struct GatherArgs {
     uint64_t idx;
     Fe* out;
 };
-__global__ void k_gather_elems(const GatherArgs a) {
+static __global__ void k_gather_elems(const GatherArgs a) {
     int t = threadIdx.x;
     if (t < a.n) a.out[t] = ld_fe(a.t[t], a.idx);
 }

@@ -1,0 +1,1637 @@
+// zkb200.cu -- host driver and C ABI (include/zkb200.h) of the B200 sumcheck /
+// GKR prover engine.  All table arithmetic runs in the kernels of kernels.cuh;
+// this file owns device memory, the round loop, the mailbox through which the
+// (d+1) round evaluations reach the host, the host transcript, and the optional
+// NCCL communicator for tables sharded on low index bits.
+//
+// There is no CPU fallback: every table entry point needs a ctx, and a ctx can
+// only be created on a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/zkb200.h"
+#include "host_math.hpp"
+
+using namespace zkb;
+
+// ------------------------------------------------------------------ NCCL (lazy)
+// Resolved with dlopen at zkb_ctx_comm_init so that (a) the library loads on a
+// machine without NCCL/GPU and (b) a process that already carries NCCL (torch)
+// shares that copy instead of loading a second one.
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !h; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+    }
+};
+NcclApi g_nccl;
+
+const FieldKernels* kernels_for(int field) {
+    switch (field) {
+        case ZKB_FIELD_BN254_FR: return field_kernels_bn254_fr();
+        case ZKB_FIELD_BN254_FQ: return field_kernels_bn254_fq();
+        case ZKB_FIELD_BLS12_381_FR: return field_kernels_bls12_381_fr();
+    }
+    return nullptr;
+}
+
+inline Fe fe_from_u64x4(const uint64_t* p) {
+    Fe r;
+    std::memcpy(r.l, p, 32);
+    return r;
+}
+inline void fe_to_u64x4(const Fe& v, uint64_t* p) { std::memcpy(p, v.l, 32); }
+inline int ilog2_u64(uint64_t x) {
+    int r = 0;
+    while (x > 1) {
+        x >>= 1;
+        ++r;
+    }
+    return r;
+}
+inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+
+// A device table in the planar layout of kernels.cuh.
+struct Table {
+    uint4* base = nullptr;
+    uint64_t n = 0;       // live entries
+    uint64_t stride = 0;  // distance between the two limb planes (uint4 units) = allocated entries
+    TabRef ref() const { return TabRef{base, stride}; }
+};
+
+struct SumPolyState {
+    int P = 0, D = 0;             // declared shape (SumPoly of P ProductPolys of D factors)
+    int kind = KIND_PROD;
+    int kP = 0, kD = 0, npts = 0; // what the round kernel multiplies / how many points it returns
+    std::vector<int> sel;         // tables the round kernel reads (kernel order)
+    std::vector<int> rest;        // tables that are only folded (compat mode)
+    std::vector<Table> src;       // caller's tables, never written
+    std::vector<Table> work;      // private folded copies
+    std::vector<Table> gath;      // after the multi-GPU gather
+    uint64_t n0 = 0;              // local entries per table before any bind
+    uint64_t cur_n = 0;           // local entries per table now
+    int state = 0;                // 0 = unbound (src), 1 = in work, 2 = in gath
+    bool sharded = false;         // partial sums need the allreduce
+    Table& cur(int t) { return state == 0 ? src[t] : (state == 1 ? work[t] : gath[t]); }
+};
+
+struct CircuitState {
+    int L = 0;
+    std::vector<uint32_t> gates;  // input side first
+    std::vector<size_t> opoff;
+    std::vector<uint8_t> h_ops;
+    uint8_t* d_ops = nullptr;
+    Table inputs;
+    std::vector<Table> vals;  // per layer outputs
+    Table H1, HA2, coef;      // phase tables (max size)
+    Table eq[8];              // split eq tables: rb hi/lo, rc hi/lo, u hi/lo, w hi/lo
+    SumPolyState sp;          // the XYZ sumcheck state (work tables reused across layers)
+    void* aos_stage = nullptr;
+    size_t aos_stage_bytes = 0;
+};
+}  // namespace
+
+struct zkb_transcript {
+    TranscriptImpl impl;
+};
+
+struct zkb_ctx {
+    int field = 0, device = 0, mode = 0;
+    const FieldKernels* K = nullptr;
+    HostField H;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    std::string last_error;
+    // mailbox (mapped, pinned host memory)
+    Fe* h_res = nullptr;
+    volatile unsigned int* h_flag = nullptr;
+    unsigned int seq = 0;
+    // device scratch of the reducing kernels
+    Fe* d_partials = nullptr;
+    size_t partials_cap = 0;
+    unsigned int* d_ticket = nullptr;
+    Fe* d_res = nullptr;
+    unsigned long long* d_wide = nullptr;
+    unsigned long long* h_wide = nullptr;
+    // staging for uploads / downloads
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // handles
+    uint64_t next_handle = 1;
+    std::unordered_map<uint64_t, Table> mles;
+    std::unordered_map<uint64_t, std::unique_ptr<SumPolyState>> sps;
+    std::unordered_map<uint64_t, std::unique_ptr<CircuitState>> circs;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, log2world = 0;
+    uint32_t gather_log2 = 12;
+    RoundInterpolator interp[MAXPTS + 1];
+    std::unordered_map<std::string, int> occ_cache;
+};
+
+namespace {
+
+#define ZK_CUDA(ctx, call)                                                                    \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);           \
+            return e_ == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA;               \
+        }                                                                                     \
+    } while (0)
+#define ZK_NCCL(ctx, call)                                                                    \
+    do {                                                                                      \
+        ncclResult_t e_ = (call);                                                             \
+        if (e_ != ncclSuccess) {                                                              \
+            (ctx)->last_error = std::string(#call) + ": " +                                   \
+                                (g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "nccl"); \
+            return ZKB_ERR_NCCL;                                                              \
+        }                                                                                     \
+    } while (0)
+#define ZK_TRY(expr)                 \
+    do {                             \
+        int32_t s_ = (expr);         \
+        if (s_ != ZKB_OK) return s_; \
+    } while (0)
+#define ZK_FAIL(ctx, code, msg)    \
+    do {                           \
+        (ctx)->last_error = (msg); \
+        return (code);             \
+    } while (0)
+
+int32_t check_launch(zkb_ctx* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        return ZKB_ERR_CUDA;
+    }
+    ++c->launches;
+    return ZKB_OK;
+}
+
+int grid_for(const zkb_ctx* c, uint64_t items, int ctas_per_sm) {
+    uint64_t need = (items + BLOCK - 1) / BLOCK;
+    uint64_t cap = (uint64_t)c->sm_count * (uint64_t)(ctas_per_sm > 0 ? ctas_per_sm : 1);
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+int32_t alloc_table(zkb_ctx* c, uint64_t n, Table* t) {
+    void* p = nullptr;
+    ZK_CUDA(c, cudaMallocAsync(&p, (size_t)n * 32, c->stream));
+    t->base = (uint4*)p;
+    t->n = n;
+    t->stride = n;
+    return ZKB_OK;
+}
+void free_table(zkb_ctx* c, Table* t) {
+    if (t->base) cudaFreeAsync(t->base, c->stream);
+    t->base = nullptr;
+    t->n = t->stride = 0;
+}
+int32_t ensure_stage(zkb_ctx* c, size_t bytes) {
+    if (c->stage_bytes >= bytes) return ZKB_OK;
+    if (c->stage) cudaFreeAsync(c->stage, c->stream);
+    c->stage = nullptr;
+    c->stage_bytes = 0;
+    ZK_CUDA(c, cudaMallocAsync(&c->stage, bytes, c->stream));
+    c->stage_bytes = bytes;
+    return ZKB_OK;
+}
+int32_t ensure_partials(zkb_ctx* c, size_t n_fe) {
+    if (c->partials_cap >= n_fe) return ZKB_OK;
+    if (c->d_partials) cudaFreeAsync(c->d_partials, c->stream);
+    c->d_partials = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&c->d_partials, n_fe * sizeof(Fe), c->stream));
+    c->partials_cap = n_fe;
+    return ZKB_OK;
+}
+
+Table* find_mle(zkb_ctx* c, zkb_mle h) {
+    auto it = c->mles.find(h);
+    return it == c->mles.end() ? nullptr : &it->second;
+}
+zkb_mle put_mle(zkb_ctx* c, const Table& t) {
+    zkb_mle h = c->next_handle++;
+    c->mles[h] = t;
+    return h;
+}
+
+// Wait for the mailbox flag to reach `seq` (spin on mapped host memory; a stream
+// query every few thousand spins turns a faulted kernel into an error instead of
+// a hang).
+int32_t wait_mailbox(zkb_ctx* c, unsigned int seq) {
+    uint32_t spins = 0;
+    while (*c->h_flag != seq) {
+        if ((++spins & 0x3fff) == 0) {
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess) {
+                if (*c->h_flag == seq) break;
+                ZK_FAIL(c, ZKB_ERR_CUDA, "mailbox: stream drained without a result");
+            }
+            if (e != cudaErrorNotReady) {
+                c->last_error = std::string("mailbox: ") + cudaGetErrorString(e);
+                return ZKB_ERR_CUDA;
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    asm volatile("" ::: "memory");  // results are read only after the flag
+    return ZKB_OK;
+}
+
+// Fill the FinishArgs of a reducing launch of `grid` CTAs returning `npts` sums.
+int32_t prep_finish(zkb_ctx* c, int grid, int npts, bool sharded, FinishArgs* f) {
+    ZK_TRY(ensure_partials(c, (size_t)grid * npts));
+    f->partials = c->d_partials;
+    f->ticket = c->d_ticket;
+    if (sharded) {
+        f->result = c->d_res;
+        f->result_wide = c->d_wide;
+        f->flag = nullptr;
+        f->seq = 0;
+    } else {
+        f->result = c->h_res;
+        f->result_wide = nullptr;
+        f->flag = c->h_flag;
+        f->seq = ++c->seq;
+    }
+    return ZKB_OK;
+}
+// Bring the `npts` sums of the launch prepared by prep_finish to the host.
+int32_t collect(zkb_ctx* c, int npts, bool sharded, const FinishArgs& f, Fe* out) {
+    if (!sharded) {
+        ZK_TRY(wait_mailbox(c, f.seq));
+        for (int p = 0; p < npts; ++p) out[p] = c->h_res[p];
+        return ZKB_OK;
+    }
+    // C1: exact integer sum of the ranks' residues on zero-extended limbs, reduced mod p on the host
+    ZK_NCCL(c, g_nccl.AllReduce(c->d_wide, c->d_wide, (size_t)npts * 8, ncclUint64, ncclSum, c->comm, c->stream));
+    ZK_CUDA(c, cudaMemcpyAsync(c->h_wide, c->d_wide, (size_t)npts * 8 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int p = 0; p < npts; ++p) out[p] = c->H.from_wide_limbs(c->h_wide + 8 * p);
+    return ZKB_OK;
+}
+
+int sc_occ(zkb_ctx* c, int fused, int kind, int D, int npts) {
+    char key[64];
+    snprintf(key, sizeof key, "%d/%d/%d/%d", fused, kind, D, npts);
+    auto it = c->occ_cache.find(key);
+    if (it != c->occ_cache.end()) return it->second;
+    int o = c->K->sc_occupancy(fused, kind, D, npts);
+    c->occ_cache[key] = o;
+    return o;
+}
+
+// --------------------------------------------------------------- SumPoly core
+int32_t sp_configure(zkb_ctx* c, SumPolyState* sp, int P, int D, int kind) {
+    sp->P = P;
+    sp->D = D;
+    sp->kind = kind;
+    sp->sel.clear();
+    sp->rest.clear();
+    const int T = P * D;
+    if (kind == KIND_XYZ) {
+        sp->kP = 1;
+        sp->kD = 2;
+        sp->npts = 3;
+        for (int t = 0; t < 3; ++t) sp->sel.push_back(t);
+        return ZKB_OK;
+    }
+    if (T > MAXT || D + 1 > MAXPTS || D < 1 || P < 1) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sumpoly: more than 16 tables or degree > 4");
+    sp->npts = D + 1;
+    if (c->mode == ZKB_MODE_COMPAT && !(P == 1 && D == 1)) {
+        // SumPoly::reduce adds products 0 and 1 of ProductPoly::reduce = factor0 * factor1 (composed_polynomial.rs:52-54,88-99)
+        if (P < 2 || D < 2) ZK_FAIL(c, ZKB_ERR_COMPAT_SHAPE, "compat mode needs >= 2 products of >= 2 factors");
+        sp->kP = 2;
+        sp->kD = 2;
+        for (int p = 0; p < 2; ++p)
+            for (int f = 0; f < 2; ++f) sp->sel.push_back(p * D + f);
+        for (int t = 0; t < T; ++t) {
+            bool used = (t / D < 2) && (t % D < 2);
+            if (!used) sp->rest.push_back(t);
+        }
+    } else {
+        sp->kP = P;
+        sp->kD = D;
+        for (int t = 0; t < T; ++t) sp->sel.push_back(t);
+    }
+    if (sc_occ(c, 0, sp->kind, sp->kD, sp->npts) <= 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sumpoly: no kernel for this (degree, points) shape");
+    return ZKB_OK;
+}
+
+void sp_release(zkb_ctx* c, SumPolyState* sp) {
+    for (auto& t : sp->work) free_table(c, &t);
+    for (auto& t : sp->gath) free_table(c, &t);
+    sp->work.clear();
+    sp->gath.clear();
+}
+void sp_reset(zkb_ctx* c, SumPolyState* sp) {
+    sp->state = 0;
+    sp->cur_n = sp->n0;
+    sp->sharded = c->comm != nullptr && c->world > 1;
+    for (auto& t : sp->gath) free_table(c, &t);
+    sp->gath.clear();
+}
+
+int32_t sp_round_evals(zkb_ctx* c, SumPolyState* sp, Fe* evals) {
+    if (sp->cur_n < 2) ZK_FAIL(c, ZKB_ERR_ARITY, "round_evals: no variable left");
+    ScArgs a;
+    std::memset(&a, 0, sizeof a);
+    for (size_t i = 0; i < sp->sel.size(); ++i) a.in[i] = sp->cur(sp->sel[i]).ref();
+    a.n_tables = (int)sp->sel.size();
+    a.n_products = sp->kP;
+    a.n_out = sp->cur_n;
+    const int grid = grid_for(c, sp->cur_n / 2, sc_occ(c, 0, sp->kind, sp->kD, sp->npts));
+    ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
+    if (!c->K->sc_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_eval: shape not instantiated");
+    ZK_TRY(check_launch(c, "k_sc_eval"));
+    return collect(c, sp->npts, sp->sharded, a.fin, evals);
+}
+
+int32_t sp_ensure_work(zkb_ctx* c, SumPolyState* sp) {
+    if (!sp->work.empty()) return ZKB_OK;
+    const int T = (int)sp->src.size();
+    sp->work.resize(T);
+    for (int t = 0; t < T; ++t) ZK_TRY(alloc_table(c, sp->n0 / 2 ? sp->n0 / 2 : 1, &sp->work[t]));
+    return ZKB_OK;
+}
+
+// C2: gather every rank's shard of every table and interleave to global order.
+int32_t sp_gather(zkb_ctx* c, SumPolyState* sp) {
+    const int T = (int)sp->src.size();
+    const uint64_t nl = sp->cur_n, G = (uint64_t)c->world;
+    ZK_TRY(ensure_stage(c, (size_t)(G + 1) * nl * 32));
+    uint4* send = (uint4*)c->stage;
+    uint4* recv = send + 2 * nl;
+    sp->gath.resize(T);
+    for (int t = 0; t < T; ++t) {
+        Table& cur = sp->cur(t);
+        ZK_CUDA(c, cudaMemcpyAsync(send, cur.base, nl * 16, cudaMemcpyDeviceToDevice, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(send + nl, cur.base + cur.stride, nl * 16, cudaMemcpyDeviceToDevice, c->stream));
+        ZK_NCCL(c, g_nccl.AllGather(send, recv, (size_t)nl * 32, ncclUint8, c->comm, c->stream));
+        Table g;
+        ZK_TRY(alloc_table(c, nl * G, &g));
+        TabRef gr{recv, nl};
+        c->K->interleave_shards(gr, 2 * nl, g.ref(), nl, (uint32_t)c->log2world, grid_for(c, nl * G, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_interleave_shards"));
+        sp->gath[t] = g;
+    }
+    sp->state = 2;
+    sp->cur_n = nl * G;
+    sp->sharded = false;
+    return ZKB_OK;
+}
+
+// Fold every table with r; if `evals` != NULL also return the next round's evaluations (one pass).
+int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, Fe* final_vals) {
+    if (sp->cur_n < 2) ZK_FAIL(c, ZKB_ERR_ARITY, "bind: no variable left");
+    if (sp->sharded && sp->cur_n <= (1ull << (c->gather_log2 < 1 ? 1 : c->gather_log2))) ZK_TRY(sp_gather(c, sp));
+    const int T = (int)sp->src.size();
+    if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
+    const uint64_t n_out = sp->cur_n / 2;
+    auto dst = [&](int t) -> Table& { return sp->state == 2 ? sp->gath[t] : sp->work[t]; };
+
+    if (n_out == 1 && !sp->sharded) {  // last bind: publish the bound values
+        FoldTablesArgs fa;
+        std::memset(&fa, 0, sizeof fa);
+        for (int t = 0; t < T; ++t) {
+            fa.in[t] = sp->cur(t).ref();
+            fa.out[t] = dst(t).ref();
+        }
+        fa.n_tables = T;
+        fa.n_out = 1;
+        fa.r = r;
+        unsigned int seq = ++c->seq;
+        c->K->final_bind(fa, c->h_res, c->h_flag, seq, c->stream);
+        ZK_TRY(check_launch(c, "k_final_bind"));
+        if (sp->state == 0) sp->state = 1;
+        sp->cur_n = 1;
+        ZK_TRY(wait_mailbox(c, seq));
+        if (final_vals)
+            for (int t = 0; t < T; ++t) final_vals[t] = c->h_res[t];
+        if (evals) ZK_FAIL(c, ZKB_ERR_ARITY, "bind_and_next: no next round after the last variable");
+        return ZKB_OK;
+    }
+
+    if (!sp->rest.empty() || !evals || n_out < 2) {
+        // tables outside the round kernel (compat mode) or a plain fold request
+        FoldTablesArgs fa;
+        std::memset(&fa, 0, sizeof fa);
+        int k = 0;
+        const bool all = (!evals || n_out < 2);
+        for (int t = 0; t < T; ++t) {
+            bool in_rest = false;
+            for (int x : sp->rest) in_rest |= (x == t);
+            if (!all && !in_rest) continue;
+            fa.in[k] = sp->cur(t).ref();
+            fa.out[k] = dst(t).ref();
+            ++k;
+        }
+        fa.n_tables = k;
+        fa.n_out = n_out;
+        fa.r = r;
+        c->K->fold_tables(fa, grid_for(c, n_out * (uint64_t)k, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_fold_tables"));
+        if (all) {
+            if (sp->state == 0) sp->state = 1;
+            sp->cur_n = n_out;
+            if (evals) return sp_round_evals(c, sp, evals);  // only reached for sharded 1-entry shards
+            return ZKB_OK;
+        }
+    }
+    ScArgs a;
+    std::memset(&a, 0, sizeof a);
+    for (size_t i = 0; i < sp->sel.size(); ++i) {
+        a.in[i] = sp->cur(sp->sel[i]).ref();
+        a.out[i] = dst(sp->sel[i]).ref();
+    }
+    a.n_tables = (int)sp->sel.size();
+    a.n_products = sp->kP;
+    a.n_out = n_out;
+    a.r = r;
+    const int grid = grid_for(c, n_out / 2, sc_occ(c, 1, sp->kind, sp->kD, sp->npts));
+    ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
+    if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
+    ZK_TRY(check_launch(c, "k_sc_fold_eval"));
+    if (sp->state == 0) sp->state = 1;
+    sp->cur_n = n_out;
+    return collect(c, sp->npts, sp->sharded, a.fin, evals);
+}
+
+int32_t sp_final_values(zkb_ctx* c, SumPolyState* sp, Fe* vals) {
+    if (sp->cur_n != 1) ZK_FAIL(c, ZKB_ERR_ARITY, "final_values: variables left to bind");
+    const int T = (int)sp->src.size();
+    GatherArgs g;
+    std::memset(&g, 0, sizeof g);
+    for (int t = 0; t < T; ++t) g.t[t] = sp->cur(t).ref();
+    g.n = T;
+    g.idx = 0;
+    g.out = c->d_res;
+    launch_gather_elems(g, c->stream);
+    ZK_TRY(check_launch(c, "k_gather_elems"));
+    ZK_CUDA(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(Fe) * T, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < T; ++t) vals[t] = c->h_res[t];
+    return ZKB_OK;
+}
+
+// The composed sumcheck loop (sum_check_protocol.rs:86-115) over a configured state.
+// coeffs: rounds x slots elements; returns challenges and the T bound values.
+int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, uint64_t* coeffs, int32_t* lens,
+                 uint64_t* challenges, Fe* final_vals, bool as_evals) {
+    sp_reset(c, sp);
+    const int n_rounds = ilog2_u64(sp->n0) + (sp->sharded ? c->log2world : 0);
+    const RoundInterpolator& ip = c->interp[sp->npts];
+    Fe evals[MAXPTS], co[MAXPTS];
+    if (n_rounds == 0) return sp_final_values(c, sp, final_vals);
+    ZK_TRY(sp_round_evals(c, sp, evals));
+    for (int k = 0; k < n_rounds; ++k) {
+        int len;
+        if (as_evals) {  // plain sumcheck: the message is the evaluations themselves (:168-175)
+            len = sp->npts;
+            for (int i = 0; i < len; ++i) co[i] = evals[i];
+        } else {
+            len = ip.interpolate(evals, co);
+        }
+        tr->append_elements(co, (size_t)len);
+        if (lens) lens[k] = len;
+        for (int i = 0; i < slots; ++i) fe_to_u64x4(i < len ? co[i] : c->H.zero(), coeffs + ((size_t)k * slots + i) * 4);
+        Fe r = tr->challenge();
+        if (challenges) fe_to_u64x4(r, challenges + (size_t)k * 4);
+        ZK_TRY(sp_bind_and_next(c, sp, r, k + 1 < n_rounds ? evals : nullptr, final_vals));
+    }
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------ MLE helpers
+int32_t upload_aos(zkb_ctx* c, const uint64_t* aos, uint64_t n_src, uint64_t first, uint64_t stride, uint64_t n_dst,
+                   int conv, Table* out) {
+    ZK_TRY(alloc_table(c, n_dst, out));
+    // chunked: stage up to 2^21 source elements (64 MiB) at a time
+    const uint64_t chunk_dst = stride > 1 ? n_dst : (n_dst < (1ull << 21) ? n_dst : (1ull << 21));
+    (void)n_src;
+    if (stride > 1) {
+        // strided shard: copy only this rank's elements with a 2D copy (32-byte rows)
+        ZK_TRY(ensure_stage(c, (size_t)n_dst * 32));
+        ZK_CUDA(c, cudaMemcpy2DAsync(c->stage, 32, (const uint8_t*)aos + first * 32, (size_t)stride * 32, 32, n_dst,
+                                     cudaMemcpyHostToDevice, c->stream));
+        c->K->aos_to_planar(c->stage, out->ref(), n_dst, 0, 1, conv, grid_for(c, n_dst, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_aos_to_planar"));
+        return ZKB_OK;
+    }
+    ZK_TRY(ensure_stage(c, (size_t)chunk_dst * 32));
+    for (uint64_t off = 0; off < n_dst; off += chunk_dst) {
+        const uint64_t m = (n_dst - off < chunk_dst) ? n_dst - off : chunk_dst;
+        ZK_CUDA(c, cudaMemcpyAsync(c->stage, (const uint8_t*)aos + (first + off) * 32, (size_t)m * 32, cudaMemcpyHostToDevice,
+                                   c->stream));
+        TabRef dst{out->base + off, out->stride};
+        c->K->aos_to_planar(c->stage, dst, m, 0, 1, conv, grid_for(c, m, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_aos_to_planar"));
+    }
+    return ZKB_OK;
+}
+
+int32_t download_aos(zkb_ctx* c, const Table& t, void* host, int conv) {
+    const uint64_t chunk = t.n < (1ull << 21) ? t.n : (1ull << 21);
+    ZK_TRY(ensure_stage(c, (size_t)chunk * 32));
+    for (uint64_t off = 0; off < t.n; off += chunk) {
+        const uint64_t m = (t.n - off < chunk) ? t.n - off : chunk;
+        TabRef src{t.base + off, t.stride};
+        c->K->planar_to_aos(src, c->stage, m, conv, grid_for(c, m, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_planar_to_aos"));
+        ZK_CUDA(c, cudaMemcpyAsync((uint8_t*)host + off * 32, c->stage, (size_t)m * 32, cudaMemcpyDeviceToHost, c->stream));
+    }
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ZKB_OK;
+}
+
+// evaluate / multi_partial_evaluate: bind the k leading variables of `src` into a fresh table.
+int32_t multi_fold(zkb_ctx* c, const Table& src, const Fe* rs, uint32_t k, Table* out) {
+    const int nv = ilog2_u64(src.n);
+    if ((int)k > nv) ZK_FAIL(c, ZKB_ERR_ARITY, "Invalid number of values");
+    Table w;
+    if (k == 0) {
+        ZK_TRY(alloc_table(c, src.n, &w));
+        ZK_CUDA(c, cudaMemcpyAsync(w.base, src.base, src.n * 16, cudaMemcpyDeviceToDevice, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(w.base + w.stride, src.base + src.stride, src.n * 16, cudaMemcpyDeviceToDevice, c->stream));
+        *out = w;
+        return ZKB_OK;
+    }
+    ZK_TRY(alloc_table(c, src.n / 2, &w));
+    uint64_t n = src.n;
+    for (uint32_t i = 0; i < k; ++i) {
+        FoldTablesArgs fa;
+        std::memset(&fa, 0, sizeof fa);
+        fa.in[0] = i == 0 ? src.ref() : w.ref();
+        fa.out[0] = w.ref();
+        fa.n_tables = 1;
+        fa.n_out = n / 2;
+        fa.r = rs[i];
+        c->K->fold_tables(fa, grid_for(c, n / 2, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_fold_tables"));
+        n /= 2;
+    }
+    w.n = n;
+    *out = w;
+    return ZKB_OK;
+}
+
+int32_t read_elems(zkb_ctx* c, const Table& t, uint64_t first, int count, Fe* out) {
+    GatherArgs g;
+    for (int i = 0; i < count; i += MAXT) {
+        std::memset(&g, 0, sizeof g);
+        int m = count - i < MAXT ? count - i : MAXT;
+        for (int j = 0; j < m; ++j) {
+            g.t[j] = TabRef{t.base + first + i + j, t.stride};
+        }
+        g.n = m;
+        g.idx = 0;
+        g.out = c->d_res;
+        launch_gather_elems(g, c->stream);
+        ZK_TRY(check_launch(c, "k_gather_elems"));
+        ZK_CUDA(c, cudaMemcpyAsync(c->h_res, c->d_res, sizeof(Fe) * m, cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int j = 0; j < m; ++j) out[i + j] = c->h_res[j];
+    }
+    return ZKB_OK;
+}
+
+// Full evaluation of a (possibly sharded) table at k = log2(global size) values.
+int32_t evaluate_table(zkb_ctx* c, const Table& src, const Fe* rs, uint32_t k, Fe* out) {
+    const int nv_local = ilog2_u64(src.n);
+    const bool sharded = c->comm && c->world > 1;
+    const int nv = nv_local + (sharded ? c->log2world : 0);
+    if ((int)k != nv) ZK_FAIL(c, ZKB_ERR_ARITY, "Invalid number of values");
+    Table w;
+    ZK_TRY(multi_fold(c, src, rs, (uint32_t)nv_local, &w));
+    Fe v;
+    int32_t st = read_elems(c, w, 0, 1, &v);
+    free_table(c, &w);
+    ZK_TRY(st);
+    if (sharded) {
+        // the remaining log2(world) variables index the rank: gather the per-rank values, finish on the host
+        Fe* dbuf = c->d_res;
+        ZK_CUDA(c, cudaMemcpyAsync(dbuf + c->world, &v, sizeof(Fe), cudaMemcpyHostToDevice, c->stream));
+        ZK_NCCL(c, g_nccl.AllGather(dbuf + c->world, dbuf, sizeof(Fe), ncclUint8, c->comm, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(c->h_res, dbuf, sizeof(Fe) * c->world, cudaMemcpyDeviceToHost, c->stream));
+        ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::vector<Fe> vals(c->h_res, c->h_res + c->world);
+        for (int i = 0; i < c->log2world; ++i) {
+            size_t h = vals.size() / 2;
+            const Fe& r = rs[nv_local + i];
+            for (size_t j = 0; j < h; ++j) vals[j] = c->H.add(vals[j], c->H.mul(r, c->H.sub(vals[j + h], vals[j])));
+            vals.resize(h);
+        }
+        v = vals[0];
+    }
+    *out = v;
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------- GKR core
+uint32_t layer_rounds(uint32_t gates) {
+    int nb = ilog2_u64(2ull * gates);
+    if (nb < 1) nb = 1;
+    return 2u * (uint32_t)nb;
+}
+
+int32_t circuit_check_shape(zkb_ctx* c, uint32_t n_layers, const uint32_t* g) {
+    if (n_layers < 1) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: no layers");
+    if (g[n_layers - 1] != 1 && g[n_layers - 1] != 2) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: output layer must have 1 or 2 gates (gkr_protocol.rs:235)");
+    for (uint32_t l = 0; l + 1 < n_layers; ++l)
+        if (g[l] != 2 * g[l + 1]) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: each layer must have twice the gates of the next (gkr_circuit.rs:76-78)");
+    return ZKB_OK;
+}
+
+int32_t circuit_run(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont, uint64_t n_inputs) {
+    if (n_inputs != 2ull * cs->gates[0]) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: inputs must be 2 x gates of the first layer");
+    // inputs: AoS Montgomery -> planar
+    if (cs->aos_stage_bytes < n_inputs * 32) {
+        if (cs->aos_stage) cudaFreeAsync(cs->aos_stage, c->stream);
+        ZK_CUDA(c, cudaMallocAsync(&cs->aos_stage, n_inputs * 32, c->stream));
+        cs->aos_stage_bytes = n_inputs * 32;
+    }
+    ZK_CUDA(c, cudaMemcpyAsync(cs->aos_stage, inputs_mont, n_inputs * 32, cudaMemcpyHostToDevice, c->stream));
+    c->K->aos_to_planar(cs->aos_stage, cs->inputs.ref(), n_inputs, 0, 1, 0, grid_for(c, n_inputs, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_aos_to_planar"));
+    for (int l = 0; l < cs->L; ++l) {
+        const Table& in = l == 0 ? cs->inputs : cs->vals[l - 1];
+        c->K->layer_eval(in.ref(), cs->vals[l].ref(), cs->d_ops + cs->opoff[l], cs->gates[l], grid_for(c, cs->gates[l], 8), c->stream);
+        ZK_TRY(check_launch(c, "k_layer_eval"));
+    }
+    return ZKB_OK;
+}
+
+int32_t eq_tables(zkb_ctx* c, const Fe* r, int n, Table* hi, Table* lo, int* n_lo_out) {
+    ChalList cl;
+    std::memset(&cl, 0, sizeof cl);
+    for (int i = 0; i < n; ++i) cl.r[i] = r[i];
+    const int n_hi = n / 2, n_lo = n - n_hi;
+    c->K->eq_split(cl, n, n_hi, hi->ref(), lo->ref(), grid_for(c, (1ull << n_hi) + (1ull << n_lo), 8), c->stream);
+    ZK_TRY(check_launch(c, "k_eq_split"));
+    *n_lo_out = n_lo;
+    return ZKB_OK;
+}
+
+// One phase (nb rounds) of the two-phase layer sumcheck over X*Y + Z.
+int32_t xyz_phase(zkb_ctx* c, CircuitState* cs, const Table& X, const Table& Y, const Table& Z, uint64_t nw,
+                  TranscriptImpl* tr, uint64_t* coeffs, int32_t* lens, uint64_t* chals, Fe* point, Fe* x_final) {
+    SumPolyState* sp = &cs->sp;
+    sp->src.resize(3);
+    sp->src[0] = X;
+    sp->src[1] = Y;
+    sp->src[2] = Z;
+    for (auto& t : sp->src) t.n = nw;
+    sp->n0 = nw;
+    sp_reset(c, sp);
+    sp->sharded = false;  // GKR layers are never sharded (replicas only)
+    const int nb = ilog2_u64(nw);
+    const RoundInterpolator& ip = c->interp[3];
+    Fe evals[3], co[3], fin[3];
+    ZK_TRY(sp_round_evals(c, sp, evals));
+    for (int k = 0; k < nb; ++k) {
+        int len = ip.interpolate(evals, co);
+        tr->append_elements(co, (size_t)len);
+        lens[k] = len;
+        for (int i = 0; i < 3; ++i) fe_to_u64x4(i < len ? co[i] : c->H.zero(), coeffs + ((size_t)k * 3 + i) * 4);
+        Fe r = tr->challenge();
+        point[k] = r;
+        if (chals) fe_to_u64x4(r, chals + (size_t)k * 4);
+        ZK_TRY(sp_bind_and_next(c, sp, r, k + 1 < nb ? evals : nullptr, fin));
+    }
+    *x_final = fin[0];
+    return ZKB_OK;
+}
+
+struct GkrLayerCtx {
+    Fe r0, alpha, beta;
+    std::vector<Fe> rb, rc;
+};
+
+int32_t gkr_prove_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont, uint64_t n_inputs, uint64_t* w0_out,
+                       uint64_t* coeffs, int32_t* lens, uint64_t* challenges, uint64_t* claimed, uint64_t* final_openings,
+                       uint32_t* n_rounds_out) {
+    ZK_TRY(circuit_run(c, cs, inputs_mont, n_inputs));
+    const int L = cs->L;
+    TranscriptImpl tr;
+    tr.H = c->H;
+    // w_0 padded to two entries (gkr_protocol.rs:34-39); initiate_protocol (:229-241)
+    Fe w0[2] = {c->H.zero(), c->H.zero()};
+    ZK_TRY(read_elems(c, cs->vals[L - 1], 0, (int)cs->gates[L - 1], w0));
+    fe_to_u64x4(w0[0], w0_out);
+    fe_to_u64x4(w0[1], w0_out + 4);
+    tr.append_elements(w0, 2);
+    Fe r0 = tr.challenge();
+    Fe m0 = c->H.add(w0[0], c->H.mul(r0, c->H.sub(w0[1], w0[0])));
+    tr.append_elements(&m0, 1);
+
+    Fe alpha = c->H.zero(), beta = c->H.zero();
+    std::vector<Fe> rb, rc;
+    size_t round_base = 0;
+    Fe o1 = c->H.zero(), o2 = c->H.zero();
+    for (int idx = 0; idx < L; ++idx) {
+        const int l = L - 1 - idx;
+        const uint64_t G = cs->gates[l], nw = 2 * G;
+        const int nb = ilog2_u64(nw);
+        const Table& W = l == 0 ? cs->inputs : cs->vals[l - 1];
+        GkrP1Args p1;
+        std::memset(&p1, 0, sizeof p1);
+        p1.W = W.ref();
+        p1.H1 = cs->H1.ref();
+        p1.HA2 = cs->HA2.ref();
+        p1.coef = cs->coef.ref();
+        p1.ops = cs->d_ops + cs->opoff[l];
+        p1.n_gates = G;
+        p1.first_layer = idx == 0;
+        p1.r0 = r0;
+        p1.alpha = alpha;
+        p1.beta = beta;
+        if (idx > 0) {
+            if ((1ull << rb.size()) != G) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "gkr: challenge count does not match the layer width");
+            int n_lo = 0;
+            ZK_TRY(eq_tables(c, rb.data(), (int)rb.size(), &cs->eq[0], &cs->eq[1], &n_lo));
+            ZK_TRY(eq_tables(c, rc.data(), (int)rc.size(), &cs->eq[2], &cs->eq[3], &n_lo));
+            p1.eb_hi = cs->eq[0].ref();
+            p1.eb_lo = cs->eq[1].ref();
+            p1.ec_hi = cs->eq[2].ref();
+            p1.ec_lo = cs->eq[3].ref();
+            p1.n_lo = n_lo;
+        }
+        c->K->gkr_phase1(p1, grid_for(c, G, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_gkr_phase1"));
+        std::vector<Fe> u(nb), v(nb);
+        Fe Wu, Wv;
+        ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + round_base * 12, lens + round_base,
+                         challenges ? challenges + round_base * 4 : nullptr, u.data(), &Wu));
+        // phase 2: b bound to u
+        int n_lo_u = 0;
+        ZK_TRY(eq_tables(c, u.data(), nb, &cs->eq[4], &cs->eq[5], &n_lo_u));
+        GkrP2Args p2;
+        std::memset(&p2, 0, sizeof p2);
+        p2.C = cs->H1.ref();
+        p2.D = cs->HA2.ref();
+        p2.coef = cs->coef.ref();
+        p2.eu_hi = cs->eq[4].ref();
+        p2.eu_lo = cs->eq[5].ref();
+        p2.n_lo = n_lo_u;
+        p2.ops = cs->d_ops + cs->opoff[l];
+        p2.n_gates = G;
+        p2.Wu = Wu;
+        c->K->gkr_phase2(p2, grid_for(c, G, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_gkr_phase2"));
+        ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + (round_base + nb) * 12, lens + round_base + nb,
+                         challenges ? challenges + (round_base + nb) * 4 : nullptr, v.data(), &Wv));
+        round_base += 2 * (size_t)nb;
+        rb = u;
+        rc = v;
+        o1 = Wu;
+        o2 = Wv;
+        if (idx < L - 1) {  // :80-89
+            tr.append_elements(&o1, 1);
+            alpha = tr.challenge();
+            tr.append_elements(&o2, 1);
+            beta = tr.challenge();
+            fe_to_u64x4(o1, claimed + (size_t)idx * 8);
+            fe_to_u64x4(o2, claimed + (size_t)idx * 8 + 4);
+        }
+    }
+    fe_to_u64x4(o1, final_openings);
+    fe_to_u64x4(o2, final_openings + 4);
+    if (n_rounds_out) *n_rounds_out = (uint32_t)round_base;
+    return ZKB_OK;
+}
+
+// gkr_verify (sum_check_protocol.rs:117-150) on the host.
+bool sc_verify_rounds(const HostField& H, TranscriptImpl* tr, uint32_t n_rounds, uint32_t slots, const uint64_t* coeffs,
+                      const int32_t* lens, Fe claim, Fe* final_claim, Fe* chals) {
+    const Fe one = H.one();
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        Fe co[MAXPTS + 3];
+        const int len = lens[k];
+        for (int i = 0; i < len; ++i) co[i] = fe_from_u64x4(coeffs + ((size_t)k * slots + i) * 4);
+        Fe p0 = uni_evaluate(H, co, len, H.zero());
+        Fe p1 = uni_evaluate(H, co, len, one);
+        if (!H.eq(H.add(p0, p1), claim)) return false;
+        tr->append_elements(co, (size_t)len);
+        Fe r = tr->challenge();
+        chals[k] = r;
+        claim = uni_evaluate(H, co, len, r);
+    }
+    *final_claim = claim;
+    return true;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* zkb_strerror(int32_t s) {
+    switch (s) {
+        case ZKB_OK: return "ok";
+        case ZKB_ERR_BAD_ARG: return "bad argument";
+        case ZKB_ERR_NOT_POW2: return "Invalid evaluations";
+        case ZKB_ERR_ARITY: return "Invalid number of values";
+        case ZKB_ERR_LENGTH_MISMATCH: return "all evaluations must have same length";
+        case ZKB_ERR_DEGREE_MISMATCH: return "all product polys must have same degree";
+        case ZKB_ERR_CUDA: return "CUDA error";
+        case ZKB_ERR_NCCL: return "NCCL error";
+        case ZKB_ERR_OOM: return "out of device memory";
+        case ZKB_ERR_UNSUPPORTED: return "shape outside the instantiated kernels";
+        case ZKB_ERR_COMPAT_SHAPE: return "compat mode needs >= 2 products of >= 2 factors";
+        case ZKB_ERR_CIRCUIT_SHAPE: return "circuit shape not expressible by the reference wiring";
+    }
+    return "unknown status";
+}
+const char* zkb_version(void) { return "zkb200 0.1 (sm_100a)"; }
+
+int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx** out) {
+    if (!out) return ZKB_ERR_BAD_ARG;
+    *out = nullptr;
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || (mode != ZKB_MODE_COMPAT && mode != ZKB_MODE_FULL)) return ZKB_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return ZKB_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ZKB_ERR_CUDA;
+    std::unique_ptr<zkb_ctx> c(new zkb_ctx);
+    c->field = field_id;
+    c->device = device;
+    c->mode = mode;
+    c->K = K;
+    c->H.K = K;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ZKB_ERR_CUDA;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return ZKB_ERR_CUDA;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    void* hp = nullptr;
+    if (cudaHostAlloc(&hp, sizeof(Fe) * 64 + 64, cudaHostAllocMapped) != cudaSuccess) return ZKB_ERR_CUDA;
+    std::memset(hp, 0, sizeof(Fe) * 64 + 64);
+    c->h_res = (Fe*)hp;
+    c->h_flag = (volatile unsigned int*)((uint8_t*)hp + sizeof(Fe) * 64);
+    if (cudaHostAlloc((void**)&c->h_wide, sizeof(unsigned long long) * 8 * MAXPTS, cudaHostAllocDefault) != cudaSuccess) return ZKB_ERR_CUDA;
+    if (cudaMalloc((void**)&c->d_ticket, sizeof(unsigned int)) != cudaSuccess) return ZKB_ERR_CUDA;
+    cudaMemset(c->d_ticket, 0, sizeof(unsigned int));
+    if (cudaMalloc((void**)&c->d_res, sizeof(Fe) * 64) != cudaSuccess) return ZKB_ERR_CUDA;
+    if (cudaMalloc((void**)&c->d_wide, sizeof(unsigned long long) * 8 * MAXPTS) != cudaSuccess) return ZKB_ERR_CUDA;
+    for (int n = 2; n <= MAXPTS; ++n) c->interp[n].init(c->H, n);
+    *out = c.release();
+    return ZKB_OK;
+}
+
+int32_t zkb_ctx_destroy(zkb_ctx* c) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->sps) sp_release(c, kv.second.get());
+    for (auto& kv : c->circs) {
+        CircuitState* cs = kv.second.get();
+        sp_release(c, &cs->sp);
+        free_table(c, &cs->inputs);
+        for (auto& t : cs->vals) free_table(c, &t);
+        free_table(c, &cs->H1);
+        free_table(c, &cs->HA2);
+        free_table(c, &cs->coef);
+        for (auto& t : cs->eq) free_table(c, &t);
+        if (cs->d_ops) cudaFreeAsync(cs->d_ops, c->stream);
+        if (cs->aos_stage) cudaFreeAsync(cs->aos_stage, c->stream);
+    }
+    for (auto& kv : c->mles) free_table(c, &kv.second);
+    if (c->stage) cudaFreeAsync(c->stage, c->stream);
+    if (c->d_partials) cudaFreeAsync(c->d_partials, c->stream);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->d_ticket);
+    cudaFree(c->d_res);
+    cudaFree(c->d_wide);
+    cudaFreeHost(c->h_res);
+    cudaFreeHost(c->h_wide);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return ZKB_OK;
+}
+const char* zkb_ctx_last_error(const zkb_ctx* c) { return c ? c->last_error.c_str() : "null ctx"; }
+void* zkb_ctx_stream(const zkb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t zkb_ctx_launch_count(const zkb_ctx* c) { return c ? c->launches : 0; }
+int32_t zkb_ctx_sync(zkb_ctx* c) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ZKB_OK;
+}
+
+int32_t zkb_comm_unique_id(uint8_t out[128]) {
+    if (!g_nccl.load()) return ZKB_ERR_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return ZKB_ERR_NCCL;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out, &id, 128);
+    return ZKB_OK;
+}
+int32_t zkb_ctx_comm_init(zkb_ctx* c, int32_t rank, int32_t world, const uint8_t unique_id[128]) {
+    if (!c || world < 1 || rank < 0 || rank >= world || !is_pow2((uint64_t)world)) return ZKB_ERR_BAD_ARG;
+    if (world == 1) return ZKB_OK;
+    if (!g_nccl.load()) ZK_FAIL(c, ZKB_ERR_NCCL, "cannot load libnccl.so.2");
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, 128);
+    ZK_CUDA(c, cudaSetDevice(c->device));
+    ZK_NCCL(c, g_nccl.CommInitRank(&c->comm, world, id, rank));
+    c->rank = rank;
+    c->world = world;
+    c->log2world = ilog2_u64((uint64_t)world);
+    return ZKB_OK;
+}
+int32_t zkb_ctx_set_gather_threshold(zkb_ctx* c, uint32_t log2_local_entries) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    c->gather_log2 = log2_local_entries < 1 ? 1 : log2_local_entries;
+    return ZKB_OK;
+}
+
+// --------------------------------------------------------------- MultilinearPoly
+int32_t zkb_mle_upload(zkb_ctx* c, const uint64_t* aos, uint64_t len, zkb_mle* out) {
+    if (!c || !aos || !out) return ZKB_ERR_BAD_ARG;
+    if (!is_pow2(len)) ZK_FAIL(c, ZKB_ERR_NOT_POW2, "Invalid evaluations");
+    Table t;
+    ZK_TRY(upload_aos(c, aos, len, 0, 1, len, 0, &t));
+    *out = put_mle(c, t);
+    return ZKB_OK;
+}
+int32_t zkb_mle_upload_shard(zkb_ctx* c, const uint64_t* aos, uint64_t len_full, zkb_mle* out) {
+    if (!c || !aos || !out) return ZKB_ERR_BAD_ARG;
+    if (!is_pow2(len_full) || len_full < (uint64_t)c->world * 2) ZK_FAIL(c, ZKB_ERR_NOT_POW2, "Invalid evaluations");
+    Table t;
+    ZK_TRY(upload_aos(c, aos, len_full, (uint64_t)c->rank, (uint64_t)c->world, len_full / c->world, 0, &t));
+    *out = put_mle(c, t);
+    return ZKB_OK;
+}
+int32_t zkb_mle_generate(zkb_ctx* c, uint64_t seed, uint64_t table_id, uint32_t n_vars, zkb_mle* out) {
+    if (!c || !out || n_vars > 40) return ZKB_ERR_BAD_ARG;
+    if ((int)n_vars < c->log2world + 1 && c->world > 1) return ZKB_ERR_BAD_ARG;
+    const uint64_t n_local = (1ull << n_vars) >> c->log2world;
+    Table t;
+    ZK_TRY(alloc_table(c, n_local, &t));
+    c->K->generate(t.ref(), n_local, seed, table_id, (uint64_t)c->rank, (uint64_t)c->world, grid_for(c, n_local, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_generate"));
+    *out = put_mle(c, t);
+    return ZKB_OK;
+}
+int32_t zkb_mle_download(zkb_ctx* c, zkb_mle m, uint64_t* aos) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t || !aos) return ZKB_ERR_BAD_ARG;
+    return download_aos(c, *t, aos, 0);
+}
+int32_t zkb_mle_download_canonical(zkb_ctx* c, zkb_mle m, uint8_t* bytes) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t || !bytes) return ZKB_ERR_BAD_ARG;
+    return download_aos(c, *t, bytes, 2);
+}
+int32_t zkb_mle_clone(zkb_ctx* c, zkb_mle m, zkb_mle* out) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t || !out) return ZKB_ERR_BAD_ARG;
+    Table w;
+    ZK_TRY(multi_fold(c, *t, nullptr, 0, &w));
+    *out = put_mle(c, w);
+    return ZKB_OK;
+}
+int32_t zkb_mle_free(zkb_ctx* c, zkb_mle m) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t) return ZKB_ERR_BAD_ARG;
+    free_table(c, t);
+    c->mles.erase(m);
+    return ZKB_OK;
+}
+int32_t zkb_mle_num_vars(zkb_ctx* c, zkb_mle m, uint32_t* n_vars) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t || !n_vars) return ZKB_ERR_BAD_ARG;
+    *n_vars = (uint32_t)ilog2_u64(t->n);
+    return ZKB_OK;
+}
+int32_t zkb_mle_partial_evaluate(zkb_ctx* c, zkb_mle in, uint32_t bit, const uint64_t value[4], zkb_mle* out) {
+    Table* t = c ? find_mle(c, in) : nullptr;
+    if (!t || !value || !out) return ZKB_ERR_BAD_ARG;
+    const int nv = ilog2_u64(t->n);
+    if ((int)bit >= nv) ZK_FAIL(c, ZKB_ERR_ARITY, "partial_evaluate: bit out of range");
+    Table w;
+    ZK_TRY(alloc_table(c, t->n / 2, &w));
+    c->K->fold(t->ref(), w.ref(), t->n / 2, (uint32_t)(nv - 1 - (int)bit), fe_from_u64x4(value), grid_for(c, t->n / 2, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_fold"));
+    *out = put_mle(c, w);
+    return ZKB_OK;
+}
+int32_t zkb_mle_multi_partial_evaluate(zkb_ctx* c, zkb_mle in, const uint64_t* values, uint32_t k, zkb_mle* out) {
+    Table* t = c ? find_mle(c, in) : nullptr;
+    if (!t || (!values && k) || !out) return ZKB_ERR_BAD_ARG;
+    std::vector<Fe> rs(k);
+    for (uint32_t i = 0; i < k; ++i) rs[i] = fe_from_u64x4(values + 4 * i);
+    Table w;
+    ZK_TRY(multi_fold(c, *t, rs.data(), k, &w));
+    *out = put_mle(c, w);
+    return ZKB_OK;
+}
+int32_t zkb_mle_evaluate(zkb_ctx* c, zkb_mle m, const uint64_t* values, uint32_t k, uint64_t out[4]) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t || (!values && k) || !out) return ZKB_ERR_BAD_ARG;
+    std::vector<Fe> rs(k);
+    for (uint32_t i = 0; i < k; ++i) rs[i] = fe_from_u64x4(values + 4 * i);
+    Fe v;
+    ZK_TRY(evaluate_table(c, *t, rs.data(), k, &v));
+    fe_to_u64x4(v, out);
+    return ZKB_OK;
+}
+int32_t zkb_mle_sum_halves(zkb_ctx* c, zkb_mle m, uint64_t out[8]) {
+    Table* t = c ? find_mle(c, m) : nullptr;
+    if (!t || !out) return ZKB_ERR_BAD_ARG;
+    if (t->n < 2) ZK_FAIL(c, ZKB_ERR_ARITY, "sum_halves: table has no variable");
+    SumPolyState sp;
+    ZK_TRY(sp_configure(c, &sp, 1, 1, KIND_PROD));
+    sp.src.push_back(*t);
+    sp.n0 = t->n;
+    sp_reset(c, &sp);
+    Fe ev[2];
+    ZK_TRY(sp_round_evals(c, &sp, ev));
+    fe_to_u64x4(ev[0], out);
+    fe_to_u64x4(ev[1], out + 4);
+    return ZKB_OK;
+}
+int32_t zkb_mle_scale(zkb_ctx* c, zkb_mle in, const uint64_t value[4], zkb_mle* out) {
+    Table* t = c ? find_mle(c, in) : nullptr;
+    if (!t || !value || !out) return ZKB_ERR_BAD_ARG;
+    Table w;
+    ZK_TRY(alloc_table(c, t->n, &w));
+    TabRef none{nullptr, 0};
+    c->K->axpby(t->ref(), none, w.ref(), t->n, fe_from_u64x4(value), c->H.zero(), grid_for(c, t->n, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_axpby"));
+    *out = put_mle(c, w);
+    return ZKB_OK;
+}
+int32_t zkb_mle_binary(zkb_ctx* c, zkb_mle a, zkb_mle b, int32_t op, zkb_mle* out) {
+    Table* x = c ? find_mle(c, a) : nullptr;
+    Table* y = c ? find_mle(c, b) : nullptr;
+    if (!x || !y || !out || op < ZKB_OP_ADD || op > ZKB_OP_SUB) return ZKB_ERR_BAD_ARG;
+    if (x->n != y->n) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "all evaluations must have same length");
+    Table w;
+    ZK_TRY(alloc_table(c, x->n, &w));
+    const int kop = op == ZKB_OP_ADD ? 0 : (op == ZKB_OP_SUB ? 1 : 2);
+    c->K->vec_op(x->ref(), y->ref(), w.ref(), x->n, kop, grid_for(c, x->n, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_vec_op"));
+    *out = put_mle(c, w);
+    return ZKB_OK;
+}
+int32_t zkb_mle_tensor(zkb_ctx* c, zkb_mle a, zkb_mle b, int32_t op, zkb_mle* out) {
+    Table* x = c ? find_mle(c, a) : nullptr;
+    Table* y = c ? find_mle(c, b) : nullptr;
+    if (!x || !y || !out || (op != ZKB_OP_ADD && op != ZKB_OP_MUL)) return ZKB_ERR_BAD_ARG;
+    Table w;
+    ZK_TRY(alloc_table(c, x->n * y->n, &w));
+    c->K->tensor(x->ref(), y->ref(), w.ref(), x->n, y->n, op == ZKB_OP_ADD ? 0 : 1, grid_for(c, x->n * y->n, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_tensor"));
+    *out = put_mle(c, w);
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------ ProductPoly / SumPoly
+int32_t zkb_sumpoly_create(zkb_ctx* c, const zkb_mle* tables, uint32_t n_products, uint32_t degree, zkb_sp* out) {
+    if (!c || !tables || !out || n_products < 1 || degree < 1) return ZKB_ERR_BAD_ARG;
+    if (c->mode == ZKB_MODE_COMPAT && (n_products < 2 || degree < 2))
+        ZK_FAIL(c, ZKB_ERR_COMPAT_SHAPE, "compat mode needs >= 2 products of >= 2 factors");
+    std::unique_ptr<SumPolyState> sp(new SumPolyState);
+    ZK_TRY(sp_configure(c, sp.get(), (int)n_products, (int)degree, KIND_PROD));
+    for (uint32_t i = 0; i < n_products * degree; ++i) {
+        Table* t = find_mle(c, tables[i]);
+        if (!t) return ZKB_ERR_BAD_ARG;
+        if (i && t->n != sp->src[0].n) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "all evaluations must have same length");
+        sp->src.push_back(*t);
+    }
+    sp->n0 = sp->src[0].n;
+    sp_reset(c, sp.get());
+    zkb_sp h = c->next_handle++;
+    c->sps[h] = std::move(sp);
+    *out = h;
+    return ZKB_OK;
+}
+int32_t zkb_sumpoly_free(zkb_ctx* c, zkb_sp h) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    sp_release(c, it->second.get());
+    c->sps.erase(it);
+    return ZKB_OK;
+}
+int32_t zkb_sumpoly_evaluate(zkb_ctx* c, zkb_sp h, const uint64_t* values, uint32_t k, uint64_t out[4]) {
+    if (!c || !out) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    SumPolyState* sp = it->second.get();
+    std::vector<Fe> rs(k);
+    for (uint32_t i = 0; i < k; ++i) rs[i] = fe_from_u64x4(values + 4 * i);
+    Fe sum = c->H.zero();
+    for (int p = 0; p < sp->P; ++p) {
+        Fe prod = c->H.one();
+        for (int f = 0; f < sp->D; ++f) {
+            Fe v;
+            ZK_TRY(evaluate_table(c, sp->src[p * sp->D + f], rs.data(), k, &v));
+            prod = c->H.mul(prod, v);
+        }
+        sum = c->H.add(sum, prod);
+    }
+    fe_to_u64x4(sum, out);
+    return ZKB_OK;
+}
+int32_t zkb_sc_round_evals(zkb_ctx* c, zkb_sp h, uint64_t* evals) {
+    if (!c || !evals) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    Fe ev[MAXPTS];
+    ZK_TRY(sp_round_evals(c, it->second.get(), ev));
+    for (int i = 0; i < it->second->npts; ++i) fe_to_u64x4(ev[i], evals + 4 * i);
+    return ZKB_OK;
+}
+int32_t zkb_sc_bind_and_next(zkb_ctx* c, zkb_sp h, const uint64_t r[4], uint64_t* evals) {
+    if (!c || !r) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    SumPolyState* sp = it->second.get();
+    Fe ev[MAXPTS];
+    const bool last = sp->cur_n == 2 && !sp->sharded;
+    if (last && evals) evals = nullptr;
+    ZK_TRY(sp_bind_and_next(c, sp, fe_from_u64x4(r), evals ? ev : nullptr, nullptr));
+    if (evals)
+        for (int i = 0; i < sp->npts; ++i) fe_to_u64x4(ev[i], evals + 4 * i);
+    return ZKB_OK;
+}
+int32_t zkb_sc_final_values(zkb_ctx* c, zkb_sp h, uint64_t* values) {
+    if (!c || !values) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    SumPolyState* sp = it->second.get();
+    std::vector<Fe> v(sp->src.size());
+    ZK_TRY(sp_final_values(c, sp, v.data()));
+    for (size_t t = 0; t < v.size(); ++t) fe_to_u64x4(v[t], values + 4 * t);
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------ Transcript
+int32_t zkb_transcript_new(int32_t field_id, zkb_transcript** out) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || !out) return ZKB_ERR_BAD_ARG;
+    zkb_transcript* t = new zkb_transcript;
+    t->impl.H.K = K;
+    *out = t;
+    return ZKB_OK;
+}
+int32_t zkb_transcript_free(zkb_transcript* t) {
+    delete t;
+    return ZKB_OK;
+}
+int32_t zkb_transcript_append(zkb_transcript* t, const uint8_t* bytes, size_t len) {
+    if (!t || (!bytes && len)) return ZKB_ERR_BAD_ARG;
+    t->impl.append(bytes, len);
+    return ZKB_OK;
+}
+int32_t zkb_transcript_append_elements(zkb_transcript* t, const uint64_t* mont, size_t n) {
+    if (!t || (!mont && n)) return ZKB_ERR_BAD_ARG;
+    for (size_t i = 0; i < n; ++i) {
+        Fe v = fe_from_u64x4(mont + 4 * i);
+        t->impl.append_elements(&v, 1);
+    }
+    return ZKB_OK;
+}
+int32_t zkb_transcript_challenge(zkb_transcript* t, uint64_t out_mont[4]) {
+    if (!t || !out_mont) return ZKB_ERR_BAD_ARG;
+    fe_to_u64x4(t->impl.challenge(), out_mont);
+    return ZKB_OK;
+}
+int32_t zkb_keccak256(const uint8_t* bytes, size_t len, uint8_t out[32]) {
+    if ((!bytes && len) || !out) return ZKB_ERR_BAD_ARG;
+    Keccak256 k;
+    k.update(bytes, len);
+    k.finalize_reset(out);
+    return ZKB_OK;
+}
+
+int32_t zkb_fe_to_mont(int32_t field_id, const uint64_t* canonical, uint64_t* mont, size_t n) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || (!canonical && n) || (!mont && n)) return ZKB_ERR_BAD_ARG;
+    HostField H{K};
+    for (size_t i = 0; i < n; ++i) fe_to_u64x4(H.to_mont(fe_from_u64x4(canonical + 4 * i)), mont + 4 * i);
+    return ZKB_OK;
+}
+int32_t zkb_fe_from_mont(int32_t field_id, const uint64_t* mont, uint64_t* canonical, size_t n) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || (!canonical && n) || (!mont && n)) return ZKB_ERR_BAD_ARG;
+    HostField H{K};
+    for (size_t i = 0; i < n; ++i) fe_to_u64x4(H.from_mont(fe_from_u64x4(mont + 4 * i)), canonical + 4 * i);
+    return ZKB_OK;
+}
+
+int32_t zkb_fe_reduce_wide(int32_t field_id, const uint64_t* wide, uint64_t* out, size_t n) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || (!wide && n) || (!out && n)) return ZKB_ERR_BAD_ARG;
+    HostField H{K};
+    for (size_t i = 0; i < n; ++i) fe_to_u64x4(H.from_wide_limbs((const unsigned long long*)wide + 8 * i), out + 4 * i);
+    return ZKB_OK;
+}
+
+// -------------------------------------------------------------- UnivariatePoly
+int32_t zkb_uni_interpolate(int32_t field_id, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint64_t* coeffs, uint32_t* len) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || !xs || !ys || !coeffs || !len || n > 64) return ZKB_ERR_BAD_ARG;
+    HostField H{K};
+    std::vector<Fe> x(n), y(n), co(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        x[i] = fe_from_u64x4(xs + 4 * i);
+        y[i] = fe_from_u64x4(ys + 4 * i);
+    }
+    int l = uni_interpolate(H, x.data(), y.data(), (int)n, co.data());
+    for (int i = 0; i < l; ++i) fe_to_u64x4(co[i], coeffs + 4 * i);
+    *len = (uint32_t)l;
+    return ZKB_OK;
+}
+int32_t zkb_uni_evaluate(int32_t field_id, const uint64_t* coeffs, uint32_t len, const uint64_t x[4], uint64_t out[4]) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || (!coeffs && len) || !x || !out) return ZKB_ERR_BAD_ARG;
+    HostField H{K};
+    std::vector<Fe> co(len);
+    for (uint32_t i = 0; i < len; ++i) co[i] = fe_from_u64x4(coeffs + 4 * i);
+    fe_to_u64x4(uni_evaluate(H, co.data(), (int)len, fe_from_u64x4(x)), out);
+    return ZKB_OK;
+}
+
+// ---------------------------------------------------------- sum_check_protocol
+static int32_t absorb_table(zkb_ctx* c, const Table& t, TranscriptImpl* tr) {
+    // fq_vec_to_bytes(&polynomial.evaluation) (sum_check_protocol.rs:27): canonical bytes made on the
+    // device, hashed on the host.  Sharded tables are not supported here (the reference order needs the whole table).
+    if (c->comm && c->world > 1) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "absorbing a sharded table into the transcript is not supported");
+    std::vector<uint8_t> bytes((size_t)t.n * 32);
+    ZK_TRY(download_aos(c, t, bytes.data(), 2));
+    tr->append(bytes.data(), bytes.size());
+    return ZKB_OK;
+}
+
+int32_t zkb_sumcheck_prove(zkb_ctx* c, zkb_mle poly, uint32_t flags, uint64_t claimed_sum[4], uint64_t* msgs, uint64_t* challenges) {
+    Table* t = c ? find_mle(c, poly) : nullptr;
+    if (!t || !claimed_sum) return ZKB_ERR_BAD_ARG;
+    TranscriptImpl tr;
+    tr.H = c->H;
+    if (flags & 1u) ZK_TRY(absorb_table(c, *t, &tr));
+    SumPolyState sp;
+    ZK_TRY(sp_configure(c, &sp, 1, 1, KIND_PROD));
+    sp.src.push_back(*t);
+    sp.n0 = t->n;
+    sp_reset(c, &sp);
+    const int n_rounds = ilog2_u64(sp.n0) + (sp.sharded ? c->log2world : 0);
+    int32_t st = ZKB_OK;
+    Fe ev[2], fin[1];
+    if (n_rounds == 0) {
+        Fe v;
+        ZK_TRY(read_elems(c, *t, 0, 1, &v));
+        fe_to_u64x4(v, claimed_sum);
+        return ZKB_OK;
+    }
+    if (!msgs) return ZKB_ERR_BAD_ARG;
+    st = sp_round_evals(c, &sp, ev);
+    if (st == ZKB_OK) {
+        Fe claimed = c->H.add(ev[0], ev[1]);  // :29 the claimed sum is the sum of the two halves
+        fe_to_u64x4(claimed, claimed_sum);
+        tr.append_elements(&claimed, 1);
+        for (int k = 0; k < n_rounds && st == ZKB_OK; ++k) {
+            tr.append_elements(ev, 2);
+            fe_to_u64x4(ev[0], msgs + (size_t)k * 8);
+            fe_to_u64x4(ev[1], msgs + (size_t)k * 8 + 4);
+            Fe r = tr.challenge();
+            if (challenges) fe_to_u64x4(r, challenges + (size_t)k * 4);
+            st = sp_bind_and_next(c, &sp, r, k + 1 < n_rounds ? ev : nullptr, fin);
+        }
+    }
+    sp_release(c, &sp);
+    return st;
+}
+
+int32_t zkb_sumcheck_verify(zkb_ctx* c, zkb_mle poly, uint32_t flags, const uint64_t claimed_sum[4], const uint64_t* msgs,
+                            uint32_t n_msgs, int32_t* accepted) {
+    Table* t = c ? find_mle(c, poly) : nullptr;
+    if (!t || !claimed_sum || !accepted || (!msgs && n_msgs)) return ZKB_ERR_BAD_ARG;
+    *accepted = 0;
+    TranscriptImpl tr;
+    tr.H = c->H;
+    if (flags & 1u) ZK_TRY(absorb_table(c, *t, &tr));
+    Fe expected = fe_from_u64x4(claimed_sum);
+    tr.append_elements(&expected, 1);
+    std::vector<Fe> chals;
+    for (uint32_t k = 0; k < n_msgs; ++k) {
+        Fe s[2] = {fe_from_u64x4(msgs + (size_t)k * 8), fe_from_u64x4(msgs + (size_t)k * 8 + 4)};
+        if (!c->H.eq(c->H.add(s[0], s[1]), expected)) return ZKB_OK;  // :66-68
+        tr.append_elements(s, 2);
+        Fe r = tr.challenge();
+        chals.push_back(r);
+        expected = c->H.add(s[0], c->H.mul(r, c->H.sub(s[1], s[0])));  // :73-74
+    }
+    // :81 polynomial.evaluate(challenges) -- panics (arity) if the proof has the wrong number of rounds
+    Fe v;
+    ZK_TRY(evaluate_table(c, *t, chals.data(), (uint32_t)chals.size(), &v));
+    *accepted = c->H.eq(v, expected) ? 1 : 0;
+    return ZKB_OK;
+}
+
+int32_t zkb_gkr_sumcheck_prove(zkb_ctx* c, zkb_transcript* t, const uint64_t claimed_sum[4], zkb_sp h, uint64_t* coeffs,
+                               int32_t* lens, uint64_t* challenges, uint64_t* final_values) {
+    (void)claimed_sum;  // the reference echoes it without using it (sum_check_protocol.rs:87,112)
+    if (!c || !t || !coeffs || !lens) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    SumPolyState* sp = it->second.get();
+    std::vector<Fe> fin(sp->src.size());
+    ZK_TRY(sp_prove(c, sp, &t->impl, sp->npts, coeffs, lens, challenges, fin.data(), false));
+    if (final_values)
+        for (size_t i = 0; i < fin.size(); ++i) fe_to_u64x4(fin[i], final_values + 4 * i);
+    return ZKB_OK;
+}
+
+int32_t zkb_gkr_sumcheck_verify(zkb_transcript* t, uint32_t n_rounds, uint32_t slots, const uint64_t* coeffs, const int32_t* lens,
+                                const uint64_t claimed_sum[4], int32_t* accepted, uint64_t final_claim[4], uint64_t* challenges) {
+    if (!t || (!coeffs && n_rounds) || (!lens && n_rounds) || !claimed_sum || !accepted || !final_claim || !challenges) return ZKB_ERR_BAD_ARG;
+    for (uint32_t k = 0; k < n_rounds; ++k)
+        if (lens[k] < 0 || (uint32_t)lens[k] > slots || lens[k] > MAXPTS + 3) return ZKB_ERR_BAD_ARG;
+    const HostField& H = t->impl.H;
+    std::vector<Fe> ch(n_rounds ? n_rounds : 1);
+    Fe fin;
+    if (!sc_verify_rounds(H, &t->impl, n_rounds, slots, coeffs, lens, fe_from_u64x4(claimed_sum), &fin, ch.data())) {
+        *accepted = 0;  // :129-133
+        std::memset(final_claim, 0, 32);
+        std::memset(challenges, 0, 32);
+        return ZKB_OK;
+    }
+    *accepted = 1;
+    fe_to_u64x4(fin, final_claim);
+    for (uint32_t k = 0; k < n_rounds; ++k) fe_to_u64x4(ch[k], challenges + 4 * (size_t)k);
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------ gkr_circuit / gkr
+uint32_t zkb_gkr_total_rounds(uint32_t n_layers, const uint32_t* gates) {
+    uint32_t tot = 0;
+    for (uint32_t l = 0; l < n_layers; ++l) tot += layer_rounds(gates[l]);
+    return tot;
+}
+
+int32_t zkb_circuit_create(zkb_ctx* c, uint32_t n_layers, const uint32_t* gates, const uint8_t* ops, zkb_circ* out) {
+    if (!c || !gates || !ops || !out) return ZKB_ERR_BAD_ARG;
+    ZK_TRY(circuit_check_shape(c, n_layers, gates));
+    std::unique_ptr<CircuitState> cs(new CircuitState);
+    cs->L = (int)n_layers;
+    cs->gates.assign(gates, gates + n_layers);
+    size_t tot = 0;
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        cs->opoff.push_back(tot);
+        tot += gates[l];
+    }
+    cs->h_ops.assign(ops, ops + tot);
+    for (size_t i = 0; i < tot; ++i)
+        if (ops[i] != ZKB_OP_ADD && ops[i] != ZKB_OP_MUL) return ZKB_ERR_BAD_ARG;
+    ZK_CUDA(c, cudaMallocAsync((void**)&cs->d_ops, tot, c->stream));
+    ZK_CUDA(c, cudaMemcpyAsync(cs->d_ops, cs->h_ops.data(), tot, cudaMemcpyHostToDevice, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint64_t n_in = 2ull * gates[0];
+    ZK_TRY(alloc_table(c, n_in, &cs->inputs));
+    cs->vals.resize(n_layers);
+    for (uint32_t l = 0; l < n_layers; ++l) ZK_TRY(alloc_table(c, gates[l], &cs->vals[l]));
+    ZK_TRY(alloc_table(c, n_in, &cs->H1));
+    ZK_TRY(alloc_table(c, n_in, &cs->HA2));
+    ZK_TRY(alloc_table(c, gates[0], &cs->coef));
+    const int nmax = ilog2_u64(n_in);
+    for (auto& t : cs->eq) ZK_TRY(alloc_table(c, 1ull << ((nmax + 1) / 2 + 1), &t));
+    ZK_TRY(sp_configure(c, &cs->sp, 1, 3, KIND_XYZ));
+    cs->sp.work.resize(3);
+    for (auto& t : cs->sp.work) ZK_TRY(alloc_table(c, n_in / 2, &t));
+    zkb_circ h = c->next_handle++;
+    c->circs[h] = std::move(cs);
+    *out = h;
+    return ZKB_OK;
+}
+int32_t zkb_circuit_free(zkb_ctx* c, zkb_circ h) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end()) return ZKB_ERR_BAD_ARG;
+    CircuitState* cs = it->second.get();
+    sp_release(c, &cs->sp);
+    free_table(c, &cs->inputs);
+    for (auto& t : cs->vals) free_table(c, &t);
+    free_table(c, &cs->H1);
+    free_table(c, &cs->HA2);
+    free_table(c, &cs->coef);
+    for (auto& t : cs->eq) free_table(c, &t);
+    if (cs->d_ops) cudaFreeAsync(cs->d_ops, c->stream);
+    if (cs->aos_stage) cudaFreeAsync(cs->aos_stage, c->stream);
+    c->circs.erase(it);
+    return ZKB_OK;
+}
+int32_t zkb_circuit_evaluate(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t n_inputs, uint64_t* outputs) {
+    if (!c || !inputs) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end()) return ZKB_ERR_BAD_ARG;
+    CircuitState* cs = it->second.get();
+    ZK_TRY(circuit_run(c, cs, inputs, n_inputs));
+    if (outputs) {
+        size_t off = 0;
+        for (int l = 0; l < cs->L; ++l) {
+            ZK_TRY(download_aos(c, cs->vals[l], outputs + off * 4, 0));
+            off += cs->gates[l];
+        }
+    } else {
+        ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return ZKB_OK;
+}
+int32_t zkb_gkr_prove(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t n_inputs, uint64_t w0[8], uint64_t* coeffs,
+                      int32_t* lens, uint64_t* challenges, uint64_t* claimed, uint64_t final_openings[8], uint32_t* n_rounds) {
+    if (!c || !inputs || !w0 || !coeffs || !lens || !final_openings) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end()) return ZKB_ERR_BAD_ARG;
+    if (it->second->L > 1 && !claimed) return ZKB_ERR_BAD_ARG;
+    return gkr_prove_impl(c, it->second.get(), inputs, n_inputs, w0, coeffs, lens, challenges, claimed, final_openings, n_rounds);
+}
+
+int32_t zkb_gkr_verify(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t n_inputs, const uint64_t w0_in[8],
+                       const uint64_t* coeffs, const int32_t* lens, const uint64_t* claimed, const uint64_t final_openings[8],
+                       int32_t* accepted) {
+    if (!c || !inputs || !w0_in || !coeffs || !lens || !final_openings || !accepted) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end()) return ZKB_ERR_BAD_ARG;
+    CircuitState* cs = it->second.get();
+    *accepted = 0;
+    const int L = cs->L;
+    if (n_inputs != 2ull * cs->gates[0]) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: inputs must be 2 x gates of the first layer");
+    const HostField& H = c->H;
+    TranscriptImpl tr;
+    tr.H = H;
+    Fe w0[2] = {fe_from_u64x4(w0_in), fe_from_u64x4(w0_in + 4)};
+    tr.append_elements(w0, 2);
+    Fe r0 = tr.challenge();
+    Fe claim = H.add(w0[0], H.mul(r0, H.sub(w0[1], w0[0])));
+    tr.append_elements(&claim, 1);
+    // the input MLE on the device (the reference checks a KZG opening instead, gkr_protocol.rs:157-183)
+    Table in_tab;
+    ZK_TRY(upload_aos(c, inputs, n_inputs, 0, 1, n_inputs, 0, &in_tab));
+    Fe alpha = H.zero(), beta = H.zero();
+    std::vector<Fe> prb, prc;
+    size_t round_base = 0;
+    int32_t st = ZKB_OK;
+    bool ok = true;
+    for (int idx = 0; idx < L && ok && st == ZKB_OK; ++idx) {
+        const int l = L - 1 - idx;
+        const uint64_t G = cs->gates[l], nw = 2 * G;
+        const int nb = ilog2_u64(nw);
+        const uint32_t nr = 2 * (uint32_t)nb;
+        std::vector<Fe> cur(nr);
+        Fe fin;
+        for (uint32_t k = 0; k < nr; ++k)
+            if (lens[round_base + k] < 0 || lens[round_base + k] > 3) { ok = false; break; }
+        if (!ok) break;
+        if (!sc_verify_rounds(H, &tr, nr, 3, coeffs + round_base * 12, lens + round_base, claim, &fin, cur.data())) { ok = false; break; }
+        round_base += nr;
+        std::vector<Fe> u(cur.begin(), cur.begin() + nb), w(cur.begin() + nb, cur.end());
+        Fe o1, o2;
+        if (idx == L - 1) {
+            st = evaluate_table(c, in_tab, u.data(), (uint32_t)nb, &o1);
+            if (st == ZKB_OK) st = evaluate_table(c, in_tab, w.data(), (uint32_t)nb, &o2);
+            if (st != ZKB_OK) break;
+            if (!H.eq(o1, fe_from_u64x4(final_openings)) || !H.eq(o2, fe_from_u64x4(final_openings + 4))) { ok = false; break; }
+        } else {
+            o1 = fe_from_u64x4(claimed + (size_t)idx * 8);
+            o2 = fe_from_u64x4(claimed + (size_t)idx * 8 + 4);
+        }
+        // wiring predicates at (prev point, u, w) in O(G)
+        GkrWiringArgs wa;
+        std::memset(&wa, 0, sizeof wa);
+        wa.ops = cs->d_ops + cs->opoff[l];
+        wa.n_gates = G;
+        wa.first_layer = idx == 0;
+        wa.r0 = r0;
+        wa.alpha = alpha;
+        wa.beta = beta;
+        int n_lo = 0;
+        if (idx > 0) {
+            if ((1ull << prb.size()) != G) { ok = false; break; }
+            st = eq_tables(c, prb.data(), (int)prb.size(), &cs->eq[0], &cs->eq[1], &n_lo);
+            if (st == ZKB_OK) st = eq_tables(c, prc.data(), (int)prc.size(), &cs->eq[2], &cs->eq[3], &n_lo);
+            if (st != ZKB_OK) break;
+            wa.eb_hi = cs->eq[0].ref();
+            wa.eb_lo = cs->eq[1].ref();
+            wa.ec_hi = cs->eq[2].ref();
+            wa.ec_lo = cs->eq[3].ref();
+            wa.n_lo_a = n_lo;
+        }
+        st = eq_tables(c, u.data(), nb, &cs->eq[4], &cs->eq[5], &n_lo);
+        if (st == ZKB_OK) st = eq_tables(c, w.data(), nb, &cs->eq[6], &cs->eq[7], &n_lo);
+        if (st != ZKB_OK) break;
+        wa.eu_hi = cs->eq[4].ref();
+        wa.eu_lo = cs->eq[5].ref();
+        wa.ew_hi = cs->eq[6].ref();
+        wa.ew_lo = cs->eq[7].ref();
+        wa.n_lo_w = n_lo;
+        const int grid = grid_for(c, G, 4);
+        st = prep_finish(c, grid, 2, false, &wa.fin);
+        if (st != ZKB_OK) break;
+        c->K->gkr_wiring(wa, grid, c->stream);
+        st = check_launch(c, "k_gkr_wiring");
+        if (st != ZKB_OK) break;
+        Fe am[2];
+        st = collect(c, 2, false, wa.fin, am);
+        if (st != ZKB_OK) break;
+        Fe expected = H.add(H.mul(am[0], H.add(o1, o2)), H.mul(am[1], H.mul(o1, o2)));  // :211,313,340
+        if (!H.eq(expected, fin)) { ok = false; break; }
+        prb = u;
+        prc = w;
+        tr.append_elements(&o1, 1);  // :217-221 (the verifier absorbs after every layer)
+        alpha = tr.challenge();
+        tr.append_elements(&o2, 1);
+        beta = tr.challenge();
+        claim = H.add(H.mul(alpha, o1), H.mul(beta, o2));
+    }
+    free_table(c, &in_tab);
+    if (st != ZKB_OK) return st;
+    *accepted = ok ? 1 : 0;
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------- microbenchmarks
+int32_t zkb_bench_modmul(zkb_ctx* c, int32_t variant, uint32_t iters, double* out) {
+    if (!c || !out || variant < 0 || variant > 3) return ZKB_ERR_BAD_ARG;
+    const int grid = c->sm_count * 8;
+    Fe* buf = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&buf, (size_t)grid * BLOCK * sizeof(Fe), c->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    c->K->bench_mul(variant, buf, iters / 8 + 1, grid, c->stream);  // warm-up
+    cudaEventRecord(e0, c->stream);
+    c->K->bench_mul(variant, buf, iters, grid, c->stream);
+    cudaEventRecord(e1, c->stream);
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->launches += 2;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFreeAsync(buf, c->stream);
+    const int ilp = (variant & 1) ? 2 : 1;
+    *out = (double)grid * BLOCK * (double)iters * ilp / (ms * 1e-3);
+    return ZKB_OK;
+}
+int32_t zkb_bench_imad(zkb_ctx* c, int32_t mode, uint32_t iters, double* out) {
+    if (!c || !out || mode < 0 || mode > 3) return ZKB_ERR_BAD_ARG;
+    const int grid = c->sm_count * 8;
+    uint64_t* buf = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&buf, (size_t)grid * BLOCK * sizeof(uint64_t), c->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    launch_bench_imad(mode, buf, iters / 8 + 1, grid, c->stream);
+    cudaEventRecord(e0, c->stream);
+    launch_bench_imad(mode, buf, iters, grid, c->stream);
+    cudaEventRecord(e1, c->stream);
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->launches += 2;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFreeAsync(buf, c->stream);
+    *out = (double)grid * BLOCK * (double)iters * 32.0 / (ms * 1e-3);
+    return ZKB_OK;
+}
+
+}  // extern "C"

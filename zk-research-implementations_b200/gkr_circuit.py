@@ -1,0 +1,68 @@
+"""Device-backed mirror of `gkr::gkr_circuit` (gkr_circuit.rs:4-143)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+from . import engine as E
+from .engine import Context, _ck, lib
+from .multilinear_polynomial import Operation
+
+
+@dataclass
+class Gate:  # :4-23
+    l_input: int
+    r_input: int
+    output: int
+    op: Operation
+
+
+class Layer:  # :25-104
+    def __init__(self, gates: List[Gate]):
+        self.gates = gates
+
+    def get_layer_poly(self) -> List[int]:  # :35-37
+        return [g.output for g in self.gates]
+
+
+class Circuit:
+    """Circuit::new(structure) (:113-125): `structure` lists the layers input side first."""
+
+    def __init__(self, ctx: Context, structure: Sequence[Sequence[Operation]]):
+        self.ctx = ctx
+        self.layers = [Layer([Gate(0, 0, 0, Operation(op)) for op in ops]) for ops in structure]
+        self.gates = np.array([len(ops) for ops in structure], dtype=np.uint32)
+        self.ops = np.array([int(op) for ops in structure for op in ops], dtype=np.uint8)
+        h = C.c_uint64()
+        _ck(ctx, lib().zkb_circuit_create(ctx.handle, len(self.gates), self.gates.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                          self.ops.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(h)))
+        self._h = h.value
+
+    @property
+    def handle(self) -> int:
+        return self._h
+
+    def evaluate(self, inputs: Sequence[int]) -> List[List[int]]:  # :127-143
+        ctx = self.ctx
+        arr = ctx.mont(inputs)
+        out = np.zeros((int(self.gates.sum()), 4), dtype=np.uint64)
+        _ck(ctx, lib().zkb_circuit_evaluate(ctx.handle, self._h, arr.ctypes.data, len(inputs), out.ctypes.data))
+        vals = ctx.unmont(out)
+        res, off = [], 0
+        cur = [int(x) % ctx.p for x in inputs]
+        for layer, g in zip(self.layers, self.gates):
+            lay = vals[off: off + int(g)]
+            for i, gate in enumerate(layer.gates):
+                gate.l_input, gate.r_input, gate.output = cur[2 * i], cur[2 * i + 1], lay[i]
+            res.append(lay)
+            cur = lay
+            off += int(g)
+        return res
+
+    def free(self) -> None:
+        if self._h:
+            lib().zkb_circuit_free(self.ctx.handle, self._h)
+            self._h = 0
