@@ -74,6 +74,15 @@ void* zkb_ctx_stream(const zkb_ctx* ctx);
 /* Number of this library's kernels launched through ctx so far (bench.py's `gpu_launches`). */
 uint64_t zkb_ctx_launch_count(const zkb_ctx* ctx);
 int32_t zkb_ctx_sync(zkb_ctx* ctx);
+/* Per-launch device timing for the roofline report: while enabled, every table-kernel launch is bracketed by
+ * CUDA events on the ctx's stream.  zkb_ctx_profile_read synchronises and returns, for one kernel id
+ * (ZKB_K_*), the number of launches, their summed duration and their summed ALGORITHMIC bytes
+ * (compulsory reads + writes, DESIGN.md "Kernels") since profiling was enabled. */
+enum { ZKB_K_SC_EVAL = 0, ZKB_K_SC_FOLD_EVAL = 1, ZKB_K_FOLD_TABLES = 2, ZKB_K_FINAL_BIND = 3, ZKB_K_FOLD = 4,
+       ZKB_K_LAYOUT = 5, ZKB_K_GKR_BUILD = 6, ZKB_K_OTHER = 7, ZKB_K_COUNT = 8 };
+int32_t zkb_ctx_profile(zkb_ctx* ctx, int32_t enable);
+int32_t zkb_ctx_profile_read(zkb_ctx* ctx, int32_t kernel_id, uint64_t* launches, double* ms, double* alg_bytes);
+const char* zkb_kernel_name(int32_t kernel_id);
 
 /* Multi-GPU (one process per GPU).  The table is sharded on LOW index bits: rank j of 2^g holds entries
  * i with i mod 2^g == j, so both halves of every bound variable stay local.  Per round the
@@ -118,6 +127,8 @@ int32_t zkb_mle_tensor(zkb_ctx* ctx, zkb_mle a, zkb_mle b, int32_t op, zkb_mle* 
  * read-only and folds into private scratch, so the caller's tables stay intact (the reference clones). */
 int32_t zkb_sumpoly_create(zkb_ctx* ctx, const zkb_mle* tables, uint32_t n_products, uint32_t degree, zkb_sp* out);
 int32_t zkb_sumpoly_free(zkb_ctx* ctx, zkb_sp sp);
+/* Back to the unbound state (the caller's tables were never written). */
+int32_t zkb_sumpoly_reset(zkb_ctx* ctx, zkb_sp sp);
 /* ProductPoly/SumPoly::evaluate (:31-36, :71-76): sum of products of the factors' evaluations. */
 int32_t zkb_sumpoly_evaluate(zkb_ctx* ctx, zkb_sp sp, const uint64_t* values, uint32_t k, uint64_t out[4]);
 /* Step API of the composed sumcheck (the body of gkr_prove's loop, sum_check_protocol.rs:96-108):

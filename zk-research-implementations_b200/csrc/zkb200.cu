@@ -153,6 +153,15 @@ struct zkb_ctx {
     uint32_t gather_log2 = 12;
     RoundInterpolator interp[MAXPTS + 1];
     std::unordered_map<std::string, int> occ_cache;
+    // per-launch event timing (zkb_ctx_profile)
+    bool prof = false;
+    struct ProfRec { int kind; cudaEvent_t e0, e1; double bytes; bool open; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> ev_pool;
+    uint64_t prof_launches[ZKB_K_COUNT] = {0};
+    double prof_ms[ZKB_K_COUNT] = {0}, prof_bytes[ZKB_K_COUNT] = {0};
+    int cur_kind = ZKB_K_OTHER;
+    double cur_bytes = 0;
 };
 
 namespace {
@@ -185,7 +194,42 @@ namespace {
         return (code);             \
     } while (0)
 
+cudaEvent_t prof_event(zkb_ctx* c) {
+    if (!c->ev_pool.empty()) {
+        cudaEvent_t e = c->ev_pool.back();
+        c->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+// Call right before a launch: names the kernel and its algorithmic bytes for the profile.
+inline void prof_begin(zkb_ctx* c, int kind, double bytes) {
+    if (!c->prof) return;
+    zkb_ctx::ProfRec r{kind, prof_event(c), prof_event(c), bytes, true};
+    cudaEventRecord(r.e0, c->stream);
+    c->prof_recs.push_back(r);
+}
+void prof_drain(zkb_ctx* c) {
+    for (auto& r : c->prof_recs) {
+        float ms = 0;
+        if (!r.open && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            c->prof_launches[r.kind] += 1;
+            c->prof_ms[r.kind] += ms;
+            c->prof_bytes[r.kind] += r.bytes;
+        }
+        c->ev_pool.push_back(r.e0);
+        c->ev_pool.push_back(r.e1);
+    }
+    c->prof_recs.clear();
+}
+
 int32_t check_launch(zkb_ctx* c, const char* what) {
+    if (c->prof && !c->prof_recs.empty() && c->prof_recs.back().open) {
+        cudaEventRecord(c->prof_recs.back().e1, c->stream);
+        c->prof_recs.back().open = false;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -373,6 +417,7 @@ int32_t sp_round_evals(zkb_ctx* c, SumPolyState* sp, Fe* evals) {
     a.n_out = sp->cur_n;
     const int grid = grid_for(c, sp->cur_n / 2, sc_occ(c, 0, sp->kind, sp->kD, sp->npts));
     ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
+    prof_begin(c, ZKB_K_SC_EVAL, 32.0 * (double)sp->sel.size() * (double)sp->cur_n);
     if (!c->K->sc_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_eval: shape not instantiated");
     ZK_TRY(check_launch(c, "k_sc_eval"));
     return collect(c, sp->npts, sp->sharded, a.fin, evals);
@@ -432,6 +477,7 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
         fa.n_out = 1;
         fa.r = r;
         unsigned int seq = ++c->seq;
+        prof_begin(c, ZKB_K_FINAL_BIND, 96.0 * T);
         c->K->final_bind(fa, c->h_res, c->h_flag, seq, c->stream);
         ZK_TRY(check_launch(c, "k_final_bind"));
         if (sp->state == 0) sp->state = 1;
@@ -460,6 +506,7 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
         fa.n_tables = k;
         fa.n_out = n_out;
         fa.r = r;
+        prof_begin(c, ZKB_K_FOLD_TABLES, 96.0 * (double)k * (double)n_out);
         c->K->fold_tables(fa, grid_for(c, n_out * (uint64_t)k, 8), c->stream);
         ZK_TRY(check_launch(c, "k_fold_tables"));
         if (all) {
@@ -481,6 +528,7 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
     a.r = r;
     const int grid = grid_for(c, n_out / 2, sc_occ(c, 1, sp->kind, sp->kD, sp->npts));
     ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
+    prof_begin(c, ZKB_K_SC_FOLD_EVAL, 96.0 * (double)sp->sel.size() * (double)n_out);
     if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
     ZK_TRY(check_launch(c, "k_sc_fold_eval"));
     if (sp->state == 0) sp->state = 1;
@@ -545,6 +593,7 @@ int32_t upload_aos(zkb_ctx* c, const uint64_t* aos, uint64_t n_src, uint64_t fir
         ZK_TRY(ensure_stage(c, (size_t)n_dst * 32));
         ZK_CUDA(c, cudaMemcpy2DAsync(c->stage, 32, (const uint8_t*)aos + first * 32, (size_t)stride * 32, 32, n_dst,
                                      cudaMemcpyHostToDevice, c->stream));
+        prof_begin(c, ZKB_K_LAYOUT, 64.0 * (double)n_dst);
         c->K->aos_to_planar(c->stage, out->ref(), n_dst, 0, 1, conv, grid_for(c, n_dst, 8), c->stream);
         ZK_TRY(check_launch(c, "k_aos_to_planar"));
         return ZKB_OK;
@@ -555,6 +604,7 @@ int32_t upload_aos(zkb_ctx* c, const uint64_t* aos, uint64_t n_src, uint64_t fir
         ZK_CUDA(c, cudaMemcpyAsync(c->stage, (const uint8_t*)aos + (first + off) * 32, (size_t)m * 32, cudaMemcpyHostToDevice,
                                    c->stream));
         TabRef dst{out->base + off, out->stride};
+        prof_begin(c, ZKB_K_LAYOUT, 64.0 * (double)m);
         c->K->aos_to_planar(c->stage, dst, m, 0, 1, conv, grid_for(c, m, 8), c->stream);
         ZK_TRY(check_launch(c, "k_aos_to_planar"));
     }
@@ -567,6 +617,7 @@ int32_t download_aos(zkb_ctx* c, const Table& t, void* host, int conv) {
     for (uint64_t off = 0; off < t.n; off += chunk) {
         const uint64_t m = (t.n - off < chunk) ? t.n - off : chunk;
         TabRef src{t.base + off, t.stride};
+        prof_begin(c, ZKB_K_LAYOUT, 64.0 * (double)m);
         c->K->planar_to_aos(src, c->stage, m, conv, grid_for(c, m, 8), c->stream);
         ZK_TRY(check_launch(c, "k_planar_to_aos"));
         ZK_CUDA(c, cudaMemcpyAsync((uint8_t*)host + off * 32, c->stage, (size_t)m * 32, cudaMemcpyDeviceToHost, c->stream));
@@ -597,6 +648,7 @@ int32_t multi_fold(zkb_ctx* c, const Table& src, const Fe* rs, uint32_t k, Table
         fa.n_tables = 1;
         fa.n_out = n / 2;
         fa.r = rs[i];
+        prof_begin(c, ZKB_K_FOLD_TABLES, 96.0 * (double)(n / 2));
         c->K->fold_tables(fa, grid_for(c, n / 2, 8), c->stream);
         ZK_TRY(check_launch(c, "k_fold_tables"));
         n /= 2;
@@ -787,6 +839,7 @@ int32_t gkr_prove_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont
             p1.ec_lo = cs->eq[3].ref();
             p1.n_lo = n_lo;
         }
+        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * (double)G * 6.0);
         c->K->gkr_phase1(p1, grid_for(c, G, 8), c->stream);
         ZK_TRY(check_launch(c, "k_gkr_phase1"));
         std::vector<Fe> u(nb), v(nb);
@@ -807,6 +860,7 @@ int32_t gkr_prove_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont
         p2.ops = cs->d_ops + cs->opoff[l];
         p2.n_gates = G;
         p2.Wu = Wu;
+        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * (double)G * 5.0);
         c->K->gkr_phase2(p2, grid_for(c, G, 8), c->stream);
         ZK_TRY(check_launch(c, "k_gkr_phase2"));
         ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + (round_base + nb) * 12, lens + round_base + nb,
@@ -935,6 +989,8 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     if (c->d_partials) cudaFreeAsync(c->d_partials, c->stream);
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    prof_drain(c);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_ticket);
     cudaFree(c->d_res);
     cudaFree(c->d_wide);
@@ -951,6 +1007,34 @@ int32_t zkb_ctx_sync(zkb_ctx* c) {
     if (!c) return ZKB_ERR_BAD_ARG;
     ZK_CUDA(c, cudaStreamSynchronize(c->stream));
     return ZKB_OK;
+}
+
+int32_t zkb_ctx_profile(zkb_ctx* c, int32_t enable) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    prof_drain(c);
+    if (enable && !c->prof) {
+        for (int k = 0; k < ZKB_K_COUNT; ++k) {
+            c->prof_launches[k] = 0;
+            c->prof_ms[k] = c->prof_bytes[k] = 0;
+        }
+    }
+    c->prof = enable != 0;
+    return ZKB_OK;
+}
+int32_t zkb_ctx_profile_read(zkb_ctx* c, int32_t k, uint64_t* launches, double* ms, double* alg_bytes) {
+    if (!c || k < 0 || k >= ZKB_K_COUNT) return ZKB_ERR_BAD_ARG;
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    prof_drain(c);
+    if (launches) *launches = c->prof_launches[k];
+    if (ms) *ms = c->prof_ms[k];
+    if (alg_bytes) *alg_bytes = c->prof_bytes[k];
+    return ZKB_OK;
+}
+const char* zkb_kernel_name(int32_t k) {
+    static const char* names[ZKB_K_COUNT] = {"k_sc_eval", "k_sc_fold_eval", "k_fold_tables", "k_final_bind", "k_fold",
+                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other"};
+    return (k >= 0 && k < ZKB_K_COUNT) ? names[k] : "?";
 }
 
 int32_t zkb_comm_unique_id(uint8_t out[128]) {
@@ -1046,6 +1130,7 @@ int32_t zkb_mle_partial_evaluate(zkb_ctx* c, zkb_mle in, uint32_t bit, const uin
     if ((int)bit >= nv) ZK_FAIL(c, ZKB_ERR_ARITY, "partial_evaluate: bit out of range");
     Table w;
     ZK_TRY(alloc_table(c, t->n / 2, &w));
+    prof_begin(c, ZKB_K_FOLD, 96.0 * (double)(t->n / 2));
     c->K->fold(t->ref(), w.ref(), t->n / 2, (uint32_t)(nv - 1 - (int)bit), fe_from_u64x4(value), grid_for(c, t->n / 2, 8), c->stream);
     ZK_TRY(check_launch(c, "k_fold"));
     *out = put_mle(c, w);
@@ -1148,6 +1233,13 @@ int32_t zkb_sumpoly_free(zkb_ctx* c, zkb_sp h) {
     if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
     sp_release(c, it->second.get());
     c->sps.erase(it);
+    return ZKB_OK;
+}
+int32_t zkb_sumpoly_reset(zkb_ctx* c, zkb_sp h) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    auto it = c->sps.find(h);
+    if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
+    sp_reset(c, it->second.get());
     return ZKB_OK;
 }
 int32_t zkb_sumpoly_evaluate(zkb_ctx* c, zkb_sp h, const uint64_t* values, uint32_t k, uint64_t out[4]) {

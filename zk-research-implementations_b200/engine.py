@@ -69,6 +69,10 @@ def lib() -> C.CDLL:
         "zkb_ctx_stream": (vp, [vp]),
         "zkb_ctx_launch_count": (u64, [vp]),
         "zkb_ctx_sync": (i32, [vp]),
+        "zkb_ctx_profile": (i32, [vp, i32]),
+        "zkb_ctx_profile_read": (i32, [vp, i32, C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "zkb_kernel_name": (C.c_char_p, [i32]),
+        "zkb_sumpoly_reset": (i32, [vp, u64]),
         "zkb_comm_unique_id": (i32, [u8p]),
         "zkb_ctx_comm_init": (i32, [vp, i32, i32, u8p]),
         "zkb_ctx_set_gather_threshold": (i32, [vp, u32]),
@@ -220,6 +224,19 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().zkb_ctx_launch_count(self._h))
+
+    def profile(self, enable: bool) -> None:
+        _ck(self, lib().zkb_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        """{kernel name: (launches, total ms, total algorithmic bytes)} since profile(True)."""
+        out = {}
+        for k in range(8):
+            n, ms, by = C.c_uint64(), C.c_double(), C.c_double()
+            _ck(self, lib().zkb_ctx_profile_read(self._h, k, C.byref(n), C.byref(ms), C.byref(by)))
+            if n.value:
+                out[lib().zkb_kernel_name(k).decode()] = (int(n.value), float(ms.value), float(by.value))
+        return out
 
     def comm_init(self, rank: int, world: int, unique_id: bytes) -> None:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
