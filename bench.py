@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-vars", type=int, default=N_VARS_PER_GPU, help="variables per GPU shard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling run: resident leg only, warm-up as given (numbers are not bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -181,7 +182,7 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    warmup = max(args.warmup, 3)
+    warmup = args.warmup if args.quick else max(args.warmup, 3)
     log2w = world.bit_length() - 1
     assert world == 1 << log2w, "the number of GPUs must be a power of two"
     n = args.n_vars + log2w
@@ -239,6 +240,14 @@ def main():
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = (1 << n) / (ms_step * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_step, "value": value, "gpu_launches": launches,
+                              "profile": {k: v for k, v in prof.items()}}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     # ---------------------------------------------------------------- end to end from host buffers (`e2e`)
     n_local = 1 << args.n_vars

@@ -19,6 +19,36 @@ static void run(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, siz
             case 4: r = Field<F>::to_mont(x); break;
             case 5: r = Field<F>::from_mont(x); break;
             case 6: r = Field<F>::fold(x, y, Field<F>::to_mont(y)); break;
+            case 7: {  // x * y * R^-1 through the fixed-multiplicand path (table built like host_math.hpp)
+                FixedMul T;
+                Fe v = Field<F>::zero();
+                v.l[0] = 1;
+                for (int k = 0; k < 64; ++k) v = Field<F>::add(v, v);
+                for (int j = 0; j < 8; ++j) {
+                    Fe t = Field<F>::mul(y, v);
+                    memcpy(T.t[j], t.l, 32);
+                    for (int k = 0; k < 32; ++k) v = Field<F>::add(v, v);
+                }
+                r = Field<F>::mul_fixed(x, T);
+                break;
+            }
+            case 8: {  // lazy sum of the products of this and the next 3 pairs (wrapping), reduced once
+                Wide w = Field<F>::wide_zero();
+                for (size_t k = 0; k < 4; ++k) {
+                    Fe p, q;
+                    memcpy(p.l, a + 8 * ((i + k) % n), 32);
+                    memcpy(q.l, b + 8 * ((i + k) % n), 32);
+                    Field<F>::mac_wide(w, p, q);
+                }
+                r = Field<F>::reduce_wide(w);
+                break;
+            }
+            case 9: {  // the same product accumulated 5000 times (exercises the guard limb)
+                Wide w = Field<F>::wide_zero();
+                for (int k = 0; k < 5000; ++k) Field<F>::mac_wide(w, x, y);
+                r = Field<F>::reduce_wide(w);
+                break;
+            }
             default: r = Field<F>::zero();
         }
         memcpy(out + 8 * i, r.l, 32);

@@ -51,5 +51,9 @@ def test_limb_arithmetic(shim, fid):
     assert run(shim, fid, 3, a, b) == want      # 32-bit lo/hi formulation
     assert run(shim, fid, 4, a, b) == [x * R.R256 % p for x in a]
     assert run(shim, fid, 5, a, b) == [x * rinv % p for x in a]
+    assert run(shim, fid, 7, a, b) == want      # fixed-multiplicand product (challenge table)
+    n = len(a)
+    assert run(shim, fid, 8, a, b) == [sum(a[(i + k) % n] * b[(i + k) % n] for k in range(4)) * rinv % p for i in range(n)]
+    assert run(shim, fid, 9, a[:200], b[:200]) == [5000 * x * y * rinv % p for x, y in zip(a[:200], b[:200])]
     # fold(a, b, r=to_mont(b)) in Montgomery arithmetic == a + b*(b-a) on raw residues
     assert run(shim, fid, 6, a, b) == [(x + y * (y - x)) % p for x, y in zip(a, b)]

@@ -43,8 +43,8 @@ void l_fold_tables(const FoldTablesArgs& a, int grid, cudaStream_t s) { k_fold_t
 void l_final_bind(const FoldTablesArgs& a, Fe* out, volatile unsigned int* flag, unsigned int seq, cudaStream_t s) {
     k_final_bind<FT><<<1, 32, 0, s>>>(a, out, flag, seq);
 }
-void l_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const Fe& r, int grid, cudaStream_t s) {
-    k_fold<FT><<<grid, BLOCK, 0, s>>>(in, out, n_out, shift, r);
+void l_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const FixedMul& rt, int grid, cudaStream_t s) {
+    k_fold<FT><<<grid, BLOCK, 0, s>>>(in, out, n_out, shift, rt);
 }
 void l_aos_to_planar(const void* aos, TabRef out, uint64_t n, uint64_t first, uint64_t stride, int conv, int grid, cudaStream_t s) {
     k_aos_to_planar<FT><<<grid, BLOCK, 0, s>>>((const uint4*)aos, out, n, first, stride, conv);

@@ -131,6 +131,28 @@ struct alignas(16) Fe {
     uint32_t l[8];
 };
 
+// ------------------------------------------------ 64-bit carry helpers
+#if defined(__CUDA_ARCH__)
+ZK_D uint64_t addc64(uint64_t a, uint64_t b) { uint64_t r; ZK_ASM("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+#else
+inline uint64_t addc64(uint64_t a, uint64_t b) { return a + b + detail::cf(); }
+#endif
+
+// Multiplication by a value fixed for a whole launch (the round challenge r):
+// t[i] = r * 2^(32 i + 64) * R^-1 mod p as plain 8 x u32 integers, made on the
+// host once per round.  x*r*R^-1 = (sum_i x_i * t[i]) * 2^-64, i.e. 64 wide
+// multiply-accumulates WITHOUT interleaved reduction plus two reduction rows
+// (16 more) instead of the 136 of a general Montgomery product.
+struct FixedMul {
+    uint32_t t[8][8];
+};
+
+// 512-bit (+32 guard bits) integer accumulator for sums of raw products
+// a*b of Montgomery residues; one Montgomery reduction at the very end.
+struct Wide {
+    uint32_t l[17];
+};
+
 template <class F>
 struct Field {
     ZK_HD static Fe zero() {
@@ -322,6 +344,157 @@ struct Field {
         return reduce_once(r);
     }
     ZK_HD static Fe sqr(const Fe& a) { return mul(a, a); }
+
+    // ---- fixed-multiplicand product: x * r * R^-1 mod p (see FixedMul) ------
+    ZK_HD static Fe mul_fixed(const Fe& x, const FixedMul& T) {
+        // S = sum_i x_i * T_i < 2^289 in two interleaved accumulators:
+        // ev[k] = limbs (2k, 2k+1), od[k] = limbs (2k+1, 2k+2); word 4 collects carries.
+        uint64_t ev[5], od[5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ev[k] = mul_wide(T.t[0][2 * k], x.l[0]);
+            od[k] = mul_wide(T.t[0][2 * k + 1], x.l[0]);
+        }
+        ev[4] = 0;
+        od[4] = 0;
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            ev[0] = madw_cc(T.t[i][0], x.l[i], ev[0]);
+            ev[1] = madwc_cc(T.t[i][2], x.l[i], ev[1]);
+            ev[2] = madwc_cc(T.t[i][4], x.l[i], ev[2]);
+            ev[3] = madwc_cc(T.t[i][6], x.l[i], ev[3]);
+            ev[4] = addc64(ev[4], 0ull);
+            od[0] = madw_cc(T.t[i][1], x.l[i], od[0]);
+            od[1] = madwc_cc(T.t[i][3], x.l[i], od[1]);
+            od[2] = madwc_cc(T.t[i][5], x.l[i], od[2]);
+            od[3] = madwc_cc(T.t[i][7], x.l[i], od[3]);
+            od[4] = addc64(od[4], 0ull);
+        }
+        // merge to 10 x 32-bit limbs: s = ev + (od << 32)
+        uint32_t s[10];
+        s[0] = lo32(ev[0]);
+        s[1] = add_cc(hi32(ev[0]), lo32(od[0]));
+        s[2] = addc_cc(lo32(ev[1]), hi32(od[0]));
+        s[3] = addc_cc(hi32(ev[1]), lo32(od[1]));
+        s[4] = addc_cc(lo32(ev[2]), hi32(od[1]));
+        s[5] = addc_cc(hi32(ev[2]), lo32(od[2]));
+        s[6] = addc_cc(lo32(ev[3]), hi32(od[2]));
+        s[7] = addc_cc(hi32(ev[3]), lo32(od[3]));
+        s[8] = addc_cc(lo32(ev[4]), hi32(od[3]));
+        s[9] = addc(hi32(ev[4]), lo32(od[4]));
+        // two reduction rows: s = (s + m*p) / 2^32
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            const uint32_t m = mul_lo(s[0], F::INV);
+            s[0] = mad_lo_cc(F::P(0), m, s[0]);
+            s[1] = madc_hi_cc(F::P(0), m, s[1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                s[j] = madc_lo_cc(F::P(j), m, s[j]);
+                s[j + 1] = madc_hi_cc(F::P(j), m, s[j + 1]);
+            }
+            s[8] = addc_cc(s[8], 0u);
+            s[9] = addc(s[9], 0u);
+            s[1] = mad_lo_cc(F::P(1), m, s[1]);
+            s[2] = madc_hi_cc(F::P(1), m, s[2]);
+#pragma unroll
+            for (int j = 3; j < 8; j += 2) {
+                s[j] = madc_lo_cc(F::P(j), m, s[j]);
+                s[j + 1] = madc_hi_cc(F::P(j), m, s[j + 1]);
+            }
+            s[9] = addc(s[9], 0u);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) s[j] = s[j + 1];
+            s[9] = 0;
+        }
+        Fe r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.l[j] = s[j];
+        return reduce_once(r);  // s < 2p, s[8] == 0
+    }
+    // a + r*(b - a) with the fixed-multiplicand product
+    ZK_HD static Fe fold_fixed(const Fe& a, const Fe& b, const FixedMul& T) { return add(a, mul_fixed(sub(b, a), T)); }
+
+    // ---- lazy sums of products ---------------------------------------------
+    ZK_HD static Wide wide_zero() {
+        Wide w;
+#pragma unroll
+        for (int i = 0; i < 17; ++i) w.l[i] = 0;
+        return w;
+    }
+    // acc += a * b (plain 512-bit integer product; up to 2^36 products fit)
+    ZK_HD static void mac_wide(Wide& acc, const Fe& a, const Fe& b) {
+        // schoolbook rows in order; ev[k] = limbs (2k, 2k+1), od[k] = limbs (2k+1, 2k+2)
+        uint64_t ev[8], od[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ev[k] = mul_wide(a.l[2 * k], b.l[0]);
+            od[k] = mul_wide(a.l[2 * k + 1], b.l[0]);
+            ev[k + 4] = 0;
+            od[k + 4] = 0;
+        }
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            if (j & 1) {  // a_even * b_j -> od[(j-1)/2 ..], a_odd * b_j -> ev[(j+1)/2 ..]
+                const int o = (j - 1) / 2, e = (j + 1) / 2;
+                od[o] = madw_cc(a.l[0], b.l[j], od[o]);
+                od[o + 1] = madwc_cc(a.l[2], b.l[j], od[o + 1]);
+                od[o + 2] = madwc_cc(a.l[4], b.l[j], od[o + 2]);
+                od[o + 3] = madwc_cc(a.l[6], b.l[j], od[o + 3]);
+                if (o + 4 < 8) od[o + 4] = addc64(od[o + 4], 0ull);
+                ev[e] = madw_cc(a.l[1], b.l[j], ev[e]);
+                ev[e + 1] = madwc_cc(a.l[3], b.l[j], ev[e + 1]);
+                ev[e + 2] = madwc_cc(a.l[5], b.l[j], ev[e + 2]);
+                ev[e + 3] = madwc_cc(a.l[7], b.l[j], ev[e + 3]);
+                if (e + 4 < 8) ev[e + 4] = addc64(ev[e + 4], 0ull);
+            } else {
+                const int e = j / 2;
+                ev[e] = madw_cc(a.l[0], b.l[j], ev[e]);
+                ev[e + 1] = madwc_cc(a.l[2], b.l[j], ev[e + 1]);
+                ev[e + 2] = madwc_cc(a.l[4], b.l[j], ev[e + 2]);
+                ev[e + 3] = madwc_cc(a.l[6], b.l[j], ev[e + 3]);
+                if (e + 4 < 8) ev[e + 4] = addc64(ev[e + 4], 0ull);
+                od[e] = madw_cc(a.l[1], b.l[j], od[e]);
+                od[e + 1] = madwc_cc(a.l[3], b.l[j], od[e + 1]);
+                od[e + 2] = madwc_cc(a.l[5], b.l[j], od[e + 2]);
+                od[e + 3] = madwc_cc(a.l[7], b.l[j], od[e + 3]);
+                if (e + 4 < 8) od[e + 4] = addc64(od[e + 4], 0ull);
+            }
+        }
+        // acc += ev ; acc += od << 32
+        acc.l[0] = add_cc(acc.l[0], lo32(ev[0]));
+        acc.l[1] = addc_cc(acc.l[1], hi32(ev[0]));
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            acc.l[2 * k] = addc_cc(acc.l[2 * k], lo32(ev[k]));
+            acc.l[2 * k + 1] = addc_cc(acc.l[2 * k + 1], hi32(ev[k]));
+        }
+        acc.l[16] = addc(acc.l[16], 0u);
+        acc.l[1] = add_cc(acc.l[1], lo32(od[0]));
+        acc.l[2] = addc_cc(acc.l[2], hi32(od[0]));
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            acc.l[2 * k + 1] = addc_cc(acc.l[2 * k + 1], lo32(od[k]));
+            if (k < 7) acc.l[2 * k + 2] = addc_cc(acc.l[2 * k + 2], hi32(od[k]));
+        }
+        acc.l[16] = addc(acc.l[16], hi32(od[7]));
+    }
+    // acc * R^-1 mod p, fully reduced: acc = A0 + A1*2^256 + A2*2^512 ->
+    // A0*R^-1 + A1 + A2*R  =  mul(1, A0) + mul(R, A1) + mul(R^2, A2)   (mul = Montgomery product).
+    // The chunks A_k may exceed p: they go in as the limb-iterated operand `b`, for which mul() only
+    // needs b < 2^256 (its row invariant T < a + p depends on the full operand `a` alone).
+    ZK_HD static Fe reduce_wide(const Wide& acc) {
+        Fe a0, a1, a2 = zero(), u = zero();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a0.l[i] = acc.l[i];
+            a1.l[i] = acc.l[8 + i];
+        }
+        a2.l[0] = acc.l[16];
+        u.l[0] = 1;
+        return add(add(mul(u, a0), mul(one(), a1)), mul(r2(), a2));
+    }
+
 
     ZK_HD static Fe to_mont(const Fe& canon) { return mul(canon, r2()); }
     ZK_HD static Fe from_mont(const Fe& m) {

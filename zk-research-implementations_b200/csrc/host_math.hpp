@@ -204,6 +204,27 @@ struct HostField {
     }
 };
 
+// Per-launch multiplication table for a fixed multiplicand r (fr.cuh FixedMul):
+// t[i] = r * 2^(32 i + 64) * R^-1 mod p = mul(r, 2^(32 i + 64) mod p).
+struct FixedMulBuilder {
+    Fe c[8];  // 2^(32 i + 64) mod p as plain integers
+    void init(const HostField& H) {
+        Fe v = H.zero();
+        v.l[0] = 1;
+        for (int k = 0; k < 64; ++k) v = H.add(v, v);
+        for (int i = 0; i < 8; ++i) {
+            c[i] = v;
+            for (int k = 0; k < 32; ++k) v = H.add(v, v);
+        }
+    }
+    void make(const HostField& H, const Fe& r, FixedMul* out) const {
+        for (int i = 0; i < 8; ++i) {
+            Fe t = H.mul(r, c[i]);
+            std::memcpy(out->t[i], t.l, 32);
+        }
+    }
+};
+
 // -------------------------------------------------------------- Transcript
 // fiat_shamir_transcript.rs:5-30
 struct TranscriptImpl {

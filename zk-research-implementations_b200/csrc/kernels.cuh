@@ -56,7 +56,7 @@ struct ScArgs {
     int n_tables;      // tables to fold (product-major: table = p*D + f)
     int n_products;    // P (KIND_PROD)
     uint64_t n_out;    // entries per table AFTER the fold (k_sc_fold_eval) / table size (k_sc_eval)
-    Fe r;              // challenge being bound (k_sc_fold_eval)
+    FixedMul rt;       // multiplication table of the challenge being bound (k_sc_fold_eval)
     FinishArgs fin;
 };
 
@@ -120,6 +120,21 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a) {
     __shared__ Fe smem[BLOCK / 32][NPTS];
     __shared__ bool is_last;
     block_sum<F, NPTS>(acc, smem);
+    if (gridDim.x == 1) {  // small tables: the CTA's sums are the round's sums
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int p = 0; p < NPTS; ++p) {
+                a.result[p] = acc[p];
+                if (a.result_wide) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a.result_wide[p * 8 + k] = acc[p].l[k];
+                }
+            }
+            __threadfence_system();
+            if (a.flag) *a.flag = a.seq;
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int p = 0; p < NPTS; ++p) a.partials[(uint64_t)blockIdx.x * NPTS + p] = acc[p];
@@ -162,81 +177,149 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a) {
 }
 
 // --------------------------------------------- round-polynomial evaluation
-// Adds this pair position's contribution to the NPTS accumulators.
-// KIND_PROD: sum over products p of prod_f (lo_f + t*(hi_f-lo_f)), t = 0..NPTS-1
-//            (get_round_partial_polynomial_proof_gkr, sum_check_protocol.rs:152-166,
-//             without materialising the (d+1) folded copies it builds).
-// KIND_XYZ : X(t)*Y(t) + Z(t) -- the two-phase GKR integrand.
-template <class F, int D, int NPTS>
-__device__ __forceinline__ void eval_product(const Fe* lo, const Fe* hi, Fe* acc) {
+// The round polynomial s(t) = sum over pair positions of the integrand at
+// lo + t*(hi - lo), t = 0..NPTS-1 (get_round_partial_polynomial_proof_gkr,
+// sum_check_protocol.rs:152-166, without materialising the (d+1) folded copies).
+// KIND_PROD: integrand = sum over products p of prod_f table[p][f]
+// KIND_XYZ : integrand = X*Y + Z  (two-phase GKR)
+//
+// Accumulation is LAZY: the raw 512-bit products of Montgomery residues are
+// summed in Wide accumulators and reduced once per thread (fr.cuh mac_wide /
+// reduce_wide), which halves the multiplier work of every product.
+// SKIP1: s(1) is not computed -- the host derives it from the running claim,
+// s(1) = claim - s(0); slot layout is then {s(0), s(2), s(3), ...}.
+template <int NPTS, bool SKIP1>
+struct Slots {
+    static constexpr int N = SKIP1 ? NPTS - 1 : NPTS;
+    __device__ __forceinline__ static constexpr int of(int t) { return SKIP1 ? (t == 0 ? 0 : t - 1) : t; }
+};
+
+template <class F, int D, int NPTS, bool SKIP1>
+struct RoundAcc {
     typedef Field<F> Fd;
-    if (D == 1) {
-        acc[0] = Fd::add(acc[0], lo[0]);
-        acc[1] = Fd::add(acc[1], hi[0]);
+    typedef Slots<NPTS, SKIP1> S;
+    Wide w[S::N];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int p = 0; p < S::N; ++p) w[p] = Fd::wide_zero();
+    }
+    // one product of D factors at this pair position
+    __device__ __forceinline__ void add_product(const Fe* lo, const Fe* hi) {
+        {
+            Fe m = lo[0];
+#pragma unroll
+            for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, lo[f]);
+            Fd::mac_wide(w[0], m, lo[D - 1]);
+        }
+        if (!SKIP1) {
+            Fe m = hi[0];
+#pragma unroll
+            for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, hi[f]);
+            Fd::mac_wide(w[S::of(1)], m, hi[D - 1]);
+        }
+        Fe cur[D], dl[D];
+#pragma unroll
+        for (int f = 0; f < D; ++f) {
+            dl[f] = Fd::sub(hi[f], lo[f]);
+            cur[f] = hi[f];
+        }
+#pragma unroll
+        for (int t = 2; t < NPTS; ++t) {
+#pragma unroll
+            for (int f = 0; f < D; ++f) cur[f] = Fd::add(cur[f], dl[f]);
+            Fe m = cur[0];
+#pragma unroll
+            for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, cur[f]);
+            Fd::mac_wide(w[S::of(t)], m, cur[D - 1]);
+        }
+    }
+    __device__ __forceinline__ void finish(Fe* out) {
+#pragma unroll
+        for (int p = 0; p < S::N; ++p) out[p] = Fd::reduce_wide(w[p]);
+    }
+};
+// D == 1 (plain sumcheck, sum_check_protocol.rs:168-175): sums of table values, modular adds.
+template <class F, int NPTS, bool SKIP1>
+struct RoundAcc<F, 1, NPTS, SKIP1> {
+    typedef Field<F> Fd;
+    typedef Slots<NPTS, SKIP1> S;
+    Fe v[S::N];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int p = 0; p < S::N; ++p) v[p] = Fd::zero();
+    }
+    __device__ __forceinline__ void add_product(const Fe* lo, const Fe* hi) {
+        v[0] = Fd::add(v[0], lo[0]);
+        if (!SKIP1) v[S::of(1)] = Fd::add(v[S::of(1)], hi[0]);
         Fe cur = hi[0];
         Fe dl = Fd::sub(hi[0], lo[0]);
 #pragma unroll
         for (int t = 2; t < NPTS; ++t) {
             cur = Fd::add(cur, dl);
-            acc[t] = Fd::add(acc[t], cur);
+            v[S::of(t)] = Fd::add(v[S::of(t)], cur);
         }
-        return;
     }
-    Fe m0 = lo[0], m1 = hi[0];
+    __device__ __forceinline__ void finish(Fe* out) {
 #pragma unroll
-    for (int f = 1; f < D; ++f) {
-        m0 = Fd::mul(m0, lo[f]);
-        m1 = Fd::mul(m1, hi[f]);
+        for (int p = 0; p < S::N; ++p) out[p] = v[p];
     }
-    acc[0] = Fd::add(acc[0], m0);
-    acc[1] = Fd::add(acc[1], m1);
-    Fe cur[D], dl[D];
-#pragma unroll
-    for (int f = 0; f < D; ++f) {
-        dl[f] = Fd::sub(hi[f], lo[f]);
-        cur[f] = hi[f];
-    }
-#pragma unroll
-    for (int t = 2; t < NPTS; ++t) {
-#pragma unroll
-        for (int f = 0; f < D; ++f) cur[f] = Fd::add(cur[f], dl[f]);
-        Fe m = cur[0];
-#pragma unroll
-        for (int f = 1; f < D; ++f) m = Fd::mul(m, cur[f]);
-        acc[t] = Fd::add(acc[t], m);
-    }
-}
-
-template <class F>
-__device__ __forceinline__ void eval_xyz(const Fe* lo, const Fe* hi, Fe* acc) {
+};
+// X*Y + Z at t = 0, (1), 2: products lazily, the Z column with modular adds.
+template <class F, bool SKIP1>
+struct XyzAcc {
     typedef Field<F> Fd;
-    acc[0] = Fd::add(acc[0], Fd::add(Fd::mul(lo[0], lo[1]), lo[2]));
-    acc[1] = Fd::add(acc[1], Fd::add(Fd::mul(hi[0], hi[1]), hi[2]));
-    Fe x2 = Fd::sub(Fd::dbl(hi[0]), lo[0]);
-    Fe y2 = Fd::sub(Fd::dbl(hi[1]), lo[1]);
-    Fe z2 = Fd::sub(Fd::dbl(hi[2]), lo[2]);
-    acc[2] = Fd::add(acc[2], Fd::add(Fd::mul(x2, y2), z2));
-}
+    typedef Slots<3, SKIP1> S;
+    Wide w[S::N];
+    Fe z[S::N];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int p = 0; p < S::N; ++p) {
+            w[p] = Fd::wide_zero();
+            z[p] = Fd::zero();
+        }
+    }
+    __device__ __forceinline__ void add(const Fe* lo, const Fe* hi) {
+        Fd::mac_wide(w[0], lo[0], lo[1]);
+        z[0] = Fd::add(z[0], lo[2]);
+        if (!SKIP1) {
+            Fd::mac_wide(w[S::of(1)], hi[0], hi[1]);
+            z[S::of(1)] = Fd::add(z[S::of(1)], hi[2]);
+        }
+        Fe x2 = Fd::sub(Fd::dbl(hi[0]), lo[0]);
+        Fe y2 = Fd::sub(Fd::dbl(hi[1]), lo[1]);
+        Fe z2 = Fd::sub(Fd::dbl(hi[2]), lo[2]);
+        Fd::mac_wide(w[S::of(2)], x2, y2);
+        z[S::of(2)] = Fd::add(z[S::of(2)], z2);
+    }
+    __device__ __forceinline__ void finish(Fe* out) {
+#pragma unroll
+        for (int p = 0; p < S::N; ++p) out[p] = Fd::add(Fd::reduce_wide(w[p]), z[p]);
+    }
+};
 
-// K7: evaluations of the first round (no challenge to bind yet).
+// K7: evaluations of the first round (no challenge to bind yet): all NPTS points.
 template <class F, int KIND, int D, int NPTS>
 __global__ void __launch_bounds__(BLOCK) k_sc_eval(const ScArgs a) {
-    typedef Field<F> Fd;
-    Fe acc[NPTS];
-#pragma unroll
-    for (int p = 0; p < NPTS; ++p) acc[p] = Fd::zero();
     const uint64_t half = a.n_out >> 1;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
-    for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
-        if (KIND == KIND_XYZ) {
+    Fe out[NPTS];
+    if (KIND == KIND_XYZ) {
+        XyzAcc<F, false> acc;
+        acc.init();
+        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
             Fe lo[3], hi[3];
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
                 lo[f] = ld_fe(a.in[f], j);
                 hi[f] = ld_fe(a.in[f], j + half);
             }
-            eval_xyz<F>(lo, hi, acc);
-        } else {
+            acc.add(lo, hi);
+        }
+        acc.finish(out);
+    } else {
+        RoundAcc<F, D, NPTS, false> acc;
+        acc.init();
+        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
             for (int p = 0; p < a.n_products; ++p) {
                 Fe lo[D], hi[D];
 #pragma unroll
@@ -244,11 +327,12 @@ __global__ void __launch_bounds__(BLOCK) k_sc_eval(const ScArgs a) {
                     lo[f] = ld_fe(a.in[p * D + f], j);
                     hi[f] = ld_fe(a.in[p * D + f], j + half);
                 }
-                eval_product<F, D, NPTS>(lo, hi, acc);
+                acc.add_product(lo, hi);
             }
         }
+        acc.finish(out);
     }
-    finish_round<F, NPTS>(acc, a.fin);
+    finish_round<F, NPTS>(out, a.fin);
 }
 
 // K8: one HBM pass per round.  Thread j owns the quad
@@ -257,30 +341,34 @@ __global__ void __launch_bounds__(BLOCK) k_sc_eval(const ScArgs a) {
 // (j+n_out/2, j+n_out+n_out/2) -> new[j+n_out/2], stores both, and the pair
 // (new[j], new[j+n_out/2]) is exactly the next round's (lo, hi).
 // In-place operation (out == in) is safe: a thread only overwrites entries
-// that no other thread reads.
+// that no other thread reads.  Returns NPTS-1 sums: s(0), s(2), .. (SKIP1).
 template <class F, int KIND, int D, int NPTS>
 __global__ void __launch_bounds__(BLOCK) k_sc_fold_eval(const ScArgs a) {
     typedef Field<F> Fd;
-    Fe acc[NPTS];
-#pragma unroll
-    for (int p = 0; p < NPTS; ++p) acc[p] = Fd::zero();
     const uint64_t n_out = a.n_out, half = n_out >> 1;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
-    const Fe r = a.r;
-    for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
-        if (KIND == KIND_XYZ) {
+    Fe out[NPTS - 1];
+    if (KIND == KIND_XYZ) {
+        XyzAcc<F, true> acc;
+        acc.init();
+        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
             Fe lo[3], hi[3];
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
                 Fe x0 = ld_fe(a.in[f], j), x1 = ld_fe(a.in[f], j + n_out);
                 Fe y0 = ld_fe(a.in[f], j + half), y1 = ld_fe(a.in[f], j + half + n_out);
-                lo[f] = Fd::fold(x0, x1, r);
-                hi[f] = Fd::fold(y0, y1, r);
+                lo[f] = Fd::fold_fixed(x0, x1, a.rt);
+                hi[f] = Fd::fold_fixed(y0, y1, a.rt);
                 st_fe(a.out[f], j, lo[f]);
                 st_fe(a.out[f], j + half, hi[f]);
             }
-            eval_xyz<F>(lo, hi, acc);
-        } else {
+            acc.add(lo, hi);
+        }
+        acc.finish(out);
+    } else {
+        RoundAcc<F, D, NPTS, true> acc;
+        acc.init();
+        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
             for (int p = 0; p < a.n_products; ++p) {
                 Fe lo[D], hi[D];
 #pragma unroll
@@ -288,16 +376,17 @@ __global__ void __launch_bounds__(BLOCK) k_sc_fold_eval(const ScArgs a) {
                     const TabRef& ti = a.in[p * D + f];
                     Fe x0 = ld_fe(ti, j), x1 = ld_fe(ti, j + n_out);
                     Fe y0 = ld_fe(ti, j + half), y1 = ld_fe(ti, j + half + n_out);
-                    lo[f] = Fd::fold(x0, x1, r);
-                    hi[f] = Fd::fold(y0, y1, r);
+                    lo[f] = Fd::fold_fixed(x0, x1, a.rt);
+                    hi[f] = Fd::fold_fixed(y0, y1, a.rt);
                     st_fe(a.out[p * D + f], j, lo[f]);
                     st_fe(a.out[p * D + f], j + half, hi[f]);
                 }
-                eval_product<F, D, NPTS>(lo, hi, acc);
+                acc.add_product(lo, hi);
             }
         }
+        acc.finish(out);
     }
-    finish_round<F, NPTS>(acc, a.fin);
+    finish_round<F, NPTS - 1>(out, a.fin);
 }
 
 // K3/K1 for lists: fold variable 0 of n_tables tables of 2*n_out entries.
@@ -306,7 +395,7 @@ struct FoldTablesArgs {
     TabRef out[MAXT];
     int n_tables;
     uint64_t n_out;
-    Fe r;
+    FixedMul rt;  // multiplication table of the challenge (fr.cuh FixedMul)
 };
 template <class F>
 __global__ void __launch_bounds__(BLOCK) k_fold_tables(const FoldTablesArgs a) {
@@ -316,7 +405,7 @@ __global__ void __launch_bounds__(BLOCK) k_fold_tables(const FoldTablesArgs a) {
         const int t = (int)(w / a.n_out);
         const uint64_t j = w - (uint64_t)t * a.n_out;
         Fe x0 = ld_fe(a.in[t], j), x1 = ld_fe(a.in[t], j + a.n_out);
-        st_fe(a.out[t], j, Field<F>::fold(x0, x1, a.r));
+        st_fe(a.out[t], j, Field<F>::fold_fixed(x0, x1, a.rt));
     }
 }
 
@@ -326,7 +415,7 @@ template <class F>
 __global__ void k_final_bind(const FoldTablesArgs a, Fe* out, volatile unsigned int* flag, unsigned int seq) {
     const int t = threadIdx.x;
     if (t < a.n_tables) {
-        Fe v = Field<F>::fold(ld_fe(a.in[t], 0), ld_fe(a.in[t], 1), a.r);
+        Fe v = Field<F>::fold_fixed(ld_fe(a.in[t], 0), ld_fe(a.in[t], 1), a.rt);
         st_fe(a.out[t], 0, v);
         out[t] = v;
         __threadfence_system();
@@ -339,13 +428,13 @@ __global__ void k_final_bind(const FoldTablesArgs a, Fe* out, volatile unsigned 
 // `shift` = n_vars - 1 - bit: output index v pairs inputs insert_bit(v, shift)
 // and that | (1 << shift).
 template <class F>
-__global__ void __launch_bounds__(BLOCK) k_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, Fe r) {
+__global__ void __launch_bounds__(BLOCK) k_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const FixedMul rt) {
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
     const uint64_t lowmask = (1ull << shift) - 1;
     for (uint64_t v = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; v < n_out; v += step) {
         const uint64_t i0 = ((v >> shift) << (shift + 1)) | (v & lowmask);
         const uint64_t i1 = i0 | (1ull << shift);
-        st_fe(out, v, Field<F>::fold(ld_fe(in, i0), ld_fe(in, i1), r));
+        st_fe(out, v, Field<F>::fold_fixed(ld_fe(in, i0), ld_fe(in, i1), rt));
     }
 }
 

@@ -95,6 +95,8 @@ struct SumPolyState {
     std::vector<Table> gath;      // after the multi-GPU gather
     uint64_t n0 = 0;              // local entries per table before any bind
     uint64_t cur_n = 0;           // local entries per table now
+    Fe last_evals[MAXPTS];        // s(0..d) of the current round (the claim chain: s(1) = claim - s(0))
+    bool have_evals = false;
     int state = 0;                // 0 = unbound (src), 1 = in work, 2 = in gath
     bool sharded = false;         // partial sums need the allreduce
     Table& cur(int t) { return state == 0 ? src[t] : (state == 1 ? work[t] : gath[t]); }
@@ -152,6 +154,7 @@ struct zkb_ctx {
     int rank = 0, world = 1, log2world = 0;
     uint32_t gather_log2 = 12;
     RoundInterpolator interp[MAXPTS + 1];
+    FixedMulBuilder fmb;
     std::unordered_map<std::string, int> occ_cache;
     // per-launch event timing (zkb_ctx_profile)
     bool prof = false;
@@ -401,6 +404,7 @@ void sp_release(zkb_ctx* c, SumPolyState* sp) {
 }
 void sp_reset(zkb_ctx* c, SumPolyState* sp) {
     sp->state = 0;
+    sp->have_evals = false;
     sp->cur_n = sp->n0;
     sp->sharded = c->comm != nullptr && c->world > 1;
     for (auto& t : sp->gath) free_table(c, &t);
@@ -420,7 +424,10 @@ int32_t sp_round_evals(zkb_ctx* c, SumPolyState* sp, Fe* evals) {
     prof_begin(c, ZKB_K_SC_EVAL, 32.0 * (double)sp->sel.size() * (double)sp->cur_n);
     if (!c->K->sc_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_eval: shape not instantiated");
     ZK_TRY(check_launch(c, "k_sc_eval"));
-    return collect(c, sp->npts, sp->sharded, a.fin, evals);
+    ZK_TRY(collect(c, sp->npts, sp->sharded, a.fin, evals));
+    for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
+    sp->have_evals = true;
+    return ZKB_OK;
 }
 
 int32_t sp_ensure_work(zkb_ctx* c, SumPolyState* sp) {
@@ -475,7 +482,8 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
         }
         fa.n_tables = T;
         fa.n_out = 1;
-        fa.r = r;
+        c->fmb.make(c->H, r, &fa.rt);
+        sp->have_evals = false;
         unsigned int seq = ++c->seq;
         prof_begin(c, ZKB_K_FINAL_BIND, 96.0 * T);
         c->K->final_bind(fa, c->h_res, c->h_flag, seq, c->stream);
@@ -505,16 +513,21 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
         }
         fa.n_tables = k;
         fa.n_out = n_out;
-        fa.r = r;
+        c->fmb.make(c->H, r, &fa.rt);
         prof_begin(c, ZKB_K_FOLD_TABLES, 96.0 * (double)k * (double)n_out);
         c->K->fold_tables(fa, grid_for(c, n_out * (uint64_t)k, 8), c->stream);
         ZK_TRY(check_launch(c, "k_fold_tables"));
         if (all) {
             if (sp->state == 0) sp->state = 1;
             sp->cur_n = n_out;
+            sp->have_evals = false;
             if (evals) return sp_round_evals(c, sp, evals);  // only reached for sharded 1-entry shards
             return ZKB_OK;
         }
+    }
+    if (!sp->have_evals) {  // bind requested before this round's evaluations were taken: take them now
+        Fe tmp[MAXPTS];
+        ZK_TRY(sp_round_evals(c, sp, tmp));
     }
     ScArgs a;
     std::memset(&a, 0, sizeof a);
@@ -525,15 +538,26 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
     a.n_tables = (int)sp->sel.size();
     a.n_products = sp->kP;
     a.n_out = n_out;
-    a.r = r;
+    c->fmb.make(c->H, r, &a.rt);
+    // the claim chain: this round's s(0) + s(1) equals the previous round polynomial at r
+    const RoundInterpolator& ip = c->interp[sp->npts];
+    Fe co[MAXPTS];
+    const int colen = ip.interpolate(sp->last_evals, co);
+    const Fe claim = uni_evaluate(c->H, co, colen, r);
     const int grid = grid_for(c, n_out / 2, sc_occ(c, 1, sp->kind, sp->kD, sp->npts));
-    ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
+    ZK_TRY(prep_finish(c, grid, sp->npts - 1, sp->sharded, &a.fin));
     prof_begin(c, ZKB_K_SC_FOLD_EVAL, 96.0 * (double)sp->sel.size() * (double)n_out);
     if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
     ZK_TRY(check_launch(c, "k_sc_fold_eval"));
     if (sp->state == 0) sp->state = 1;
     sp->cur_n = n_out;
-    return collect(c, sp->npts, sp->sharded, a.fin, evals);
+    Fe got[MAXPTS];
+    ZK_TRY(collect(c, sp->npts - 1, sp->sharded, a.fin, got));
+    evals[0] = got[0];
+    evals[1] = c->H.sub(claim, got[0]);
+    for (int t = 2; t < sp->npts; ++t) evals[t] = got[t - 1];
+    for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
+    return ZKB_OK;
 }
 
 int32_t sp_final_values(zkb_ctx* c, SumPolyState* sp, Fe* vals) {
@@ -647,7 +671,7 @@ int32_t multi_fold(zkb_ctx* c, const Table& src, const Fe* rs, uint32_t k, Table
         fa.out[0] = w.ref();
         fa.n_tables = 1;
         fa.n_out = n / 2;
-        fa.r = rs[i];
+        c->fmb.make(c->H, rs[i], &fa.rt);
         prof_begin(c, ZKB_K_FOLD_TABLES, 96.0 * (double)(n / 2));
         c->K->fold_tables(fa, grid_for(c, n / 2, 8), c->stream);
         ZK_TRY(check_launch(c, "k_fold_tables"));
@@ -963,6 +987,7 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
     if (cudaMalloc((void**)&c->d_res, sizeof(Fe) * 64) != cudaSuccess) return ZKB_ERR_CUDA;
     if (cudaMalloc((void**)&c->d_wide, sizeof(unsigned long long) * 8 * MAXPTS) != cudaSuccess) return ZKB_ERR_CUDA;
     for (int n = 2; n <= MAXPTS; ++n) c->interp[n].init(c->H, n);
+    c->fmb.init(c->H);
     *out = c.release();
     return ZKB_OK;
 }
@@ -1130,8 +1155,10 @@ int32_t zkb_mle_partial_evaluate(zkb_ctx* c, zkb_mle in, uint32_t bit, const uin
     if ((int)bit >= nv) ZK_FAIL(c, ZKB_ERR_ARITY, "partial_evaluate: bit out of range");
     Table w;
     ZK_TRY(alloc_table(c, t->n / 2, &w));
+    FixedMul rt;
+    c->fmb.make(c->H, fe_from_u64x4(value), &rt);
     prof_begin(c, ZKB_K_FOLD, 96.0 * (double)(t->n / 2));
-    c->K->fold(t->ref(), w.ref(), t->n / 2, (uint32_t)(nv - 1 - (int)bit), fe_from_u64x4(value), grid_for(c, t->n / 2, 8), c->stream);
+    c->K->fold(t->ref(), w.ref(), t->n / 2, (uint32_t)(nv - 1 - (int)bit), rt, grid_for(c, t->n / 2, 8), c->stream);
     ZK_TRY(check_launch(c, "k_fold"));
     *out = put_mle(c, w);
     return ZKB_OK;
