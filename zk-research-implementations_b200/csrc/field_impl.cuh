@@ -27,11 +27,21 @@ bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaSt
 #undef X
     return false;
 }
+int l_sc_tail(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream_t s) {
+    void* params[1] = {const_cast<TailArgs*>(&a)};
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) \
+        return (int)cudaLaunchCooperativeKernel((const void*)k_sc_tail<FT, K, DD, NP>, dim3(grid), dim3(BLOCK), params, 0, s);
+    ZKB_SC_CASES(X)
+#undef X
+    return -1;
+}
 int l_sc_occupancy(int fused, int kind, int D, int npts) {
     int nb = 0;
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        if (fused) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_fold_eval<FT, K, DD, NP>, BLOCK, 0); \
+        if (fused == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_tail<FT, K, DD, NP>, BLOCK, 0); \
+        else if (fused) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_fold_eval<FT, K, DD, NP>, BLOCK, 0); \
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_eval<FT, K, DD, NP>, BLOCK, 0); \
         return nb; \
     }
@@ -93,7 +103,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_occupancy, l_fold_tables, l_final_bind, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_occupancy, l_fold_tables, l_final_bind, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

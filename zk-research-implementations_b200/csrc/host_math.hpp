@@ -102,34 +102,143 @@ class Keccak256 {
 };
 
 // ------------------------------------------------------- host field helper
-// Montgomery-residue arithmetic on the host through the per-field table
-// (fr.cuh compiled for the host; the very same limb code the kernels run).
+// Montgomery-residue arithmetic on the host, 4 x 64-bit limbs with unsigned
+// __int128 (the same residues the kernels produce: R = 2^256).  Used for the
+// few field operations per round that stay on the host: interpolation of the
+// round message, the claim chain, challenge tables, serialisation.
 struct HostField {
-    const FieldKernels* K;
+    const FieldKernels* K = nullptr;
+    uint64_t p[4] = {0, 0, 0, 0};
+    uint64_t ninv = 0;  // -p^-1 mod 2^64
+    Fe one_, r2_;
+
+    static HostField make(const FieldKernels* k) {
+        HostField H;
+        H.K = k;
+        Fe m;
+        k->h_modulus(m);
+        std::memcpy(H.p, m.l, 32);
+        uint64_t x = 1;  // Newton: x = p^-1 mod 2^64
+        for (int i = 0; i < 6; ++i) x *= 2 - H.p[0] * x;
+        H.ninv = ~x + 1;
+        Fe v = H.zero();
+        v.l[0] = 1;
+        for (int i = 0; i < 256; ++i) v = H.add(v, v);
+        H.one_ = v;
+        for (int i = 0; i < 256; ++i) v = H.add(v, v);
+        H.r2_ = v;
+        return H;
+    }
     Fe zero() const {
         Fe z;
         for (int i = 0; i < 8; ++i) z.l[i] = 0;
         return z;
     }
-    Fe add(const Fe& a, const Fe& b) const { Fe r; K->h_add(a, b, r); return r; }
-    Fe sub(const Fe& a, const Fe& b) const { Fe r; K->h_sub(a, b, r); return r; }
-    Fe mul(const Fe& a, const Fe& b) const { Fe r; K->h_mul(a, b, r); return r; }
-    Fe to_mont(const Fe& a) const { Fe r; K->h_to_mont(a, r); return r; }
-    Fe from_mont(const Fe& a) const { Fe r; K->h_from_mont(a, r); return r; }
+    static void ld(const Fe& a, uint64_t v[4]) { std::memcpy(v, a.l, 32); }
+    static Fe st(const uint64_t v[4]) {
+        Fe r;
+        std::memcpy(r.l, v, 32);
+        return r;
+    }
+    bool ge_p(const uint64_t a[4]) const {
+        for (int i = 3; i >= 0; --i) {
+            if (a[i] > p[i]) return true;
+            if (a[i] < p[i]) return false;
+        }
+        return true;
+    }
+    void sub_p(uint64_t a[4]) const {
+        unsigned __int128 bw = 0;
+        for (int i = 0; i < 4; ++i) {
+            unsigned __int128 d = (unsigned __int128)a[i] - p[i] - (uint64_t)bw;
+            a[i] = (uint64_t)d;
+            bw = (d >> 64) & 1;
+        }
+    }
+    Fe add(const Fe& x, const Fe& y) const {
+        uint64_t a[4], b[4], r[4];
+        ld(x, a);
+        ld(y, b);
+        unsigned __int128 c = 0;
+        for (int i = 0; i < 4; ++i) {
+            c += (unsigned __int128)a[i] + b[i];
+            r[i] = (uint64_t)c;
+            c >>= 64;
+        }
+        if (c || ge_p(r)) sub_p(r);
+        return st(r);
+    }
+    Fe sub(const Fe& x, const Fe& y) const {
+        uint64_t a[4], b[4], r[4];
+        ld(x, a);
+        ld(y, b);
+        unsigned __int128 bw = 0;
+        for (int i = 0; i < 4; ++i) {
+            unsigned __int128 d = (unsigned __int128)a[i] - b[i] - (uint64_t)bw;
+            r[i] = (uint64_t)d;
+            bw = (d >> 64) & 1;
+        }
+        if (bw) {
+            unsigned __int128 c = 0;
+            for (int i = 0; i < 4; ++i) {
+                c += (unsigned __int128)r[i] + p[i];
+                r[i] = (uint64_t)c;
+                c >>= 64;
+            }
+        }
+        return st(r);
+    }
+    // Montgomery product (CIOS); x < 2^256 arbitrary, y < p
+    Fe mul(const Fe& x, const Fe& y) const {
+        uint64_t a[4], b[4];
+        ld(x, a);
+        ld(y, b);
+        uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i) {
+            unsigned __int128 c = 0;
+            for (int j = 0; j < 4; ++j) {
+                c += (unsigned __int128)b[j] * a[i] + t[j];
+                t[j] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[4];
+            t[4] = (uint64_t)c;
+            t[5] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * ninv;
+            c = (unsigned __int128)m * p[0] + t[0];
+            c >>= 64;
+            for (int j = 1; j < 4; ++j) {
+                c += (unsigned __int128)m * p[j] + t[j];
+                t[j - 1] = (uint64_t)c;
+                c >>= 64;
+            }
+            c += t[4];
+            t[3] = (uint64_t)c;
+            t[4] = t[5] + (uint64_t)(c >> 64);
+        }
+        if (t[4] || ge_p(t)) sub_p(t);
+        return st(t);
+    }
+    Fe to_mont(const Fe& a) const { return mul(a, r2_); }
+    Fe from_mont(const Fe& a) const {
+        Fe o = zero();
+        o.l[0] = 1;
+        return mul(a, o);
+    }
     Fe from_u64(uint64_t x) const {
         Fe c = zero();
         c.l[0] = (uint32_t)x;
         c.l[1] = (uint32_t)(x >> 32);
         return to_mont(c);
     }
-    Fe one() const { return from_u64(1); }
+    Fe one() const { return one_; }
     bool is_zero(const Fe& a) const {
         uint32_t o = 0;
         for (int i = 0; i < 8; ++i) o |= a.l[i];
         return o == 0;
     }
     bool eq(const Fe& a, const Fe& b) const { return std::memcmp(a.l, b.l, 32) == 0; }
-    Fe modulus() const { Fe p; K->h_modulus(p); return p; }
+    Fe modulus() const { return st(p); }
     // a^(p-2)
     Fe inv(const Fe& a) const {
         Fe e = modulus();

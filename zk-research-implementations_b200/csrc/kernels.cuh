@@ -389,6 +389,181 @@ __global__ void __launch_bounds__(BLOCK) k_sc_fold_eval(const ScArgs a) {
     finish_round<F, NPTS - 1>(out, a.fin);
 }
 
+// ------------------------------------------------- persistent round kernel
+// All remaining rounds of a sumcheck in ONE cooperative launch.  The transcript
+// stays on the host: per round the kernel publishes its NPTS-1 sums to a mailbox
+// in mapped host memory, the host answers with the next challenge in the same
+// mailbox, and the exchange doubles as the grid-wide barrier between rounds
+// (a round's sums are complete only when every CTA has stored its folded
+// entries).  Per round this costs two PCIe one-way trips instead of a kernel
+// launch, a stream wait and a second-stage reduction launch gap.
+struct alignas(64) TailMailbox {
+    // host -> device: ONE 64-byte line, polled with one coalesced read.  The line may arrive as two 32-byte
+    // sectors read at different instants, so the second sector carries a checksum of the first
+    // (xor of the 8 words of r, mixed with seq): a torn read (new seq, stale r) fails it and is retried.
+    uint32_t r[8];
+    volatile unsigned int host_seq;
+    volatile unsigned int abort;
+    volatile unsigned int chk;
+    unsigned int pad0[5];
+    // device -> host
+    Fe evals[MAXPTS];
+    Fe finals[MAXT];
+    volatile unsigned int dev_seq;
+    volatile unsigned int dev_error;  // 1 = timed out waiting for the host
+    unsigned int pad1[14];
+};
+struct TailRelay {  // device memory: CTA 0 re-publishes the host's message for the other CTAs
+    FixedMul rt;
+    unsigned int seq;
+    unsigned int abort;
+};
+struct TailArgs {
+    TabRef in[MAXT];
+    TabRef out[MAXT];
+    int n_tables;
+    int n_products;
+    uint64_t n_in;             // entries per table at entry
+    FixedMul rt0;              // table of the first challenge to bind
+    Fe cpow[8];                // 2^(32 i + 64) mod p: FixedMul rows are mul(r, cpow[i])
+    TailMailbox* mb;
+    TailRelay* relay;
+    Fe* partials;
+    unsigned int* ticket;
+    unsigned int base_seq;
+    long long timeout_clocks;
+};
+
+template <class F, int KIND, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK) k_sc_tail(const TailArgs a) {
+    typedef Field<F> Fd;
+    __shared__ FixedMul s_rt;
+    __shared__ unsigned int s_abort;
+    uint64_t n_in = a.n_in;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (unsigned int it = 0;; ++it) {
+        // ---- the challenge table of this round -> shared memory
+        if (it == 0) {
+            for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = (&a.rt0.t[0][0])[w];
+            if (threadIdx.x == 0) s_abort = 0;
+        } else {
+            const unsigned int want = a.base_seq + it;
+            if (blockIdx.x == 0 && threadIdx.x < 32) {  // relay warp: host mailbox -> device memory
+                const int lane = threadIdx.x;
+                const volatile uint32_t* line = reinterpret_cast<const volatile uint32_t*>(a.mb);
+                const long long t0 = clock64();
+                uint32_t word = 0;
+                unsigned int status = 0;  // 1 = got it, 2 = abort, 3 = timeout
+                while (status == 0) {
+                    word = lane < 16 ? line[lane] : 0u;  // one coalesced 64-byte read over PCIe
+                    const uint32_t seq = __shfl_sync(0xffffffffu, word, 8);
+                    const uint32_t ab = __shfl_sync(0xffffffffu, word, 9);
+                    const uint32_t chk = __shfl_sync(0xffffffffu, word, 10);
+                    const uint32_t x = __reduce_xor_sync(0xffffffffu, lane < 8 ? word : 0u);
+                    if (ab) status = 2;
+                    else if (seq == want && (x ^ (want * 0x9E3779B9u)) == chk) status = 1;
+                    else if (clock64() - t0 > a.timeout_clocks) status = 3;
+                }
+                if (status == 1) {
+                    Fe r;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r.l[k] = __shfl_sync(0xffffffffu, word, k);
+                    if (lane < 8) {
+                        Fe t = Fd::mul(r, a.cpow[lane]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a.relay->rt.t[lane][k] = t.l[k];
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) *reinterpret_cast<volatile unsigned int*>(&a.relay->seq) = want;
+                } else if (lane == 0) {
+                    if (status == 3) {
+                        a.mb->dev_error = 1;
+                        __threadfence_system();
+                    }
+                    *reinterpret_cast<volatile unsigned int*>(&a.relay->abort) = status;
+                }
+            }
+            if (threadIdx.x == 0) {
+                const volatile unsigned int* seq = reinterpret_cast<const volatile unsigned int*>(&a.relay->seq);
+                const volatile unsigned int* ab = reinterpret_cast<const volatile unsigned int*>(&a.relay->abort);
+                unsigned int aborted = 0;
+                while (*seq != want && !(aborted = *ab)) __nanosleep(32);
+                s_abort = aborted;
+                __threadfence();
+            }
+            __syncthreads();
+            if (s_abort) return;
+            for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = __ldcg(&a.relay->rt.t[0][0] + w);
+        }
+        __syncthreads();
+        const uint64_t n_out = n_in >> 1, half = n_out >> 1;
+        const TabRef* src = it == 0 ? a.in : a.out;
+        if (n_out == 1) {  // last bind: publish the bound values and leave
+            if (blockIdx.x == 0) {
+                const int t = threadIdx.x;
+                if (t < a.n_tables) {
+                    Fe v = Fd::fold_fixed(ld_fe(src[t], 0), ld_fe(src[t], 1), s_rt);
+                    st_fe(a.out[t], 0, v);
+                    a.mb->finals[t] = v;
+                    __threadfence_system();
+                }
+                __syncthreads();
+                if (t == 0) a.mb->dev_seq = a.base_seq + it + 1;
+            }
+            return;
+        }
+        Fe out[NPTS - 1];
+        if (KIND == KIND_XYZ) {
+            XyzAcc<F, true> acc;
+            acc.init();
+            for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+                Fe lo[3], hi[3];
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    Fe x0 = ld_fe(src[f], j), x1 = ld_fe(src[f], j + n_out);
+                    Fe y0 = ld_fe(src[f], j + half), y1 = ld_fe(src[f], j + half + n_out);
+                    lo[f] = Fd::fold_fixed(x0, x1, s_rt);
+                    hi[f] = Fd::fold_fixed(y0, y1, s_rt);
+                    st_fe(a.out[f], j, lo[f]);
+                    st_fe(a.out[f], j + half, hi[f]);
+                }
+                acc.add(lo, hi);
+            }
+            acc.finish(out);
+        } else {
+            RoundAcc<F, D, NPTS, true> acc;
+            acc.init();
+            for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+                for (int p = 0; p < a.n_products; ++p) {
+                    Fe lo[D], hi[D];
+#pragma unroll
+                    for (int f = 0; f < D; ++f) {
+                        const TabRef& ti = src[p * D + f];
+                        Fe x0 = ld_fe(ti, j), x1 = ld_fe(ti, j + n_out);
+                        Fe y0 = ld_fe(ti, j + half), y1 = ld_fe(ti, j + half + n_out);
+                        lo[f] = Fd::fold_fixed(x0, x1, s_rt);
+                        hi[f] = Fd::fold_fixed(y0, y1, s_rt);
+                        st_fe(a.out[p * D + f], j, lo[f]);
+                        st_fe(a.out[p * D + f], j + half, hi[f]);
+                    }
+                    acc.add_product(lo, hi);
+                }
+            }
+            acc.finish(out);
+        }
+        FinishArgs fin;
+        fin.partials = a.partials;
+        fin.ticket = a.ticket;
+        fin.result = a.mb->evals;
+        fin.result_wide = nullptr;
+        fin.flag = &a.mb->dev_seq;
+        fin.seq = a.base_seq + it + 1;
+        finish_round<F, NPTS - 1>(out, fin);
+        n_in = n_out;
+    }
+}
+
 // K3/K1 for lists: fold variable 0 of n_tables tables of 2*n_out entries.
 struct FoldTablesArgs {
     TabRef in[MAXT];

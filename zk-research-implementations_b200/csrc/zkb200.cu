@@ -155,6 +155,11 @@ struct zkb_ctx {
     uint32_t gather_log2 = 12;
     RoundInterpolator interp[MAXPTS + 1];
     FixedMulBuilder fmb;
+    // persistent round kernel
+    TailMailbox* mb = nullptr;   // mapped pinned host memory
+    TailRelay* d_relay = nullptr;
+    unsigned int tail_seq = 0;
+    uint32_t tail_log2 = 18;
     std::unordered_map<std::string, int> occ_cache;
     // per-launch event timing (zkb_ctx_profile)
     bool prof = false;
@@ -577,6 +582,141 @@ int32_t sp_final_values(zkb_ctx* c, SumPolyState* sp, Fe* vals) {
     return ZKB_OK;
 }
 
+
+// ------------------------------------------------------------- round driver
+// One sumcheck from the first round to the last bind.  Large rounds are one launch each
+// (k_sc_fold_eval); once the tables have at most 2^tail_log2 entries the remaining rounds run inside
+// the persistent kernel k_sc_tail and only mailbox messages cross PCIe.
+struct RoundDriver {
+    zkb_ctx* c;
+    SumPolyState* sp;
+    bool live = false;       // the persistent kernel is running
+    unsigned int base = 0;   // its mailbox sequence base
+    unsigned int it = 0;     // challenges delivered to it so far
+
+    RoundDriver(zkb_ctx* ctx, SumPolyState* s) : c(ctx), sp(s) {}
+    ~RoundDriver() { abort(); }
+
+    void abort() {
+        if (!live) return;
+        c->mb->abort = 1;
+        cudaStreamSynchronize(c->stream);
+        c->mb->abort = 0;
+        live = false;
+    }
+    int32_t first(Fe* evals) { return sp_round_evals(c, sp, evals); }
+
+    bool tail_ok() const {
+        return c->tail_log2 > 0 && !sp->sharded && sp->rest.empty() && sp->have_evals && sp->cur_n >= 2 &&
+               sp->cur_n <= (1ull << c->tail_log2) && sc_occ(c, 2, sp->kind, sp->kD, sp->npts) > 0;
+    }
+    int32_t wait_dev(unsigned int want) {
+        uint32_t spins = 0;
+        while (c->mb->dev_seq != want) {
+            if ((++spins & 0x3fff) == 0) {
+                cudaError_t e = cudaStreamQuery(c->stream);
+                if (e == cudaSuccess && c->mb->dev_seq != want) {
+                    live = false;
+                    ZK_FAIL(c, ZKB_ERR_CUDA, c->mb->dev_error ? "persistent round kernel timed out waiting for the host" : "persistent round kernel exited early");
+                }
+                if (e != cudaSuccess && e != cudaErrorNotReady) {
+                    live = false;
+                    c->last_error = std::string("persistent round kernel: ") + cudaGetErrorString(e);
+                    return ZKB_ERR_CUDA;
+                }
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        asm volatile("" ::: "memory");
+        return ZKB_OK;
+    }
+    int32_t launch_tail(const Fe& r) {
+        const int T = (int)sp->src.size();
+        if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
+        TailArgs a;
+        std::memset(&a, 0, sizeof a);
+        for (size_t i = 0; i < sp->sel.size(); ++i) {
+            a.in[i] = sp->cur(sp->sel[i]).ref();
+            a.out[i] = (sp->state == 2 ? sp->gath[sp->sel[i]] : sp->work[sp->sel[i]]).ref();
+        }
+        (void)T;
+        a.n_tables = (int)sp->sel.size();
+        a.n_products = sp->kP;
+        a.n_in = sp->cur_n;
+        c->fmb.make(c->H, r, &a.rt0);
+        for (int i = 0; i < 8; ++i) a.cpow[i] = c->fmb.c[i];
+        a.mb = c->mb;
+        a.relay = c->d_relay;
+        a.ticket = c->d_ticket;
+        c->tail_seq += 64;
+        base = a.base_seq = c->tail_seq;
+        a.timeout_clocks = 6000000000ll;  // ~3 s
+        const uint64_t quads = sp->cur_n / 4 ? sp->cur_n / 4 : 1;
+        const int grid = grid_for(c, quads, sc_occ(c, 2, sp->kind, sp->kD, sp->npts));
+        ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
+        a.partials = c->d_partials;
+        c->mb->abort = 0;
+        c->mb->dev_error = 0;
+        ZK_CUDA(c, cudaMemsetAsync(&c->d_relay->seq, 0, 2 * sizeof(unsigned int), c->stream));
+        prof_begin(c, ZKB_K_SC_TAIL, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - 1));
+        int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, a, grid, c->stream);
+        if (e < 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_tail: shape not instantiated");
+        if (e != 0) {
+            c->last_error = std::string("k_sc_tail launch: ") + cudaGetErrorString((cudaError_t)e);
+            return ZKB_ERR_CUDA;
+        }
+        ZK_TRY(check_launch(c, "k_sc_tail"));
+        live = true;
+        it = 0;
+        if (sp->state == 0) sp->state = 1;
+        return ZKB_OK;
+    }
+    // Bind r; evals != NULL: the next round's s(0..d); NULL: this was the last variable, finals get the bound values.
+    int32_t next(const Fe& r, Fe* evals, Fe* finals) {
+        if (!live && !tail_ok()) return sp_bind_and_next(c, sp, r, evals, finals);
+        const RoundInterpolator& ip = c->interp[sp->npts];
+        Fe co[MAXPTS];
+        const int colen = ip.interpolate(sp->last_evals, co);
+        const Fe claim = uni_evaluate(c->H, co, colen, r);
+        if (!live) {
+            ZK_TRY(launch_tail(r));
+        } else {
+            ++it;
+            const unsigned int want = base + it;
+            uint32_t x = 0;
+            for (int k = 0; k < 8; ++k) {
+                c->mb->r[k] = r.l[k];
+                x ^= r.l[k];
+            }
+            c->mb->chk = x ^ (want * 0x9E3779B9u);
+            asm volatile("" ::: "memory");
+            c->mb->host_seq = want;  // x86 keeps store order: the payload is visible before the sequence number
+        }
+        ZK_TRY(wait_dev(base + it + 1));
+        sp->cur_n /= 2;
+        if (sp->cur_n == 1) {
+            live = false;  // the kernel leaves after publishing the bound values
+            const int T = (int)sp->sel.size();
+            if (finals)
+                for (int t = 0; t < T; ++t) finals[sp->sel[t]] = c->mb->finals[t];
+            sp->have_evals = false;
+            if (evals) ZK_FAIL(c, ZKB_ERR_ARITY, "bind_and_next: no next round after the last variable");
+            return ZKB_OK;
+        }
+        if (!evals) {  // caller stops early: not supported inside the persistent kernel
+            abort();
+            ZK_FAIL(c, ZKB_ERR_BAD_ARG, "round driver: early stop inside the persistent kernel");
+        }
+        evals[0] = c->mb->evals[0];
+        evals[1] = c->H.sub(claim, evals[0]);
+        for (int t = 2; t < sp->npts; ++t) evals[t] = c->mb->evals[t - 1];
+        for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
+        return ZKB_OK;
+    }
+};
+
 // The composed sumcheck loop (sum_check_protocol.rs:86-115) over a configured state.
 // coeffs: rounds x slots elements; returns challenges and the T bound values.
 int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, uint64_t* coeffs, int32_t* lens,
@@ -586,7 +726,8 @@ int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, ui
     const RoundInterpolator& ip = c->interp[sp->npts];
     Fe evals[MAXPTS], co[MAXPTS];
     if (n_rounds == 0) return sp_final_values(c, sp, final_vals);
-    ZK_TRY(sp_round_evals(c, sp, evals));
+    RoundDriver drv(c, sp);
+    ZK_TRY(drv.first(evals));
     for (int k = 0; k < n_rounds; ++k) {
         int len;
         if (as_evals) {  // plain sumcheck: the message is the evaluations themselves (:168-175)
@@ -600,7 +741,7 @@ int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, ui
         for (int i = 0; i < slots; ++i) fe_to_u64x4(i < len ? co[i] : c->H.zero(), coeffs + ((size_t)k * slots + i) * 4);
         Fe r = tr->challenge();
         if (challenges) fe_to_u64x4(r, challenges + (size_t)k * 4);
-        ZK_TRY(sp_bind_and_next(c, sp, r, k + 1 < n_rounds ? evals : nullptr, final_vals));
+        ZK_TRY(drv.next(r, k + 1 < n_rounds ? evals : nullptr, final_vals));
     }
     return ZKB_OK;
 }
@@ -794,7 +935,8 @@ int32_t xyz_phase(zkb_ctx* c, CircuitState* cs, const Table& X, const Table& Y, 
     const int nb = ilog2_u64(nw);
     const RoundInterpolator& ip = c->interp[3];
     Fe evals[3], co[3], fin[3];
-    ZK_TRY(sp_round_evals(c, sp, evals));
+    RoundDriver drv(c, sp);
+    ZK_TRY(drv.first(evals));
     for (int k = 0; k < nb; ++k) {
         int len = ip.interpolate(evals, co);
         tr->append_elements(co, (size_t)len);
@@ -803,7 +945,7 @@ int32_t xyz_phase(zkb_ctx* c, CircuitState* cs, const Table& X, const Table& Y, 
         Fe r = tr->challenge();
         point[k] = r;
         if (chals) fe_to_u64x4(r, chals + (size_t)k * 4);
-        ZK_TRY(sp_bind_and_next(c, sp, r, k + 1 < nb ? evals : nullptr, fin));
+        ZK_TRY(drv.next(r, k + 1 < nb ? evals : nullptr, fin));
     }
     *x_final = fin[0];
     return ZKB_OK;
@@ -966,7 +1108,7 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
     c->device = device;
     c->mode = mode;
     c->K = K;
-    c->H.K = K;
+    c->H = HostField::make(K);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ZKB_ERR_CUDA;
     c->sm_count = prop.multiProcessorCount;
@@ -986,6 +1128,10 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
     cudaMemset(c->d_ticket, 0, sizeof(unsigned int));
     if (cudaMalloc((void**)&c->d_res, sizeof(Fe) * 64) != cudaSuccess) return ZKB_ERR_CUDA;
     if (cudaMalloc((void**)&c->d_wide, sizeof(unsigned long long) * 8 * MAXPTS) != cudaSuccess) return ZKB_ERR_CUDA;
+    if (cudaHostAlloc((void**)&c->mb, sizeof(TailMailbox), cudaHostAllocMapped) != cudaSuccess) return ZKB_ERR_CUDA;
+    std::memset((void*)c->mb, 0, sizeof(TailMailbox));
+    if (cudaMalloc((void**)&c->d_relay, sizeof(TailRelay)) != cudaSuccess) return ZKB_ERR_CUDA;
+    cudaMemset(c->d_relay, 0, sizeof(TailRelay));
     for (int n = 2; n <= MAXPTS; ++n) c->interp[n].init(c->H, n);
     c->fmb.init(c->H);
     *out = c.release();
@@ -1021,6 +1167,8 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     cudaFree(c->d_wide);
     cudaFreeHost(c->h_res);
     cudaFreeHost(c->h_wide);
+    cudaFreeHost((void*)c->mb);
+    cudaFree(c->d_relay);
     cudaStreamDestroy(c->stream);
     delete c;
     return ZKB_OK;
@@ -1058,7 +1206,7 @@ int32_t zkb_ctx_profile_read(zkb_ctx* c, int32_t k, uint64_t* launches, double* 
 }
 const char* zkb_kernel_name(int32_t k) {
     static const char* names[ZKB_K_COUNT] = {"k_sc_eval", "k_sc_fold_eval", "k_fold_tables", "k_final_bind", "k_fold",
-                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other"};
+                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other", "k_sc_tail"};
     return (k >= 0 && k < ZKB_K_COUNT) ? names[k] : "?";
 }
 
@@ -1081,6 +1229,11 @@ int32_t zkb_ctx_comm_init(zkb_ctx* c, int32_t rank, int32_t world, const uint8_t
     c->rank = rank;
     c->world = world;
     c->log2world = ilog2_u64((uint64_t)world);
+    return ZKB_OK;
+}
+int32_t zkb_ctx_set_tail_threshold(zkb_ctx* c, uint32_t log2_entries) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    c->tail_log2 = log2_entries;
     return ZKB_OK;
 }
 int32_t zkb_ctx_set_gather_threshold(zkb_ctx* c, uint32_t log2_local_entries) {
@@ -1327,7 +1480,7 @@ int32_t zkb_transcript_new(int32_t field_id, zkb_transcript** out) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || !out) return ZKB_ERR_BAD_ARG;
     zkb_transcript* t = new zkb_transcript;
-    t->impl.H.K = K;
+    t->impl.H = HostField::make(K);
     *out = t;
     return ZKB_OK;
 }
@@ -1364,14 +1517,14 @@ int32_t zkb_keccak256(const uint8_t* bytes, size_t len, uint8_t out[32]) {
 int32_t zkb_fe_to_mont(int32_t field_id, const uint64_t* canonical, uint64_t* mont, size_t n) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || (!canonical && n) || (!mont && n)) return ZKB_ERR_BAD_ARG;
-    HostField H{K};
+    HostField H = HostField::make(K);
     for (size_t i = 0; i < n; ++i) fe_to_u64x4(H.to_mont(fe_from_u64x4(canonical + 4 * i)), mont + 4 * i);
     return ZKB_OK;
 }
 int32_t zkb_fe_from_mont(int32_t field_id, const uint64_t* mont, uint64_t* canonical, size_t n) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || (!canonical && n) || (!mont && n)) return ZKB_ERR_BAD_ARG;
-    HostField H{K};
+    HostField H = HostField::make(K);
     for (size_t i = 0; i < n; ++i) fe_to_u64x4(H.from_mont(fe_from_u64x4(mont + 4 * i)), canonical + 4 * i);
     return ZKB_OK;
 }
@@ -1379,7 +1532,7 @@ int32_t zkb_fe_from_mont(int32_t field_id, const uint64_t* mont, uint64_t* canon
 int32_t zkb_fe_reduce_wide(int32_t field_id, const uint64_t* wide, uint64_t* out, size_t n) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || (!wide && n) || (!out && n)) return ZKB_ERR_BAD_ARG;
-    HostField H{K};
+    HostField H = HostField::make(K);
     for (size_t i = 0; i < n; ++i) fe_to_u64x4(H.from_wide_limbs((const unsigned long long*)wide + 8 * i), out + 4 * i);
     return ZKB_OK;
 }
@@ -1388,7 +1541,7 @@ int32_t zkb_fe_reduce_wide(int32_t field_id, const uint64_t* wide, uint64_t* out
 int32_t zkb_uni_interpolate(int32_t field_id, const uint64_t* xs, const uint64_t* ys, uint32_t n, uint64_t* coeffs, uint32_t* len) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || !xs || !ys || !coeffs || !len || n > 64) return ZKB_ERR_BAD_ARG;
-    HostField H{K};
+    HostField H = HostField::make(K);
     std::vector<Fe> x(n), y(n), co(n);
     for (uint32_t i = 0; i < n; ++i) {
         x[i] = fe_from_u64x4(xs + 4 * i);
@@ -1402,7 +1555,7 @@ int32_t zkb_uni_interpolate(int32_t field_id, const uint64_t* xs, const uint64_t
 int32_t zkb_uni_evaluate(int32_t field_id, const uint64_t* coeffs, uint32_t len, const uint64_t x[4], uint64_t out[4]) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || (!coeffs && len) || !x || !out) return ZKB_ERR_BAD_ARG;
-    HostField H{K};
+    HostField H = HostField::make(K);
     std::vector<Fe> co(len);
     for (uint32_t i = 0; i < len; ++i) co[i] = fe_from_u64x4(coeffs + 4 * i);
     fe_to_u64x4(uni_evaluate(H, co.data(), (int)len, fe_from_u64x4(x)), out);
@@ -1441,7 +1594,8 @@ int32_t zkb_sumcheck_prove(zkb_ctx* c, zkb_mle poly, uint32_t flags, uint64_t cl
         return ZKB_OK;
     }
     if (!msgs) return ZKB_ERR_BAD_ARG;
-    st = sp_round_evals(c, &sp, ev);
+    RoundDriver drv(c, &sp);
+    st = drv.first(ev);
     if (st == ZKB_OK) {
         Fe claimed = c->H.add(ev[0], ev[1]);  // :29 the claimed sum is the sum of the two halves
         fe_to_u64x4(claimed, claimed_sum);
@@ -1452,9 +1606,10 @@ int32_t zkb_sumcheck_prove(zkb_ctx* c, zkb_mle poly, uint32_t flags, uint64_t cl
             fe_to_u64x4(ev[1], msgs + (size_t)k * 8 + 4);
             Fe r = tr.challenge();
             if (challenges) fe_to_u64x4(r, challenges + (size_t)k * 4);
-            st = sp_bind_and_next(c, &sp, r, k + 1 < n_rounds ? ev : nullptr, fin);
+            st = drv.next(r, k + 1 < n_rounds ? ev : nullptr, fin);
         }
     }
+    drv.abort();
     sp_release(c, &sp);
     return st;
 }
