@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-vars", type=int, default=N_VARS_PER_GPU, help="variables per GPU shard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tail-log2", type=int, default=None, help="persistent-kernel threshold (0 = one launch per round)")
     ap.add_argument("--quick", action="store_true", help="profiling run: resident leg only, warm-up as given (numbers are not bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -192,6 +193,8 @@ def main():
         box = [z.engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         ctx.comm_init(rank, world, box[0])
+    if args.tail_log2 is not None:
+        ctx.set_tail_threshold(args.tail_log2)
     S = z.sum_check_protocol
     T = z.fiat_shamir.Transcript
     a = z.MultilinearPoly.generate(ctx, SEED, 0, n)

@@ -15,14 +15,25 @@ typedef ZKB_FIELD FT;
 
 bool l_sc_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
 #define X(K, DD, NP) \
-    if (kind == K && D == DD && npts == NP) { k_sc_eval<FT, K, DD, NP><<<grid, BLOCK, 0, s>>>(a); return true; }
+    if (kind == K && D == DD && npts == NP) { \
+        static bool once = (cudaFuncSetAttribute(k_sc_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES), true); \
+        (void)once; \
+        k_sc_eval<FT, K, DD, NP><<<grid, BLOCK, STAGE_BYTES, s>>>(a); \
+        return true; \
+    }
     ZKB_SC_CASES(X)
 #undef X
     return false;
 }
 bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
 #define X(K, DD, NP) \
-    if (kind == K && D == DD && npts == NP) { k_sc_fold_eval<FT, K, DD, NP><<<grid, BLOCK, 0, s>>>(a); return true; }
+    if (kind == K && D == DD && npts == NP) { \
+        constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+        static bool once = (cudaFuncSetAttribute(k_sc_fold_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
+        (void)once; \
+        k_sc_fold_eval<FT, K, DD, NP><<<grid, BLOCK, SM, s>>>(a); \
+        return true; \
+    }
     ZKB_SC_CASES(X)
 #undef X
     return false;
@@ -41,8 +52,14 @@ int l_sc_occupancy(int fused, int kind, int D, int npts) {
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         if (fused == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_tail<FT, K, DD, NP>, BLOCK, 0); \
-        else if (fused) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_fold_eval<FT, K, DD, NP>, BLOCK, 0); \
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_eval<FT, K, DD, NP>, BLOCK, 0); \
+        else if (fused) { \
+            constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+            cudaFuncSetAttribute(k_sc_fold_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_fold_eval<FT, K, DD, NP>, BLOCK, SM); \
+        } else { \
+            cudaFuncSetAttribute(k_sc_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_eval<FT, K, DD, NP>, BLOCK, STAGE_BYTES); \
+        } \
         return nb; \
     }
     ZKB_SC_CASES(X)

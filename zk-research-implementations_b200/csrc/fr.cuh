@@ -422,10 +422,10 @@ struct Field {
         for (int i = 0; i < 17; ++i) w.l[i] = 0;
         return w;
     }
-    // acc += a * b (plain 512-bit integer product; up to 2^36 products fit)
-    ZK_HD static void mac_wide(Wide& acc, const Fe& a, const Fe& b) {
-        // schoolbook rows in order; ev[k] = limbs (2k, 2k+1), od[k] = limbs (2k+1, 2k+2)
-        uint64_t ev[8], od[8];
+    // The raw 512-bit product a * b as two interleaved column sums:
+    // ev[k] = limbs (2k, 2k+1), od[k] = limbs (2k+1, 2k+2); a*b = ev + (od << 32).
+    ZK_HD static void mul_wide16(const Fe& a, const Fe& b, uint64_t* ev, uint64_t* od) {
+        // schoolbook rows in order
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             ev[k] = mul_wide(a.l[2 * k], b.l[0]);
@@ -461,7 +461,9 @@ struct Field {
                 if (e + 4 < 8) od[e + 4] = addc64(od[e + 4], 0ull);
             }
         }
-        // acc += ev ; acc += od << 32
+    }
+    // acc += ev + (od << 32)
+    ZK_HD static void wide_add(Wide& acc, const uint64_t* ev, const uint64_t* od) {
         acc.l[0] = add_cc(acc.l[0], lo32(ev[0]));
         acc.l[1] = addc_cc(acc.l[1], hi32(ev[0]));
 #pragma unroll
@@ -478,6 +480,12 @@ struct Field {
             if (k < 7) acc.l[2 * k + 2] = addc_cc(acc.l[2 * k + 2], hi32(od[k]));
         }
         acc.l[16] = addc(acc.l[16], hi32(od[7]));
+    }
+    // acc += a * b (plain 512-bit integer product; up to 2^36 products fit)
+    ZK_HD static void mac_wide(Wide& acc, const Fe& a, const Fe& b) {
+        uint64_t ev[8], od[8];
+        mul_wide16(a, b, ev, od);
+        wide_add(acc, ev, od);
     }
     // acc * R^-1 mod p, fully reduced: acc = A0 + A1*2^256 + A2*2^512 ->
     // A0*R^-1 + A1 + A2*R  =  mul(1, A0) + mul(R, A1) + mul(R^2, A2)   (mul = Montgomery product).

@@ -188,20 +188,68 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a) {
 // reduce_wide), which halves the multiplier work of every product.
 // SKIP1: s(1) is not computed -- the host derives it from the running claim,
 // s(1) = claim - s(0); slot layout is then {s(0), s(2), s(3), ...}.
+// Accumulators parked in shared memory (one private slot per thread): the 17-word sums are
+// only needed for the 33 additions that end each product, so they need not occupy registers
+// during the folds.  Volatile asm keeps the load AFTER the product in program order.
+// Slot layout: [acc][5][BLOCK] uint4 (words 17..19 unused).
+__device__ __forceinline__ uint4 lds128(const uint4* p) {
+    uint4 v;
+    const unsigned int sa = static_cast<unsigned int>(__cvta_generic_to_shared(p));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint4* p, const uint4& v) {
+    const unsigned int sa = static_cast<unsigned int>(__cvta_generic_to_shared(p));
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+constexpr int ACC_VECS = 5;
+__device__ __forceinline__ Wide wide_load(const uint4* slot) {
+    Wide w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint4 v = lds128(slot + k * BLOCK);
+        w.l[4 * k] = v.x; w.l[4 * k + 1] = v.y; w.l[4 * k + 2] = v.z; w.l[4 * k + 3] = v.w;
+    }
+    w.l[16] = lds128(slot + 4 * BLOCK).x;
+    return w;
+}
+__device__ __forceinline__ void wide_store(uint4* slot, const Wide& w) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sts128(slot + k * BLOCK, make_uint4(w.l[4 * k], w.l[4 * k + 1], w.l[4 * k + 2], w.l[4 * k + 3]));
+    sts128(slot + 4 * BLOCK, make_uint4(w.l[16], 0u, 0u, 0u));
+}
+template <class F>
+__device__ __forceinline__ void mac_wide_sm(uint4* slot, const Fe& a, const Fe& b) {
+    uint64_t ev[8], od[8];
+    Field<F>::mul_wide16(a, b, ev, od);
+    Wide w = wide_load(slot);
+    Field<F>::wide_add(w, ev, od);
+    wide_store(slot, w);
+}
+
 template <int NPTS, bool SKIP1>
 struct Slots {
     static constexpr int N = SKIP1 ? NPTS - 1 : NPTS;
     __device__ __forceinline__ static constexpr int of(int t) { return SKIP1 ? (t == 0 ? 0 : t - 1) : t; }
 };
 
-template <class F, int D, int NPTS, bool SKIP1>
+template <class F, int D, int NPTS, bool SKIP1, bool SM = false>
 struct RoundAcc {
     typedef Field<F> Fd;
     typedef Slots<NPTS, SKIP1> S;
-    Wide w[S::N];
-    __device__ __forceinline__ void init() {
+    Wide w[SM ? 1 : S::N];
+    uint4* sm;  // SM: this thread's slot 0 (accumulator p at sm + p * ACC_VECS * BLOCK)
+    __device__ __forceinline__ void init(uint4* slots = nullptr) {
+        sm = slots;
 #pragma unroll
-        for (int p = 0; p < S::N; ++p) w[p] = Fd::wide_zero();
+        for (int p = 0; p < S::N; ++p) {
+            if (SM) wide_store(sm + p * ACC_VECS * BLOCK, Fd::wide_zero());
+            else w[p] = Fd::wide_zero();
+        }
+    }
+    __device__ __forceinline__ void mac(int p, const Fe& x, const Fe& y) {
+        if (SM) mac_wide_sm<F>(sm + p * ACC_VECS * BLOCK, x, y);
+        else Fd::mac_wide(w[p], x, y);
     }
     // one product of D factors at this pair position
     __device__ __forceinline__ void add_product(const Fe* lo, const Fe* hi) {
@@ -209,13 +257,13 @@ struct RoundAcc {
             Fe m = lo[0];
 #pragma unroll
             for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, lo[f]);
-            Fd::mac_wide(w[0], m, lo[D - 1]);
+            mac(0, m, lo[D - 1]);
         }
         if (!SKIP1) {
             Fe m = hi[0];
 #pragma unroll
             for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, hi[f]);
-            Fd::mac_wide(w[S::of(1)], m, hi[D - 1]);
+            mac(S::of(1), m, hi[D - 1]);
         }
         Fe cur[D], dl[D];
 #pragma unroll
@@ -230,21 +278,21 @@ struct RoundAcc {
             Fe m = cur[0];
 #pragma unroll
             for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, cur[f]);
-            Fd::mac_wide(w[S::of(t)], m, cur[D - 1]);
+            mac(S::of(t), m, cur[D - 1]);
         }
     }
     __device__ __forceinline__ void finish(Fe* out) {
 #pragma unroll
-        for (int p = 0; p < S::N; ++p) out[p] = Fd::reduce_wide(w[p]);
+        for (int p = 0; p < S::N; ++p) out[p] = Fd::reduce_wide(SM ? wide_load(sm + p * ACC_VECS * BLOCK) : w[p]);
     }
 };
 // D == 1 (plain sumcheck, sum_check_protocol.rs:168-175): sums of table values, modular adds.
-template <class F, int NPTS, bool SKIP1>
-struct RoundAcc<F, 1, NPTS, SKIP1> {
+template <class F, int NPTS, bool SKIP1, bool SM>
+struct RoundAcc<F, 1, NPTS, SKIP1, SM> {
     typedef Field<F> Fd;
     typedef Slots<NPTS, SKIP1> S;
     Fe v[S::N];
-    __device__ __forceinline__ void init() {
+    __device__ __forceinline__ void init(uint4* = nullptr) {
 #pragma unroll
         for (int p = 0; p < S::N; ++p) v[p] = Fd::zero();
     }
@@ -265,73 +313,136 @@ struct RoundAcc<F, 1, NPTS, SKIP1> {
     }
 };
 // X*Y + Z at t = 0, (1), 2: products lazily, the Z column with modular adds.
-template <class F, bool SKIP1>
+template <class F, bool SKIP1, bool SM = false>
 struct XyzAcc {
     typedef Field<F> Fd;
     typedef Slots<3, SKIP1> S;
-    Wide w[S::N];
+    Wide w[SM ? 1 : S::N];
     Fe z[S::N];
-    __device__ __forceinline__ void init() {
+    uint4* sm;
+    __device__ __forceinline__ void init(uint4* slots = nullptr) {
+        sm = slots;
 #pragma unroll
         for (int p = 0; p < S::N; ++p) {
-            w[p] = Fd::wide_zero();
+            if (SM) wide_store(sm + p * ACC_VECS * BLOCK, Fd::wide_zero());
+            else w[p] = Fd::wide_zero();
             z[p] = Fd::zero();
         }
     }
+    __device__ __forceinline__ void mac(int p, const Fe& x, const Fe& y) {
+        if (SM) mac_wide_sm<F>(sm + p * ACC_VECS * BLOCK, x, y);
+        else Fd::mac_wide(w[p], x, y);
+    }
     __device__ __forceinline__ void add(const Fe* lo, const Fe* hi) {
-        Fd::mac_wide(w[0], lo[0], lo[1]);
+        mac(0, lo[0], lo[1]);
         z[0] = Fd::add(z[0], lo[2]);
         if (!SKIP1) {
-            Fd::mac_wide(w[S::of(1)], hi[0], hi[1]);
+            mac(S::of(1), hi[0], hi[1]);
             z[S::of(1)] = Fd::add(z[S::of(1)], hi[2]);
         }
         Fe x2 = Fd::sub(Fd::dbl(hi[0]), lo[0]);
         Fe y2 = Fd::sub(Fd::dbl(hi[1]), lo[1]);
         Fe z2 = Fd::sub(Fd::dbl(hi[2]), lo[2]);
-        Fd::mac_wide(w[S::of(2)], x2, y2);
+        mac(S::of(2), x2, y2);
         z[S::of(2)] = Fd::add(z[S::of(2)], z2);
     }
     __device__ __forceinline__ void finish(Fe* out) {
 #pragma unroll
-        for (int p = 0; p < S::N; ++p) out[p] = Fd::add(Fd::reduce_wide(w[p]), z[p]);
+        for (int p = 0; p < S::N; ++p) out[p] = Fd::add(Fd::reduce_wide(SM ? wide_load(sm + p * ACC_VECS * BLOCK) : w[p]), z[p]);
     }
 };
 
+// ------------------------------------------------------- staged table reads
+// The streaming kernels read each thread's entries through a private slot of
+// shared memory filled by cp.async (LDGSTS): the loads of the NEXT table /
+// iteration are in flight while the current one is multiplied, without
+// holding 64 registers of not-yet-arrived data per thread.  A slot is only ever
+// touched by its own thread, so there is no CTA-wide synchronisation.
+// Layout: stage[buf][vec][thread] of uint4 -> consecutive threads hit
+// consecutive 16-byte words (bank-conflict free), global reads stay coalesced.
+__device__ __forceinline__ void cp_async16(uint4* smem, const uint4* gmem) {
+    const unsigned int sa = static_cast<unsigned int>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ Fe fe_from_smem(const uint4* slot_lo, const uint4* slot_hi) {
+    const uint4 a = *slot_lo, b = *slot_hi;
+    Fe r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+constexpr int EVAL_BUFS = 4;   // k_sc_eval: 4 buffers x 4 vectors (lo, hi of one table)
+constexpr int FOLD_BUFS = 2;   // k_sc_fold_eval: 2 buffers x 8 vectors (the quad of one table)
+constexpr int STAGE_BYTES = 2 * 8 * BLOCK * 16;  // 64 KiB per CTA of staging for both kernels
+constexpr int FOLD_SMEM_BYTES = STAGE_BYTES + (MAXPTS - 1) * ACC_VECS * BLOCK * 16;  // + parked accumulators
+
 // K7: evaluations of the first round (no challenge to bind yet): all NPTS points.
 template <class F, int KIND, int D, int NPTS>
-__global__ void __launch_bounds__(BLOCK) k_sc_eval(const ScArgs a) {
+__global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ ScArgs a) {
+    extern __shared__ uint4 stage[];
     const uint64_t half = a.n_out >> 1;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t j0 = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const int T = KIND == KIND_XYZ ? 3 : a.n_products * D;
+    uint4* my = stage + threadIdx.x;
+    // flattened prefetch sequence q = iteration * T + table
+    uint64_t pj = j0;
+    int pt = 0, pbuf = 0;
+    auto issue = [&]() {
+        if (pj < half) {
+            const TabRef& t = a.in[pt];
+            uint4* dst = my + (size_t)pbuf * 4 * BLOCK;
+            cp_async16(dst, t.base + pj);
+            cp_async16(dst + BLOCK, t.base + t.stride + pj);
+            cp_async16(dst + 2 * BLOCK, t.base + pj + half);
+            cp_async16(dst + 3 * BLOCK, t.base + t.stride + pj + half);
+        }
+        cp_async_commit();
+        pbuf = (pbuf + 1) & (EVAL_BUFS - 1);
+        if (++pt == T) {
+            pt = 0;
+            pj += step;
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < EVAL_BUFS; ++k) issue();
+    int cbuf = 0;
+    auto take = [&](Fe& lo, Fe& hi) {
+        cp_async_wait<EVAL_BUFS - 1>();
+        const uint4* src = my + (size_t)cbuf * 4 * BLOCK;
+        lo = fe_from_smem(src, src + BLOCK);
+        hi = fe_from_smem(src + 2 * BLOCK, src + 3 * BLOCK);
+        cbuf = (cbuf + 1) & (EVAL_BUFS - 1);
+        issue();
+    };
     Fe out[NPTS];
     if (KIND == KIND_XYZ) {
         XyzAcc<F, false> acc;
         acc.init();
-        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+        for (uint64_t j = j0; j < half; j += step) {
             Fe lo[3], hi[3];
 #pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                lo[f] = ld_fe(a.in[f], j);
-                hi[f] = ld_fe(a.in[f], j + half);
-            }
+            for (int f = 0; f < 3; ++f) take(lo[f], hi[f]);
             acc.add(lo, hi);
         }
         acc.finish(out);
     } else {
         RoundAcc<F, D, NPTS, false> acc;
         acc.init();
-        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+        for (uint64_t j = j0; j < half; j += step) {
             for (int p = 0; p < a.n_products; ++p) {
                 Fe lo[D], hi[D];
 #pragma unroll
-                for (int f = 0; f < D; ++f) {
-                    lo[f] = ld_fe(a.in[p * D + f], j);
-                    hi[f] = ld_fe(a.in[p * D + f], j + half);
-                }
+                for (int f = 0; f < D; ++f) take(lo[f], hi[f]);
                 acc.add_product(lo, hi);
             }
         }
         acc.finish(out);
     }
+    cp_async_wait<0>();
     finish_round<F, NPTS>(out, a.fin);
 }
 
@@ -343,49 +454,84 @@ __global__ void __launch_bounds__(BLOCK) k_sc_eval(const ScArgs a) {
 // In-place operation (out == in) is safe: a thread only overwrites entries
 // that no other thread reads.  Returns NPTS-1 sums: s(0), s(2), .. (SKIP1).
 template <class F, int KIND, int D, int NPTS>
-__global__ void __launch_bounds__(BLOCK) k_sc_fold_eval(const ScArgs a) {
+__global__ void __launch_bounds__(BLOCK, 2) k_sc_fold_eval(const __grid_constant__ ScArgs a) {
     typedef Field<F> Fd;
+    extern __shared__ uint4 stage[];
     const uint64_t n_out = a.n_out, half = n_out >> 1;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t j0 = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const int T = KIND == KIND_XYZ ? 3 : a.n_products * D;
+    uint4* my = stage + threadIdx.x;
+    uint4* accs = stage + FOLD_BUFS * 8 * BLOCK + threadIdx.x;  // accumulators after the staging buffers
+    uint64_t pj = j0;
+    int pt = 0, pbuf = 0;
+    auto issue = [&]() {
+        if (pj < half) {
+            const TabRef& t = a.in[pt];
+            uint4* dst = my + (size_t)pbuf * 8 * BLOCK;
+            const uint4* g0 = t.base + pj;
+            const uint4* g1 = t.base + t.stride + pj;
+            cp_async16(dst, g0);
+            cp_async16(dst + BLOCK, g1);
+            cp_async16(dst + 2 * BLOCK, g0 + n_out);
+            cp_async16(dst + 3 * BLOCK, g1 + n_out);
+            cp_async16(dst + 4 * BLOCK, g0 + half);
+            cp_async16(dst + 5 * BLOCK, g1 + half);
+            cp_async16(dst + 6 * BLOCK, g0 + half + n_out);
+            cp_async16(dst + 7 * BLOCK, g1 + half + n_out);
+        }
+        cp_async_commit();
+        pbuf ^= 1;
+        if (++pt == T) {
+            pt = 0;
+            pj += step;
+        }
+    };
+    issue();
+    issue();
+    int cbuf = 0;
+    // fold the quad of table `t` at position j: lo = new[j], hi = new[j + half]
+    auto fold_table = [&](int t, uint64_t j, Fe& lo, Fe& hi) {
+        cp_async_wait<FOLD_BUFS - 1>();
+        const uint4* src = my + (size_t)cbuf * 8 * BLOCK;
+        {
+            const Fe x0 = fe_from_smem(src, src + BLOCK), x1 = fe_from_smem(src + 2 * BLOCK, src + 3 * BLOCK);
+            lo = Fd::fold_fixed(x0, x1, a.rt);
+            st_fe(a.out[t], j, lo);
+        }
+        {
+            const Fe y0 = fe_from_smem(src + 4 * BLOCK, src + 5 * BLOCK), y1 = fe_from_smem(src + 6 * BLOCK, src + 7 * BLOCK);
+            cbuf ^= 1;
+            issue();
+            hi = Fd::fold_fixed(y0, y1, a.rt);
+            st_fe(a.out[t], j + half, hi);
+        }
+    };
     Fe out[NPTS - 1];
     if (KIND == KIND_XYZ) {
-        XyzAcc<F, true> acc;
-        acc.init();
-        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+        XyzAcc<F, true, true> acc;
+        acc.init(accs);
+        for (uint64_t j = j0; j < half; j += step) {
             Fe lo[3], hi[3];
 #pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                Fe x0 = ld_fe(a.in[f], j), x1 = ld_fe(a.in[f], j + n_out);
-                Fe y0 = ld_fe(a.in[f], j + half), y1 = ld_fe(a.in[f], j + half + n_out);
-                lo[f] = Fd::fold_fixed(x0, x1, a.rt);
-                hi[f] = Fd::fold_fixed(y0, y1, a.rt);
-                st_fe(a.out[f], j, lo[f]);
-                st_fe(a.out[f], j + half, hi[f]);
-            }
+            for (int f = 0; f < 3; ++f) fold_table(f, j, lo[f], hi[f]);
             acc.add(lo, hi);
         }
         acc.finish(out);
     } else {
-        RoundAcc<F, D, NPTS, true> acc;
-        acc.init();
-        for (uint64_t j = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; j < half; j += step) {
+        RoundAcc<F, D, NPTS, true, true> acc;
+        acc.init(accs);
+        for (uint64_t j = j0; j < half; j += step) {
             for (int p = 0; p < a.n_products; ++p) {
                 Fe lo[D], hi[D];
 #pragma unroll
-                for (int f = 0; f < D; ++f) {
-                    const TabRef& ti = a.in[p * D + f];
-                    Fe x0 = ld_fe(ti, j), x1 = ld_fe(ti, j + n_out);
-                    Fe y0 = ld_fe(ti, j + half), y1 = ld_fe(ti, j + half + n_out);
-                    lo[f] = Fd::fold_fixed(x0, x1, a.rt);
-                    hi[f] = Fd::fold_fixed(y0, y1, a.rt);
-                    st_fe(a.out[p * D + f], j, lo[f]);
-                    st_fe(a.out[p * D + f], j + half, hi[f]);
-                }
+                for (int f = 0; f < D; ++f) fold_table(p * D + f, j, lo[f], hi[f]);
                 acc.add_product(lo, hi);
             }
         }
         acc.finish(out);
     }
+    cp_async_wait<0>();
     finish_round<F, NPTS - 1>(out, a.fin);
 }
 
