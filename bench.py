@@ -154,6 +154,35 @@ def run_reference(args):
     return 0
 
 
+def gkr_leg(z, ctx_unused, args):
+    """BASELINE configs[2] in its reference-legal form (SURVEY F8 i): binary-tree add/mul circuit, 2^21 inputs,
+    21 layers (widest 2^20 gates), BN254 Fr.  Times zkb_gkr_prove (circuit evaluation + all layer sumchecks,
+    inputs uploaded from host memory every call) and checks the proof with zkb_gkr_verify."""
+    import numpy as np
+    from oracle import c_oracle as O
+
+    log_in = args.gkr_log_inputs
+    L = log_in
+    rng = np.random.default_rng(7)
+    ctx = z.Context(z.BN254_FR, 0, z.MODE_COMPAT)
+    structure = [[z.Operation(int(b)) for b in rng.integers(0, 2, size=1 << (L - 1 - l))] for l in range(L)]
+    circ = z.gkr_circuit.Circuit(ctx, structure)
+    inputs = z.engine.to_mont(z.BN254_FR, O.synth_table(0, SEED + 1, 0, log_in))
+    prover = z.gkr_protocol.RawGkrProver(circ, inputs)
+    for _ in range(2):
+        prover.prove()
+    reps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        prover.prove()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    ok = prover.verify()
+    ctx.close()
+    return {"prove_ms": ms, "verify_accepts": ok, "rounds": int(prover.total), "layers": L, "inputs": 1 << log_in,
+            "workload": "configs[2] (reference-legal form): binary-tree circuit, 2^%d inputs, %d layers, widest layer 2^%d gates, BN254 Fr; "
+                        "KZG input commitment excluded (SURVEY F11); host wall clock around zkb_gkr_prove incl. input upload" % (log_in, L, log_in - 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,7 +191,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-vars", type=int, default=N_VARS_PER_GPU, help="variables per GPU shard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gkr-log-inputs", type=int, default=21)
     ap.add_argument("--tail-log2", type=int, default=None, help="persistent-kernel threshold (0 = one launch per round)")
+    ap.add_argument("--small-bytes", type=int, default=None, help="shared-memory budget of the small-table kernel (0 = off)")
     ap.add_argument("--quick", action="store_true", help="profiling run: resident leg only, warm-up as given (numbers are not bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -195,6 +226,8 @@ def main():
         ctx.comm_init(rank, world, box[0])
     if args.tail_log2 is not None:
         ctx.set_tail_threshold(args.tail_log2)
+    if args.small_bytes is not None:
+        ctx.set_small_threshold(args.small_bytes)
     S = z.sum_check_protocol
     T = z.fiat_shamir.Transcript
     a = z.MultilinearPoly.generate(ctx, SEED, 0, n)
@@ -223,9 +256,9 @@ def main():
         return float(t.item())
 
     # ---------------------------------------------------------------- resident (`value`)
-    proof = None
+    raw = S.RawGkrProver(sp)  # the bare C-ABI call; outputs are Montgomery limbs as a Rust caller receives them
     for _ in range(warmup):
-        proof = S.gkr_prove(0, sp, T(z.BN254_FR))
+        raw.prove(T(z.BN254_FR))
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ctx.profile(True)
@@ -233,7 +266,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        proof = S.gkr_prove(0, sp, T(z.BN254_FR))
+        raw.prove(T(z.BN254_FR))
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -241,13 +274,14 @@ def main():
     prof = ctx.profile_read()
     ctx.profile(False)
     clocks = sampler.stop() if sampler else None
+    proof = raw.proof()
     ms_step = ms_total / args.steps
     value = (1 << n) / (ms_step * 1e-3)
 
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "value": value, "gpu_launches": launches,
-                              "profile": {k: v for k, v in prof.items()}}))
+                              "profile": {k: v for k, v in prof.items()}, "gkr": gkr_leg(z, ctx, args) if world == 1 else None}))
         if dist is not None:
             dist.destroy_process_group()
         return 0
@@ -264,16 +298,16 @@ def main():
         ta = z.MultilinearPoly.from_host_pointer(ctx, host[0].data_ptr(), n_local)
         tb = z.MultilinearPoly.from_host_pointer(ctx, host[1].data_ptr(), n_local)
         s2 = z.SumPoly(ctx, [z.ProductPoly.from_polys(ctx, [ta, tb])])
-        pr = S.gkr_prove(0, s2, T(z.BN254_FR))
+        r2 = S.RawGkrProver(s2)
+        r2.prove(T(z.BN254_FR))
         s2.free()
         ta.free()
         tb.free()
-        return pr
+        return r2
 
     e2e_steps = min(args.steps, 5)
     pr2 = e2e_step()
-    assert [q.coefficients for q in pr2.proof_polynomials] == [q.coefficients for q in proof.proof_polynomials], \
-        "host-buffer path and resident path disagree"
+    assert np.array_equal(pr2.coeffs, raw.coeffs) and np.array_equal(pr2.fin, raw.fin), "host-buffer path and resident path disagree"
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
@@ -311,6 +345,8 @@ def main():
                 "ms_per_step": e2e_ms, "steps": e2e_steps},
         "gpu_launches": launches, "roofline": roof, "clocks": clocks,
     }
+    if world == 1:
+        line["gkr"] = gkr_leg(z, ctx, args)
     if world == 1 and not args.no_cpu_baseline:
         n_s = pick_cpu_sample(6.0)
         v, cores, dt = cpu_port_run(n_s, 2)

@@ -79,7 +79,7 @@ int32_t zkb_ctx_sync(zkb_ctx* ctx);
  * (ZKB_K_*), the number of launches, their summed duration and their summed ALGORITHMIC bytes
  * (compulsory reads + writes, DESIGN.md "Kernels") since profiling was enabled. */
 enum { ZKB_K_SC_EVAL = 0, ZKB_K_SC_FOLD_EVAL = 1, ZKB_K_FOLD_TABLES = 2, ZKB_K_FINAL_BIND = 3, ZKB_K_FOLD = 4,
-       ZKB_K_LAYOUT = 5, ZKB_K_GKR_BUILD = 6, ZKB_K_OTHER = 7, ZKB_K_SC_TAIL = 8, ZKB_K_COUNT = 9 };
+       ZKB_K_LAYOUT = 5, ZKB_K_GKR_BUILD = 6, ZKB_K_OTHER = 7, ZKB_K_SC_TAIL = 8, ZKB_K_SC_SMALL = 9, ZKB_K_COUNT = 10 };
 int32_t zkb_ctx_profile(zkb_ctx* ctx, int32_t enable);
 int32_t zkb_ctx_profile_read(zkb_ctx* ctx, int32_t kernel_id, uint64_t* launches, double* ms, double* alg_bytes);
 const char* zkb_kernel_name(int32_t kernel_id);
@@ -93,8 +93,11 @@ int32_t zkb_ctx_comm_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8
 int32_t zkb_ctx_set_gather_threshold(zkb_ctx* ctx, uint32_t log2_local_entries);
 /* Rounds whose tables have at most 2^log2_entries entries run inside ONE persistent cooperative kernel that
  * exchanges round sums / challenges with the host transcript through a mailbox in mapped host memory
- * (no launch per round).  0 disables it (one launch per round).  Default 18. */
+ * (no launch per round).  0 disables it (one launch per round).  Default 40 (always). */
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* ctx, uint32_t log2_entries);
+/* Once all tables of a sumcheck fit in `smem_bytes` of shared memory (default and maximum 200 KiB) the remaining
+ * rounds run in a single-CTA kernel that keeps the tables on chip; 0 disables it. */
+int32_t zkb_ctx_set_small_threshold(zkb_ctx* ctx, uint32_t smem_bytes);
 
 /* --------------------------------------------- MultilinearPoly (device table) */
 /* MultilinearPoly::new (multilinear_polynomial_evaluation.rs:26-37): `len` must be a power of two. */

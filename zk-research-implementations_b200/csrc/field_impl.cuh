@@ -41,8 +41,26 @@ bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaSt
 int l_sc_tail(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream_t s) {
     void* params[1] = {const_cast<TailArgs*>(&a)};
 #define X(K, DD, NP) \
-    if (kind == K && D == DD && npts == NP) \
-        return (int)cudaLaunchCooperativeKernel((const void*)k_sc_tail<FT, K, DD, NP>, dim3(grid), dim3(BLOCK), params, 0, s);
+    if (kind == K && D == DD && npts == NP) { \
+        constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+        static bool once = (cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
+        (void)once; \
+        return (int)cudaLaunchCooperativeKernel((const void*)k_sc_tail<FT, K, DD, NP>, dim3(grid), dim3(BLOCK), params, SM, s); \
+    }
+    ZKB_SC_CASES(X)
+#undef X
+    return -1;
+}
+int l_sc_small(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s) {
+    const int T = a.n_tables;
+    const size_t smem = (size_t)T * a.n_in * 32;
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { \
+        static bool once = (cudaFuncSetAttribute(k_sc_small<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM_MAX), true); \
+        (void)once; \
+        k_sc_small<FT, K, DD, NP><<<1, SMALL_BLOCK, smem, s>>>(a); \
+        return (int)cudaGetLastError(); \
+    }
     ZKB_SC_CASES(X)
 #undef X
     return -1;
@@ -51,7 +69,11 @@ int l_sc_occupancy(int fused, int kind, int D, int npts) {
     int nb = 0;
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        if (fused == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_tail<FT, K, DD, NP>, BLOCK, 0); \
+        if (fused == 2) { \
+            constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+            cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_tail<FT, K, DD, NP>, BLOCK, SM); \
+        } \
         else if (fused) { \
             constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
             cudaFuncSetAttribute(k_sc_fold_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); \
@@ -120,7 +142,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_occupancy, l_fold_tables, l_final_bind, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

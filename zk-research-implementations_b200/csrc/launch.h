@@ -15,6 +15,8 @@ struct FieldKernels {
     bool (*sc_fold_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
     // persistent round kernel (cooperative launch); returns a cudaError_t, or -1 if the shape is not instantiated
     int (*sc_tail)(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream_t s);
+    // single-CTA shared-memory kernel for small tables; returns a cudaError_t, or -1 if not instantiated
+    int (*sc_small)(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s);
     // resident CTAs per SM for that instantiation (0 = unsupported); fused: 0 = k_sc_eval, 1 = k_sc_fold_eval, 2 = k_sc_tail
     int (*sc_occupancy)(int fused, int kind, int D, int npts);
     void (*fold_tables)(const FoldTablesArgs& a, int grid, cudaStream_t s);

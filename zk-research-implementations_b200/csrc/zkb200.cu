@@ -159,7 +159,8 @@ struct zkb_ctx {
     TailMailbox* mb = nullptr;   // mapped pinned host memory
     TailRelay* d_relay = nullptr;
     unsigned int tail_seq = 0;
-    uint32_t tail_log2 = 18;
+    uint32_t tail_log2 = 40;                 // every unsharded round after the first runs in a persistent kernel
+    uint32_t small_bytes = SMALL_SMEM_MAX;   // shared-memory budget of k_sc_small (0 = off)
     std::unordered_map<std::string, int> occ_cache;
     // per-launch event timing (zkb_ctx_profile)
     bool prof = false;
@@ -584,15 +585,21 @@ int32_t sp_final_values(zkb_ctx* c, SumPolyState* sp, Fe* vals) {
 
 
 // ------------------------------------------------------------- round driver
-// One sumcheck from the first round to the last bind.  Large rounds are one launch each
-// (k_sc_fold_eval); once the tables have at most 2^tail_log2 entries the remaining rounds run inside
-// the persistent kernel k_sc_tail and only mailbox messages cross PCIe.
+// One sumcheck from the first round to the last bind.  Three regimes, chosen by table size:
+//   * sharded tables (multi-GPU): one launch per round + NCCL all-reduce (sp_bind_and_next);
+//   * large tables: the persistent cooperative kernel k_sc_tail (all rounds in one launch,
+//     challenges through the host mailbox);
+//   * tables that fit in shared memory: the single-CTA kernel k_sc_small, which can also
+//     produce round 0 itself, so a small sumcheck is exactly one launch.
 struct RoundDriver {
     zkb_ctx* c;
     SumPolyState* sp;
-    bool live = false;       // the persistent kernel is running
+    bool live = false;       // a persistent kernel is running
+    bool small = false;      // ... and it is k_sc_small
     unsigned int base = 0;   // its mailbox sequence base
-    unsigned int it = 0;     // challenges delivered to it so far
+    unsigned int sent = 0;   // challenges delivered through the mailbox so far
+    unsigned int pubs = 0;   // messages consumed from it so far
+    uint64_t stop_n = 0;     // k_sc_tail leaves once the tables have <= stop_n entries
 
     RoundDriver(zkb_ctx* ctx, SumPolyState* s) : c(ctx), sp(s) {}
     ~RoundDriver() { abort(); }
@@ -604,11 +611,17 @@ struct RoundDriver {
         c->mb->abort = 0;
         live = false;
     }
-    int32_t first(Fe* evals) { return sp_round_evals(c, sp, evals); }
-
+    uint64_t small_cap() const {  // largest table (entries) k_sc_small takes for this shape
+        if (!c->small_bytes || sp->sharded || !sp->rest.empty()) return 0;
+        uint64_t budget = c->small_bytes < (uint32_t)SMALL_SMEM_MAX ? c->small_bytes : (uint32_t)SMALL_SMEM_MAX;
+        uint64_t n = 1;
+        while (2 * n * sp->sel.size() * 32 <= budget) n *= 2;
+        return n >= 2 ? n : 0;
+    }
+    bool small_ok() const { return sp->cur_n >= 2 && sp->cur_n <= small_cap(); }
     bool tail_ok() const {
         return c->tail_log2 > 0 && !sp->sharded && sp->rest.empty() && sp->have_evals && sp->cur_n >= 2 &&
-               sp->cur_n <= (1ull << c->tail_log2) && sc_occ(c, 2, sp->kind, sp->kD, sp->npts) > 0;
+               sp->cur_n <= (1ull << (c->tail_log2 > 62 ? 62 : c->tail_log2)) && sc_occ(c, 2, sp->kind, sp->kD, sp->npts) > 0;
     }
     int32_t wait_dev(unsigned int want) {
         uint32_t spins = 0;
@@ -632,8 +645,54 @@ struct RoundDriver {
         asm volatile("" ::: "memory");
         return ZKB_OK;
     }
+    void begin_mailbox() {
+        c->tail_seq += 64;
+        base = c->tail_seq;
+        sent = pubs = 0;
+        c->mb->abort = 0;
+        c->mb->dev_error = 0;
+    }
+    void send(const Fe& r) {
+        const unsigned int want = base + (++sent);
+        uint32_t x = 0;
+        for (int k = 0; k < 8; ++k) {
+            c->mb->r[k] = r.l[k];
+            x ^= r.l[k];
+        }
+        c->mb->chk = x ^ (want * 0x9E3779B9u);
+        asm volatile("" ::: "memory");
+        c->mb->host_seq = want;  // x86 keeps store order: the payload is visible before the sequence number
+    }
+    int32_t launch_small(bool first_eval, const Fe& r) {
+        if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
+        SmallArgs a;
+        std::memset(&a, 0, sizeof a);
+        for (size_t i = 0; i < sp->sel.size(); ++i) {
+            a.in[i] = sp->cur(sp->sel[i]).ref();
+            a.out[i] = (sp->state == 2 ? sp->gath[sp->sel[i]] : sp->work[sp->sel[i]]).ref();
+        }
+        a.n_tables = (int)sp->sel.size();
+        a.n_products = sp->kP;
+        a.n_in = (uint32_t)sp->cur_n;
+        a.first_eval = first_eval ? 1 : 0;
+        a.r0 = r;
+        a.mb = c->mb;
+        begin_mailbox();
+        a.base_seq = base;
+        a.timeout_clocks = 6000000000ll;
+        prof_begin(c, ZKB_K_SC_SMALL, 32.0 * (double)sp->sel.size() * (double)sp->cur_n);
+        int e = c->K->sc_small(sp->kind, sp->kD, sp->npts, a, c->stream);
+        if (e < 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_small: shape not instantiated");
+        if (e != 0) {
+            c->last_error = std::string("k_sc_small launch: ") + cudaGetErrorString((cudaError_t)e);
+            return ZKB_ERR_CUDA;
+        }
+        ZK_TRY(check_launch(c, "k_sc_small"));
+        live = small = true;
+        if (sp->state == 0) sp->state = 1;
+        return ZKB_OK;
+    }
     int32_t launch_tail(const Fe& r) {
-        const int T = (int)sp->src.size();
         if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
         TailArgs a;
         std::memset(&a, 0, sizeof a);
@@ -641,7 +700,6 @@ struct RoundDriver {
             a.in[i] = sp->cur(sp->sel[i]).ref();
             a.out[i] = (sp->state == 2 ? sp->gath[sp->sel[i]] : sp->work[sp->sel[i]]).ref();
         }
-        (void)T;
         a.n_tables = (int)sp->sel.size();
         a.n_products = sp->kP;
         a.n_in = sp->cur_n;
@@ -650,17 +708,16 @@ struct RoundDriver {
         a.mb = c->mb;
         a.relay = c->d_relay;
         a.ticket = c->d_ticket;
-        c->tail_seq += 64;
-        base = a.base_seq = c->tail_seq;
+        begin_mailbox();
+        a.base_seq = base;
         a.timeout_clocks = 6000000000ll;  // ~3 s
+        stop_n = a.stop_n = small_cap();
         const uint64_t quads = sp->cur_n / 4 ? sp->cur_n / 4 : 1;
         const int grid = grid_for(c, quads, sc_occ(c, 2, sp->kind, sp->kD, sp->npts));
         ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
         a.partials = c->d_partials;
-        c->mb->abort = 0;
-        c->mb->dev_error = 0;
         ZK_CUDA(c, cudaMemsetAsync(&c->d_relay->seq, 0, 2 * sizeof(unsigned int), c->stream));
-        prof_begin(c, ZKB_K_SC_TAIL, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - 1));
+        prof_begin(c, ZKB_K_SC_TAIL, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)));
         int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, a, grid, c->stream);
         if (e < 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_tail: shape not instantiated");
         if (e != 0) {
@@ -669,32 +726,34 @@ struct RoundDriver {
         }
         ZK_TRY(check_launch(c, "k_sc_tail"));
         live = true;
-        it = 0;
+        small = false;
         if (sp->state == 0) sp->state = 1;
         return ZKB_OK;
     }
+    // Round 0: s(0..d) of the unbound tables.
+    int32_t first(Fe* evals) {
+        if (sp->cur_n >= 2 && small_ok() && sc_occ(c, 0, sp->kind, sp->kD, sp->npts) > 0) {
+            ZK_TRY(launch_small(true, c->H.zero()));
+            ZK_TRY(wait_dev(base + (++pubs)));
+            for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i] = c->mb->evals[i];
+            sp->have_evals = true;
+            return ZKB_OK;
+        }
+        return sp_round_evals(c, sp, evals);
+    }
     // Bind r; evals != NULL: the next round's s(0..d); NULL: this was the last variable, finals get the bound values.
     int32_t next(const Fe& r, Fe* evals, Fe* finals) {
-        if (!live && !tail_ok()) return sp_bind_and_next(c, sp, r, evals, finals);
+        if (!live && !sp->have_evals) return sp_bind_and_next(c, sp, r, evals, finals);
+        const bool go_small = !live && small_ok();
+        if (!live && !go_small && !tail_ok()) return sp_bind_and_next(c, sp, r, evals, finals);
         const RoundInterpolator& ip = c->interp[sp->npts];
         Fe co[MAXPTS];
         const int colen = ip.interpolate(sp->last_evals, co);
         const Fe claim = uni_evaluate(c->H, co, colen, r);
-        if (!live) {
-            ZK_TRY(launch_tail(r));
-        } else {
-            ++it;
-            const unsigned int want = base + it;
-            uint32_t x = 0;
-            for (int k = 0; k < 8; ++k) {
-                c->mb->r[k] = r.l[k];
-                x ^= r.l[k];
-            }
-            c->mb->chk = x ^ (want * 0x9E3779B9u);
-            asm volatile("" ::: "memory");
-            c->mb->host_seq = want;  // x86 keeps store order: the payload is visible before the sequence number
-        }
-        ZK_TRY(wait_dev(base + it + 1));
+        if (live) send(r);
+        else if (go_small) ZK_TRY(launch_small(false, r));
+        else ZK_TRY(launch_tail(r));
+        ZK_TRY(wait_dev(base + (++pubs)));
         sp->cur_n /= 2;
         if (sp->cur_n == 1) {
             live = false;  // the kernel leaves after publishing the bound values
@@ -705,7 +764,8 @@ struct RoundDriver {
             if (evals) ZK_FAIL(c, ZKB_ERR_ARITY, "bind_and_next: no next round after the last variable");
             return ZKB_OK;
         }
-        if (!evals) {  // caller stops early: not supported inside the persistent kernel
+        if (!small && sp->cur_n <= stop_n) live = false;  // k_sc_tail handed over to k_sc_small
+        if (!evals) {  // caller stops early: not supported inside a persistent kernel
             abort();
             ZK_FAIL(c, ZKB_ERR_BAD_ARG, "round driver: early stop inside the persistent kernel");
         }
@@ -1206,7 +1266,7 @@ int32_t zkb_ctx_profile_read(zkb_ctx* c, int32_t k, uint64_t* launches, double* 
 }
 const char* zkb_kernel_name(int32_t k) {
     static const char* names[ZKB_K_COUNT] = {"k_sc_eval", "k_sc_fold_eval", "k_fold_tables", "k_final_bind", "k_fold",
-                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other", "k_sc_tail"};
+                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other", "k_sc_tail", "k_sc_small"};
     return (k >= 0 && k < ZKB_K_COUNT) ? names[k] : "?";
 }
 
@@ -1234,6 +1294,11 @@ int32_t zkb_ctx_comm_init(zkb_ctx* c, int32_t rank, int32_t world, const uint8_t
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* c, uint32_t log2_entries) {
     if (!c) return ZKB_ERR_BAD_ARG;
     c->tail_log2 = log2_entries;
+    return ZKB_OK;
+}
+int32_t zkb_ctx_set_small_threshold(zkb_ctx* c, uint32_t smem_bytes) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    c->small_bytes = smem_bytes;
     return ZKB_OK;
 }
 int32_t zkb_ctx_set_gather_threshold(zkb_ctx* c, uint32_t log2_local_entries) {

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
         "zkb_ctx_comm_init": (i32, [vp, i32, i32, u8p]),
         "zkb_ctx_set_gather_threshold": (i32, [vp, u32]),
         "zkb_ctx_set_tail_threshold": (i32, [vp, u32]),
+        "zkb_ctx_set_small_threshold": (i32, [vp, u32]),
         "zkb_mle_upload": (i32, [vp, vp, u64, u64p]),
         "zkb_mle_upload_shard": (i32, [vp, vp, u64, u64p]),
         "zkb_mle_generate": (i32, [vp, u64, u64, u32, u64p]),
@@ -232,7 +233,7 @@ class Context:
     def profile_read(self) -> dict:
         """{kernel name: (launches, total ms, total algorithmic bytes)} since profile(True)."""
         out = {}
-        for k in range(9):
+        for k in range(10):
             n, ms, by = C.c_uint64(), C.c_double(), C.c_double()
             _ck(self, lib().zkb_ctx_profile_read(self._h, k, C.byref(n), C.byref(ms), C.byref(by)))
             if n.value:
@@ -246,6 +247,9 @@ class Context:
 
     def set_tail_threshold(self, log2_entries: int) -> None:
         _ck(self, lib().zkb_ctx_set_tail_threshold(self._h, log2_entries))
+
+    def set_small_threshold(self, smem_bytes: int) -> None:
+        _ck(self, lib().zkb_ctx_set_small_threshold(self._h, smem_bytes))
 
     def set_gather_threshold(self, log2_local: int) -> None:
         _ck(self, lib().zkb_ctx_set_gather_threshold(self._h, log2_local))

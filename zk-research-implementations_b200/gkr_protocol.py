@@ -34,6 +34,36 @@ def _rounds_per_layer(circuit: Circuit) -> List[int]:
     return [2 * max(1, int(2 * int(g)).bit_length() - 1) for g in circuit.gates[::-1]]
 
 
+class RawGkrProver:
+    """The bare zkb_gkr_prove call on a host array of Montgomery limbs (a Rust `&[F]`), outputs preallocated."""
+
+    def __init__(self, circuit: Circuit, inputs_mont: np.ndarray):
+        self.circuit, self.ctx = circuit, circuit.ctx
+        self.inputs = np.ascontiguousarray(inputs_mont, dtype=np.uint64)
+        rpl = _rounds_per_layer(circuit)
+        self.total, L = sum(rpl), len(circuit.gates)
+        self.w0 = np.zeros((2, 4), dtype=np.uint64)
+        self.coeffs = np.zeros((self.total, 3, 4), dtype=np.uint64)
+        self.lens = np.zeros(self.total, dtype=np.int32)
+        self.chals = np.zeros((self.total, 4), dtype=np.uint64)
+        self.claimed = np.zeros((max(L - 1, 1), 2, 4), dtype=np.uint64)
+        self.fin = np.zeros((2, 4), dtype=np.uint64)
+        self.nr = C.c_uint32()
+
+    def prove(self) -> None:
+        ctx = self.ctx
+        _ck(ctx, lib().zkb_gkr_prove(ctx.handle, self.circuit.handle, self.inputs.ctypes.data, self.inputs.shape[0], _p(self.w0),
+                                     _p(self.coeffs), self.lens.ctypes.data_as(i32p), _p(self.chals), _p(self.claimed), _p(self.fin),
+                                     C.byref(self.nr)))
+
+    def verify(self) -> bool:
+        ctx = self.ctx
+        ok = C.c_int32()
+        _ck(ctx, lib().zkb_gkr_verify(ctx.handle, self.circuit.handle, self.inputs.ctypes.data, self.inputs.shape[0], _p(self.w0),
+                                      _p(self.coeffs), self.lens.ctypes.data_as(i32p), _p(self.claimed), _p(self.fin), C.byref(ok)))
+        return bool(ok.value)
+
+
 def prove(circuit: Circuit, inputs: Sequence[int]) -> GkrProof:  # :31-126
     ctx = circuit.ctx
     rpl = _rounds_per_layer(circuit)

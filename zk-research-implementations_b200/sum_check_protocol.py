@@ -68,6 +68,34 @@ def verify(polynomial: MultilinearPoly, proof: Proof, absorb_table: bool = True)
     return bool(ok.value)
 
 
+class RawGkrProver:
+    """The bare C-ABI call of gkr_prove with preallocated Montgomery-limb outputs -- what a Rust caller pays:
+    no per-call allocation and no canonical <-> Montgomery conversion (its `F` IS the Montgomery limbs)."""
+
+    def __init__(self, composed_polynomial: SumPoly):
+        self.sp = composed_polynomial
+        ctx = self.ctx = composed_polynomial.ctx
+        self.d = d = composed_polynomial.get_degree()
+        self.n = n = composed_polynomial.polys[0].evaluation[0].num_of_vars + (ctx.world.bit_length() - 1)
+        self.coeffs = np.zeros((max(n, 1), d + 1, 4), dtype=np.uint64)
+        self.lens = np.zeros(max(n, 1), dtype=np.int32)
+        self.chals = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        self.fin = np.zeros((len(composed_polynomial.polys) * d, 4), dtype=np.uint64)
+        self.claim = np.zeros((1, 4), dtype=np.uint64)
+        self._args = (ctx.handle, None, _p(self.claim), composed_polynomial.handle(), _p(self.coeffs),
+                      self.lens.ctypes.data_as(i32p), _p(self.chals), _p(self.fin))
+        self._fn = lib().zkb_gkr_sumcheck_prove
+
+    def prove(self, transcript: Transcript) -> None:
+        a = self._args
+        _ck(self.ctx, self._fn(a[0], transcript.handle, a[2], a[3], a[4], a[5], a[6], a[7]))
+
+    def proof(self, claimed_sum: int = 0) -> "GkrProof":
+        ctx, n = self.ctx, self.n
+        polys = [UnivariatePoly(ctx.unmont(self.coeffs[k, : self.lens[k]]), ctx.field) for k in range(n)]
+        return GkrProof(polys, claimed_sum, ctx.unmont(self.chals[:n]) if n else [], ctx.unmont(self.fin))
+
+
 def gkr_prove(claimed_sum: int, composed_polynomial: SumPoly, transcript: Transcript) -> GkrProof:  # :86-115
     ctx = composed_polynomial.ctx
     d = composed_polynomial.get_degree()
