@@ -28,7 +28,7 @@ bool l_sc_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_
 bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+        constexpr int SM = FoldSmem<K, DD, NP>::bytes; \
         static bool once = (cudaFuncSetAttribute(k_sc_fold_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
         (void)once; \
         k_sc_fold_eval<FT, K, DD, NP><<<grid, BLOCK, SM, s>>>(a); \
@@ -42,7 +42,7 @@ int l_sc_tail(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream
     void* params[1] = {const_cast<TailArgs*>(&a)};
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+        constexpr int SM = FoldSmem<K, DD, NP>::bytes; \
         static bool once = (cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
         (void)once; \
         return (int)cudaLaunchCooperativeKernel((const void*)k_sc_tail<FT, K, DD, NP>, dim3(grid), dim3(BLOCK), params, SM, s); \
@@ -70,12 +70,12 @@ int l_sc_occupancy(int fused, int kind, int D, int npts) {
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         if (fused == 2) { \
-            constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+            constexpr int SM = FoldSmem<K, DD, NP>::bytes; \
             cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); \
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_tail<FT, K, DD, NP>, BLOCK, SM); \
         } \
         else if (fused) { \
-            constexpr int SM = STAGE_BYTES + (NP - 1) * ACC_VECS * BLOCK * 16; \
+            constexpr int SM = FoldSmem<K, DD, NP>::bytes; \
             cudaFuncSetAttribute(k_sc_fold_eval<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); \
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_fold_eval<FT, K, DD, NP>, BLOCK, SM); \
         } else { \
@@ -91,6 +91,11 @@ int l_sc_occupancy(int fused, int kind, int D, int npts) {
 void l_fold_tables(const FoldTablesArgs& a, int grid, cudaStream_t s) { k_fold_tables<FT><<<grid, BLOCK, 0, s>>>(a); }
 void l_final_bind(const FoldTablesArgs& a, Fe* out, volatile unsigned int* flag, unsigned int seq, cudaStream_t s) {
     k_final_bind<FT><<<1, 32, 0, s>>>(a, out, flag, seq);
+}
+void l_multifold(int k, const MultiFoldArgs& a, int grid, cudaStream_t s) {
+    if (k == 3) k_multifold<FT, 3><<<grid, BLOCK, 0, s>>>(a);
+    else if (k == 2) k_multifold<FT, 2><<<grid, BLOCK, 0, s>>>(a);
+    else k_multifold<FT, 1><<<grid, BLOCK, 0, s>>>(a);
 }
 void l_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const FixedMul& rt, int grid, cudaStream_t s) {
     k_fold<FT><<<grid, BLOCK, 0, s>>>(in, out, n_out, shift, rt);
@@ -142,7 +147,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

@@ -456,19 +456,32 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ Sc
 // that no other thread reads.  Produces NPTS-1 per-thread sums: s(0), s(2), .. (SKIP1).
 // Shared by the one-launch-per-round kernel and the persistent kernel; `rt` may live in
 // the kernel parameters (constant bank) or in shared memory.
+// STAGED: table reads go through the cp.async slots (memory-latency-bound shapes, D <= 2).  Products of
+// three or more factors are multiplier-bound (5x the work per byte), so they read straight into
+// registers and spend the shared memory on the parked accumulators only (2 CTAs/SM either way).
+template <int KIND, int D>
+struct Staged {
+    static constexpr bool value = KIND == KIND_XYZ || D <= 2;
+};
+template <int KIND, int D, int NPTS>
+struct FoldSmem {
+    static constexpr int bytes = (Staged<KIND, D>::value ? STAGE_BYTES : 0) + (NPTS - 1) * ACC_VECS * BLOCK * 16;
+};
 template <class F, int KIND, int D, int NPTS>
 __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
                                            uint64_t n_out, const FixedMul& rt, uint4* stage, Fe* out) {
     typedef Field<F> Fd;
+    constexpr bool STAGED = Staged<KIND, D>::value;
     const uint64_t half = n_out >> 1;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
     const uint64_t j0 = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     const int T = KIND == KIND_XYZ ? 3 : n_products * D;
     uint4* my = stage + threadIdx.x;
-    uint4* accs = stage + FOLD_BUFS * 8 * BLOCK + threadIdx.x;  // accumulators after the staging buffers
+    uint4* accs = stage + (STAGED ? FOLD_BUFS * 8 * BLOCK : 0) + threadIdx.x;  // accumulators after the staging buffers
     uint64_t pj = j0;
     int pt = 0, pbuf = 0;
     auto issue = [&]() {
+        if (!STAGED) return;
         if (pj < half) {
             const TabRef& t = in[pt];
             uint4* dst = my + (size_t)pbuf * 8 * BLOCK;
@@ -495,6 +508,20 @@ __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const 
     int cbuf = 0;
     // fold the quad of table `t` at position j: lo = new[j], hi = new[j + half]
     auto fold_table = [&](int t, uint64_t j, Fe& lo, Fe& hi) {
+        if (!STAGED) {
+            const TabRef& ti = in[t];
+            {
+                const Fe x0 = ld_fe(ti, j), x1 = ld_fe(ti, j + n_out);
+                lo = Fd::fold_fixed(x0, x1, rt);
+                st_fe(outp[t], j, lo);
+            }
+            {
+                const Fe y0 = ld_fe(ti, j + half), y1 = ld_fe(ti, j + half + n_out);
+                hi = Fd::fold_fixed(y0, y1, rt);
+                st_fe(outp[t], j + half, hi);
+            }
+            return;
+        }
         cp_async_wait<FOLD_BUFS - 1>();
         const uint4* src = my + (size_t)cbuf * 8 * BLOCK;
         {
@@ -533,7 +560,7 @@ __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const 
         }
         acc.finish(out);
     }
-    cp_async_wait<0>();
+    if (STAGED) cp_async_wait<0>();
 }
 
 template <class F, int KIND, int D, int NPTS>
@@ -922,6 +949,32 @@ __global__ void k_final_bind(const FoldTablesArgs a, Fe* out, volatile unsigned 
     }
     __syncthreads();
     if (t == 0 && flag) *flag = seq;
+}
+
+// K3: bind the K leading variables in ONE pass (evaluate / multi_partial_evaluate,
+// multilinear_polynomial_evaluation.rs:65-91, where every challenge is known up front): thread v
+// reads the 2^K entries v + i*n_out, folds variable 0 (the top bit of i) first, writes one entry.
+// A chain of single folds moves 96 B per input entry; K = 3 moves 36 B.  In place is safe.
+struct MultiFoldArgs {
+    TabRef in, out;
+    uint64_t n_out;
+    FixedMul rt[3];
+};
+template <class F, int K>
+__global__ void __launch_bounds__(BLOCK) k_multifold(const __grid_constant__ MultiFoldArgs a) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t v = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; v < a.n_out; v += step) {
+        Fe x[1 << K];
+#pragma unroll
+        for (int i = 0; i < (1 << K); ++i) x[i] = ld_fe(a.in, v + (uint64_t)i * a.n_out);
+#pragma unroll
+        for (int l = 0; l < K; ++l) {
+            const int h = 1 << (K - 1 - l);
+#pragma unroll
+            for (int i = 0; i < h; ++i) x[i] = Field<F>::fold_fixed(x[i], x[i + h], a.rt[l]);
+        }
+        st_fe(a.out, v, x[0]);
+    }
 }
 
 // K1: partial_evaluate(bit, v) (multilinear_polynomial_evaluation.rs:52-63).
