@@ -8,6 +8,10 @@
 // only be created on a CUDA device.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <cstdio>
@@ -119,6 +123,107 @@ struct CircuitState {
 };
 }  // namespace
 
+
+// ------------------------------------------------ intra-node exchange of round sums
+// The per-round combine of the ranks' partial sums is latency-critical and tiny ((d+1) x 32 bytes per
+// rank), and the host needs the result anyway for the transcript.  On one box (the deployment this engine
+// targets: the 8 GPUs of a node) the ranks' host threads therefore exchange the sums through a POSIX
+// shared-memory segment with sequence numbers (about 1 us), and NCCL over NVLink carries the bulk step
+// (the all-gather of the shrunken tables).  If the segment cannot be opened the engine falls back to one
+// ncclAllReduce per round over zero-extended limbs.
+struct ShmSlot {
+    volatile uint64_t seq;  // rounds posted by this rank
+    uint64_t pad[7];
+    uint64_t v[2][MAXPTS][4];
+    uint64_t pad2[(512 - 64 - 2 * MAXPTS * 32) / 8];
+};
+static_assert(sizeof(ShmSlot) == 512, "one slot = 512 bytes");
+struct ShmHeader {
+    volatile uint32_t attached;
+    uint32_t pad[127];
+};
+struct ShmComm {
+    ShmHeader* hdr = nullptr;
+    ShmSlot* slots = nullptr;
+    size_t bytes = 0;
+    uint64_t round = 0;
+    int rank = 0, world = 1;
+    bool open(const uint8_t id[128], int rank_, int world_) {
+        rank = rank_;
+        world = world_;
+        char name[64];
+        unsigned long long h = 1469598103934665603ull;
+        for (int i = 0; i < 128; ++i) h = (h ^ id[i]) * 1099511628211ull;
+        snprintf(name, sizeof name, "/zkb200_%016llx", h);
+        bytes = sizeof(ShmHeader) + sizeof(ShmSlot) * (size_t)world;
+        int fd = -1;
+        if (rank == 0) {
+            shm_unlink(name);
+            fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+            if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) {
+                if (fd >= 0) close(fd);
+                return false;
+            }
+        } else {
+            for (int tries = 0; tries < 20000 && fd < 0; ++tries) {  // up to ~20 s for rank 0 to create it
+                fd = shm_open(name, O_RDWR, 0600);
+                struct stat st;
+                if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes)) {
+                    close(fd);
+                    fd = -1;
+                }
+                if (fd < 0) usleep(1000);
+            }
+            if (fd < 0) return false;
+        }
+        void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (p == MAP_FAILED) return false;
+        hdr = (ShmHeader*)p;
+        slots = (ShmSlot*)((uint8_t*)p + sizeof(ShmHeader));
+        __atomic_add_fetch(&hdr->attached, 1u, __ATOMIC_SEQ_CST);
+        for (long tries = 0; hdr->attached < (uint32_t)world; ++tries) {
+            if (tries > 20000) return false;
+            usleep(1000);
+        }
+        // every rank has it mapped: the name can go (the memory lives until the last unmap).  Rank 0 waits a
+        // little so that no rank is still between shm_open and mmap -- they all passed `attached` already.
+        if (rank == 0) shm_unlink(name);
+        return true;
+    }
+    void close_() {
+        if (hdr) munmap((void*)hdr, bytes);
+        hdr = nullptr;
+        slots = nullptr;
+    }
+    // vals[0..n) of every rank are added (mod p, in rank order, so every rank gets identical bits)
+    bool allreduce(const HostField& H, Fe* vals, int n) {
+        const uint64_t k = ++round;
+        ShmSlot& mine = slots[rank];
+        for (int i = 0; i < n; ++i) std::memcpy((void*)mine.v[k & 1][i], vals[i].l, 32);
+        __atomic_store_n(&mine.seq, k, __ATOMIC_RELEASE);
+        Fe acc[MAXPTS];
+        for (int i = 0; i < n; ++i) acc[i] = H.zero();
+        for (int r = 0; r < world; ++r) {
+            ShmSlot& s = slots[r];
+            uint64_t spins = 0;
+            while (__atomic_load_n(&s.seq, __ATOMIC_ACQUIRE) < k) {
+                if (++spins > (1ull << 33)) return false;  // a peer died
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            for (int i = 0; i < n; ++i) {
+                Fe v;
+                std::memcpy(v.l, (const void*)s.v[k & 1][i], 32);
+                acc[i] = H.add(acc[i], v);
+            }
+        }
+        for (int i = 0; i < n; ++i) vals[i] = acc[i];
+        return true;
+    }
+};
+
 struct zkb_transcript {
     TranscriptImpl impl;
 };
@@ -153,7 +258,9 @@ struct zkb_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, log2world = 0;
-    uint32_t gather_log2 = 12;
+    uint32_t gather_log2 = 14;
+    ShmComm shm;
+    bool use_shm = false;
     RoundInterpolator interp[MAXPTS + 1];
     FixedMulBuilder fmb;
     // persistent round kernel
@@ -327,7 +434,7 @@ int32_t prep_finish(zkb_ctx* c, int grid, int npts, bool sharded, FinishArgs* f)
     ZK_TRY(ensure_partials(c, (size_t)grid * npts));
     f->partials = c->d_partials;
     f->ticket = c->d_ticket;
-    if (sharded) {
+    if (sharded && !c->use_shm) {
         f->result = c->d_res;
         f->result_wide = c->d_wide;
         f->flag = nullptr;
@@ -342,9 +449,10 @@ int32_t prep_finish(zkb_ctx* c, int grid, int npts, bool sharded, FinishArgs* f)
 }
 // Bring the `npts` sums of the launch prepared by prep_finish to the host.
 int32_t collect(zkb_ctx* c, int npts, bool sharded, const FinishArgs& f, Fe* out) {
-    if (!sharded) {
+    if (!sharded || c->use_shm) {
         ZK_TRY(wait_mailbox(c, f.seq));
         for (int p = 0; p < npts; ++p) out[p] = c->h_res[p];
+        if (sharded && !c->shm.allreduce(c->H, out, npts)) ZK_FAIL(c, ZKB_ERR_NCCL, "shared-memory exchange: a peer rank stopped answering");
         return ZKB_OK;
     }
     // C1: exact integer sum of the ranks' residues on zero-extended limbs, reduced mod p on the host
@@ -620,11 +728,14 @@ struct RoundDriver {
         return n >= 2 ? n : 0;
     }
     bool small_ok() const { return sp->cur_n >= 2 && sp->cur_n <= small_cap(); }
+    uint64_t gather_n() const { return 1ull << (c->gather_log2 < 1 ? 1 : c->gather_log2); }
     bool tail_ok() const {
         // products of >= 3 factors: the persistent kernel spills with the challenge table in shared memory,
         // so their large (throughput-bound) rounds stay one launch each
         if (sp->kind == KIND_PROD && sp->kD >= 3 && sp->cur_n > (1ull << 16)) return false;
-        return c->tail_log2 > 0 && !sp->sharded && sp->rest.empty() && sp->have_evals && sp->cur_n >= 2 &&
+        // sharded tables can use it when the ranks' hosts exchange the sums through shared memory
+        if (sp->sharded && (!c->use_shm || sp->cur_n <= gather_n())) return false;
+        return c->tail_log2 > 0 && sp->rest.empty() && sp->have_evals && sp->cur_n >= 2 &&
                sp->cur_n <= (1ull << (c->tail_log2 > 62 ? 62 : c->tail_log2)) && sc_occ(c, 2, sp->kind, sp->kD, sp->npts) > 0;
     }
     int32_t wait_dev(unsigned int want) {
@@ -715,7 +826,7 @@ struct RoundDriver {
         begin_mailbox();
         a.base_seq = base;
         a.timeout_clocks = 6000000000ll;  // ~3 s
-        stop_n = a.stop_n = small_cap();
+        stop_n = a.stop_n = sp->sharded ? gather_n() : small_cap();
         const uint64_t quads = sp->cur_n / 4 ? sp->cur_n / 4 : 1;
         const int grid = grid_for(c, quads, sc_occ(c, 2, sp->kind, sp->kD, sp->npts));
         ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
@@ -747,6 +858,7 @@ struct RoundDriver {
     }
     // Bind r; evals != NULL: the next round's s(0..d); NULL: this was the last variable, finals get the bound values.
     int32_t next(const Fe& r, Fe* evals, Fe* finals) {
+        if (!live && sp->sharded && sp->cur_n <= gather_n()) ZK_TRY(sp_gather(c, sp));  // C2, then local rounds
         if (!live && !sp->have_evals) return sp_bind_and_next(c, sp, r, evals, finals);
         const bool go_small = !live && small_ok();
         if (!live && !go_small && !tail_ok()) return sp_bind_and_next(c, sp, r, evals, finals);
@@ -773,9 +885,15 @@ struct RoundDriver {
             abort();
             ZK_FAIL(c, ZKB_ERR_BAD_ARG, "round driver: early stop inside the persistent kernel");
         }
-        evals[0] = c->mb->evals[0];
+        Fe got[MAXPTS];
+        for (int t = 0; t < sp->npts - 1; ++t) got[t] = c->mb->evals[t];
+        if (sp->sharded && !c->shm.allreduce(c->H, got, sp->npts - 1)) {
+            abort();
+            ZK_FAIL(c, ZKB_ERR_NCCL, "shared-memory exchange: a peer rank stopped answering");
+        }
+        evals[0] = got[0];
         evals[1] = c->H.sub(claim, evals[0]);
-        for (int t = 2; t < sp->npts; ++t) evals[t] = c->mb->evals[t - 1];
+        for (int t = 2; t < sp->npts; ++t) evals[t] = got[t - 1];
         for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
         return ZKB_OK;
     }
@@ -1239,6 +1357,7 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     if (c->d_partials) cudaFreeAsync(c->d_partials, c->stream);
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->shm.close_();
     prof_drain(c);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_ticket);
@@ -1308,6 +1427,7 @@ int32_t zkb_ctx_comm_init(zkb_ctx* c, int32_t rank, int32_t world, const uint8_t
     c->rank = rank;
     c->world = world;
     c->log2world = ilog2_u64((uint64_t)world);
+    c->use_shm = getenv("ZKB200_NO_SHM") == nullptr && c->shm.open(unique_id, rank, world);
     return ZKB_OK;
 }
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* c, uint32_t log2_entries) {
