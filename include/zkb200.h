@@ -199,6 +199,11 @@ int32_t zkb_circuit_free(zkb_ctx* ctx, zkb_circ c);
  * concatenated, input-side layer first. */
 int32_t zkb_circuit_evaluate(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, uint64_t n_inputs,
                              uint64_t* outputs_mont);
+/* Layer::get_add_mul_i (gkr_circuit.rs:39-104): the DENSE indicator table of one layer's gates of operation `op`
+ * (2^(3w+2) entries for 2^w > 1 gates, 8 for one gate).  For the reference's dense constructions
+ * (get_fbc_poly, gkr_protocol.rs:243-292) on small layers; zkb_gkr_prove never materialises it.
+ * n_gates must be a power of two and 3*log2(n_gates)+2 <= 30. */
+int32_t zkb_layer_add_mul_i(zkb_ctx* ctx, const uint8_t* ops, uint32_t n_gates, int32_t op, zkb_mle* out);
 /* gkr_protocol::prove (gkr_protocol.rs:31-91; the KZG input opening :92-118 is out of scope).
  * Outputs: w0[2] (output_poly); per layer (output side first) 2*(log2(2G)) rounds of 3 coefficient slots
  * with trimmed lengths; claimed[(L-1)][2] (claimed_evaluations); final_openings[2] = the input MLE at

@@ -301,6 +301,43 @@ def test_gkr_prove_matches_oracle(zkb, ctxs, oracle, fid, p):
         c.free()
 
 
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_dense_reference_construction_on_device(zkb, ctxs, fid, p):
+    """Layer::get_add_mul_i / get_fbc_poly as the reference builds them (dense), on the device:
+    the known answers of gkr_circuit.rs:205-256 and gkr_protocol.rs:423-452, and the dense prover
+    == the two-phase prover on small circuits (compat mode: 2 products x 2 factors)."""
+    ctx = ctxs(fid, zkb.MODE_COMPAT)
+    Op = zkb.Operation
+    G = zkb.gkr_protocol
+    # one Add gate -> add_i has its single one at index 1 (a=0,b=0,c=1); mul_i is all zero
+    c1 = zkb.gkr_circuit.Circuit(ctx, [[Op.Add]])
+    assert c1.layers[0].get_add_mul_i(Op.Add).evaluation == [0, 1, 0, 0, 0, 0, 0, 0]
+    assert c1.layers[0].get_add_mul_i(Op.Mul).evaluation == [0] * 8
+    c2 = zkb.gkr_circuit.Circuit(ctx, [[Op.Mul]])
+    assert c2.layers[0].get_add_mul_i(Op.Mul).evaluation == [0, 1, 0, 0, 0, 0, 0, 0]
+    # test_get_fbc_poly: 1 add gate, r = 5, w = [2, 12]
+    fbc = G.get_fbc_poly(5, c1.layers[0], [2, 12], [2, 12])
+    assert fbc.polys[0].evaluation[0].evaluation == [0, (p - 4) % p, 0, 0]
+    assert fbc.polys[0].evaluation[1].evaluation == [4, 14, 14, 24]
+    assert fbc.polys[1].evaluation[1].evaluation == [4, 24, 24, 144]
+    # 2-gate layer: widths (1, 2, 2): gate 1 sits at a=1, b=2, c=3 -> index 0b1_10_11 = 27
+    c3 = zkb.gkr_circuit.Circuit(ctx, [[Op.Add, Op.Mul], [Op.Add]])
+    tab = c3.layers[0].get_add_mul_i(Op.Mul).evaluation
+    assert len(tab) == 32 and [i for i, v in enumerate(tab) if v] == [27] and tab[27] == 1
+    rng = random.Random(6000 + fid)
+    for n_layers, out_gates in ((1, 1), (2, 1), (3, 1), (3, 2), (4, 1)):
+        gates, ops = tree_circuit(rng, n_layers, out_gates)
+        inputs = [rng.randrange(p) for _ in range(2 * gates[0])]
+        c = zkb.gkr_circuit.Circuit(ctx, [[Op(o) for o in layer] for layer in ops])
+        dense = G.prove_dense(c, inputs)
+        sparse = G.prove(c, inputs)
+        assert [[q.coefficients for q in layer] for layer in dense.proof_polynomials] == \
+               [[q.coefficients for q in layer] for layer in sparse.proof_polynomials], (n_layers, out_gates)
+        assert dense.claimed_evaluations == sparse.claimed_evaluations and dense.final_openings == sparse.final_openings
+        assert dense.challenges == sparse.challenges
+        c.free()
+
+
 def test_gkr_reference_test_circuit(zkb, ctxs):
     """gkr_protocol.rs:474-506 over BLS12-381 Fr + SURVEY App. C digest of the whole proof."""
     ctx = ctxs(2, 0)

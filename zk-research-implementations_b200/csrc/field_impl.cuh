@@ -124,6 +124,9 @@ void l_tensor(TabRef x, TabRef y, TabRef out, uint64_t na, uint64_t nb, int op, 
 void l_layer_eval(TabRef in, TabRef out, const uint8_t* ops, uint64_t n_gates, int grid, cudaStream_t s) {
     k_layer_eval<FT><<<grid, BLOCK, 0, s>>>(in, out, ops, n_gates);
 }
+void l_add_mul_i(const uint8_t* ops, uint32_t n_gates, int op, int w, TabRef out, cudaStream_t s) {
+    k_add_mul_i<FT><<<(n_gates + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(ops, n_gates, op, w, out);
+}
 void l_eq_split(const ChalList& r, int n, int n_hi, TabRef hi, TabRef lo, int grid, cudaStream_t s) {
     k_eq_split<FT><<<grid, BLOCK, 0, s>>>(r, n, n_hi, hi, lo);
 }
@@ -148,7 +151,7 @@ void h_modulus(Fe& p) {
 
 const FieldKernels TABLE = {
     FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
-    l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_eq_split,     l_gkr_phase1,
+    l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };
 }  // namespace

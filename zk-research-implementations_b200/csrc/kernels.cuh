@@ -1113,6 +1113,19 @@ __global__ void __launch_bounds__(BLOCK) k_layer_eval(TabRef in, TabRef out, con
     }
 }
 
+// Dense add_i / mul_i indicator (Layer::get_add_mul_i, gkr_circuit.rs:39-104) over index a||b||c with widths
+// (w, w+1, w+1), w = log2(G) (or (1,1,1) for a single gate): a one at (g, 2g, 2g+1) for every gate g of
+// the requested operation.  `out` must be zero-filled.  Only feasible for small layers (2^(3w+2) entries);
+// the prover itself uses the sparse two-phase form (K12-K14).
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_add_mul_i(const uint8_t* __restrict__ ops, uint32_t n_gates, int op, int w, TabRef out) {
+    const uint32_t g = blockIdx.x * BLOCK + threadIdx.x;
+    if (g >= n_gates || ops[g] != op) return;
+    const int wb = n_gates == 1 ? 1 : w + 1;
+    const uint64_t idx = ((((uint64_t)g << wb) | (uint64_t)(2 * g)) << wb) | (uint64_t)(2 * g + 1);
+    st_fe(out, idx, Field<F>::one());
+}
+
 // K11: eq(r, .) in split form.  r has n challenges (variable 0 = MSB).  The
 // table over the first n_hi variables goes to `hi` (2^n_hi entries), the one
 // over the remaining n - n_hi to `lo`; eq(r, x) = hi[x >> n_lo] * lo[x & mask].

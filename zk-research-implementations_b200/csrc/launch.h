@@ -31,6 +31,7 @@ struct FieldKernels {
     void (*axpby)(TabRef x, TabRef y, TabRef out, uint64_t n, const Fe& alpha, const Fe& beta, int grid, cudaStream_t s);
     void (*tensor)(TabRef x, TabRef y, TabRef out, uint64_t na, uint64_t nb, int op, int grid, cudaStream_t s);
     void (*layer_eval)(TabRef in, TabRef out, const uint8_t* ops, uint64_t n_gates, int grid, cudaStream_t s);
+    void (*add_mul_i)(const uint8_t* ops, uint32_t n_gates, int op, int w, TabRef out, cudaStream_t s);
     void (*eq_split)(const ChalList& r, int n, int n_hi, TabRef hi, TabRef lo, int grid, cudaStream_t s);
     void (*gkr_phase1)(const GkrP1Args& a, int grid, cudaStream_t s);
     void (*gkr_phase2)(const GkrP2Args& a, int grid, cudaStream_t s);

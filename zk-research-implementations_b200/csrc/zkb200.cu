@@ -1953,6 +1953,25 @@ int32_t zkb_circuit_evaluate(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uin
     }
     return ZKB_OK;
 }
+int32_t zkb_layer_add_mul_i(zkb_ctx* c, const uint8_t* ops, uint32_t n_gates, int32_t op, zkb_mle* out) {
+    if (!c || !ops || !out || (op != ZKB_OP_ADD && op != ZKB_OP_MUL)) return ZKB_ERR_BAD_ARG;
+    if (!is_pow2(n_gates)) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "get_add_mul_i: the gate count must be a power of two");
+    const int w = ilog2_u64(n_gates);
+    const int bits = n_gates == 1 ? 3 : 3 * w + 2;
+    if (bits > 30) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "get_add_mul_i: dense table too large; zkb_gkr_prove uses the sparse form");
+    Table t;
+    ZK_TRY(alloc_table(c, 1ull << bits, &t));
+    ZK_CUDA(c, cudaMemsetAsync(t.base, 0, (size_t)t.n * 32, c->stream));
+    uint8_t* d_ops = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&d_ops, n_gates, c->stream));
+    ZK_CUDA(c, cudaMemcpyAsync(d_ops, ops, n_gates, cudaMemcpyHostToDevice, c->stream));
+    c->K->add_mul_i(d_ops, n_gates, op, w, t.ref(), c->stream);
+    ZK_TRY(check_launch(c, "k_add_mul_i"));
+    ZK_CUDA(c, cudaFreeAsync(d_ops, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));  // `ops` is the caller's pageable memory
+    *out = put_mle(c, t);
+    return ZKB_OK;
+}
 int32_t zkb_gkr_prove(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t n_inputs, uint64_t w0[8], uint64_t* coeffs,
                       int32_t* lens, uint64_t* challenges, uint64_t* claimed, uint64_t final_openings[8], uint32_t* n_rounds) {
     if (!c || !inputs || !w0 || !coeffs || !lens || !final_openings) return ZKB_ERR_BAD_ARG;

@@ -117,6 +117,7 @@ def lib() -> C.CDLL:
         "zkb_circuit_create": (i32, [vp, u32, u32p, u8p, u64p]),
         "zkb_circuit_free": (i32, [vp, u64]),
         "zkb_circuit_evaluate": (i32, [vp, u64, vp, u64, vp]),
+        "zkb_layer_add_mul_i": (i32, [vp, u8p, u32, i32, u64p]),
         "zkb_gkr_prove": (i32, [vp, u64, vp, u64, u64p, u64p, i32p, u64p, u64p, u64p, u32p]),
         "zkb_gkr_verify": (i32, [vp, u64, vp, u64, u64p, u64p, i32p, u64p, u64p, i32p]),
         "zkb_gkr_total_rounds": (u32, [u32, u32p]),

@@ -9,7 +9,7 @@ import numpy as np
 
 from . import engine as E
 from .engine import Context, _ck, lib
-from .multilinear_polynomial import Operation
+from .multilinear_polynomial import MultilinearPoly, Operation
 
 
 @dataclass
@@ -21,11 +21,18 @@ class Gate:  # :4-23
 
 
 class Layer:  # :25-104
-    def __init__(self, gates: List[Gate]):
+    def __init__(self, gates: List[Gate], ctx: Context = None):
         self.gates = gates
+        self.ctx = ctx
 
     def get_layer_poly(self) -> List[int]:  # :35-37
         return [g.output for g in self.gates]
+
+    def get_add_mul_i(self, op: Operation) -> MultilinearPoly:  # :39-52 (dense; small layers only)
+        ops = np.array([int(g.op) for g in self.gates], dtype=np.uint8)
+        h = C.c_uint64()
+        _ck(self.ctx, lib().zkb_layer_add_mul_i(self.ctx.handle, ops.ctypes.data_as(C.POINTER(C.c_uint8)), len(ops), int(op), C.byref(h)))
+        return MultilinearPoly(self.ctx, _handle=h.value)
 
 
 class Circuit:
@@ -33,7 +40,7 @@ class Circuit:
 
     def __init__(self, ctx: Context, structure: Sequence[Sequence[Operation]]):
         self.ctx = ctx
-        self.layers = [Layer([Gate(0, 0, 0, Operation(op)) for op in ops]) for ops in structure]
+        self.layers = [Layer([Gate(0, 0, 0, Operation(op)) for op in ops], ctx) for ops in structure]
         self.gates = np.array([len(ops) for ops in structure], dtype=np.uint32)
         self.ops = np.array([int(op) for ops in structure for op in ops], dtype=np.uint8)
         h = C.c_uint64()

@@ -14,7 +14,8 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from .engine import _ck, _p, lib
-from .gkr_circuit import Circuit
+from .gkr_circuit import Circuit, Layer
+from .multilinear_polynomial import MultilinearPoly, Operation, ProductPoly, SumPoly
 from .univariate_polynomial import UnivariatePoly
 
 i32p = C.POINTER(C.c_int32)
@@ -28,6 +29,73 @@ class GkrProof:  # :23-29 (input_proof replaced by final_openings)
     claimed_evaluations: List[Tuple[int, int]]
     final_openings: Tuple[int, int]
     challenges: List[List[int]]
+
+
+def get_fbc_poly(random_challenge: int, layer: Layer, w_b: Sequence[int], w_c: Sequence[int]) -> SumPoly:  # :243-263
+    """The reference's DENSE construction of the first layer's composed polynomial, on the device."""
+    ctx = layer.ctx
+    add_i = layer.get_add_mul_i(Operation.Add).partial_evaluate(0, random_challenge)
+    mul_i = layer.get_add_mul_i(Operation.Mul).partial_evaluate(0, random_challenge)
+    wb, wc = MultilinearPoly(ctx, w_b), MultilinearPoly(ctx, w_c)
+    summed = MultilinearPoly.tensor_add_mul_polynomials(wb, wc, Operation.Add)
+    multiplied = MultilinearPoly.tensor_add_mul_polynomials(wb, wc, Operation.Mul)
+    return SumPoly(ctx, [ProductPoly.from_polys(ctx, [add_i, summed]), ProductPoly.from_polys(ctx, [mul_i, multiplied])])
+
+
+def get_folded_fbc_poly(layer: Layer, w_b, w_c, r_b, r_c, alpha: int, beta: int) -> SumPoly:  # :265-292
+    ctx = layer.ctx
+    add_i, mul_i = layer.get_add_mul_i(Operation.Add), layer.get_add_mul_i(Operation.Mul)
+    s_add = add_i.multi_partial_evaluate(r_b).scale(alpha) + add_i.multi_partial_evaluate(r_c).scale(beta)
+    s_mul = mul_i.multi_partial_evaluate(r_b).scale(alpha) + mul_i.multi_partial_evaluate(r_c).scale(beta)
+    wb, wc = MultilinearPoly(ctx, w_b), MultilinearPoly(ctx, w_c)
+    summed = MultilinearPoly.tensor_add_mul_polynomials(wb, wc, Operation.Add)
+    multiplied = MultilinearPoly.tensor_add_mul_polynomials(wb, wc, Operation.Mul)
+    return SumPoly(ctx, [ProductPoly.from_polys(ctx, [s_add, summed]), ProductPoly.from_polys(ctx, [s_mul, multiplied])])
+
+
+def prove_dense(circuit: Circuit, inputs: Sequence[int]) -> "GkrProof":
+    """gkr_protocol::prove exactly as the reference builds it (:31-91): dense add_i/mul_i tables, tensor tables and
+    the composed sumcheck of sum_check_protocol::gkr_prove in `compat` reduce semantics -- every table on the
+    device.  Only for small circuits (2^(3g+2) entries per layer); used to check the two-phase prover."""
+    from . import sum_check_protocol as S
+    from .fiat_shamir import Transcript, fq_vec_to_bytes
+
+    ctx = circuit.ctx
+    p = ctx.p
+    evals = circuit.evaluate(inputs)
+    w0 = list(evals[-1])
+    if len(w0) == 1:
+        w0.append(0)
+    t = Transcript(ctx.field)
+    t.append(fq_vec_to_bytes(w0))  # initiate_protocol :229-241
+    r0 = t.get_random_challenge()
+    claimed = MultilinearPoly(ctx, w0).evaluate([r0])
+    t.append(fq_vec_to_bytes([claimed]))
+    L = len(circuit.layers)
+    polys, claimed_evals, chals = [], [], []
+    rb: List[int] = []
+    rc: List[int] = []
+    alpha = beta = o1 = o2 = 0
+    inputs = [int(x) % p for x in inputs]
+    for idx, layer in enumerate(reversed(circuit.layers)):
+        w_i = inputs if idx == L - 1 else list(reversed(evals))[idx + 1]
+        fbc = get_fbc_poly(r0, layer, w_i, w_i) if idx == 0 else get_folded_fbc_poly(layer, w_i, w_i, rb, rc, alpha, beta)
+        sc = S.gkr_prove(claimed, fbc, t)
+        polys.append(sc.proof_polynomials)
+        chals.append(sc.random_challenges)
+        mid = len(sc.random_challenges) // 2
+        rb, rc = sc.random_challenges[:mid], sc.random_challenges[mid:]
+        nxt = MultilinearPoly(ctx, w_i)
+        o1, o2 = nxt.evaluate(rb), nxt.evaluate(rc)
+        if idx < L - 1:
+            t.append(fq_vec_to_bytes([o1]))
+            alpha = t.get_random_challenge()
+            t.append(fq_vec_to_bytes([o2]))
+            beta = t.get_random_challenge()
+            claimed = (alpha * o1 + beta * o2) % p
+            claimed_evals.append((o1, o2))
+        fbc.free()
+    return GkrProof(w0, polys, claimed_evals, (o1, o2), chals)
 
 
 def _rounds_per_layer(circuit: Circuit) -> List[int]:
