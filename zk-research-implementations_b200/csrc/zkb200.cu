@@ -709,6 +709,8 @@ struct RoundDriver {
     unsigned int sent = 0;   // challenges delivered through the mailbox so far
     unsigned int pubs = 0;   // messages consumed from it so far
     uint64_t stop_n = 0;     // k_sc_tail leaves once the tables have <= stop_n entries
+    Fe poly[MAXPTS];         // coefficients of the current round polynomial, if the caller interpolated it already
+    int poly_len = -1;
 
     RoundDriver(zkb_ctx* ctx, SumPolyState* s) : c(ctx), sp(s) {}
     ~RoundDriver() { abort(); }
@@ -862,13 +864,15 @@ struct RoundDriver {
         if (!live && !sp->have_evals) return sp_bind_and_next(c, sp, r, evals, finals);
         const bool go_small = !live && small_ok();
         if (!live && !go_small && !tail_ok()) return sp_bind_and_next(c, sp, r, evals, finals);
-        const RoundInterpolator& ip = c->interp[sp->npts];
-        Fe co[MAXPTS];
-        const int colen = ip.interpolate(sp->last_evals, co);
-        const Fe claim = uni_evaluate(c->H, co, colen, r);
-        if (live) send(r);
-        else if (go_small) ZK_TRY(launch_small(false, r));
-        else ZK_TRY(launch_tail(r));
+        const bool was_live = live;
+        if (was_live) send(r);  // first, so the device works while the host finishes the claim chain
+        if (poly_len < 0) poly_len = c->interp[sp->npts].interpolate(sp->last_evals, poly);
+        const Fe claim = uni_evaluate(c->H, poly, poly_len, r);
+        poly_len = -1;
+        if (!was_live) {
+            if (go_small) ZK_TRY(launch_small(false, r));
+            else ZK_TRY(launch_tail(r));
+        }
         ZK_TRY(wait_dev(base + (++pubs)));
         sp->cur_n /= 2;
         if (sp->cur_n == 1) {
@@ -917,6 +921,8 @@ int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, ui
             for (int i = 0; i < len; ++i) co[i] = evals[i];
         } else {
             len = ip.interpolate(evals, co);
+            for (int i = 0; i < len; ++i) drv.poly[i] = co[i];
+            drv.poly_len = len;
         }
         tr->append_elements(co, (size_t)len);
         if (lens) lens[k] = len;
@@ -1124,6 +1130,8 @@ int32_t xyz_phase(zkb_ctx* c, CircuitState* cs, const Table& X, const Table& Y, 
     ZK_TRY(drv.first(evals));
     for (int k = 0; k < nb; ++k) {
         int len = ip.interpolate(evals, co);
+        for (int i = 0; i < len; ++i) drv.poly[i] = co[i];
+        drv.poly_len = len;
         tr->append_elements(co, (size_t)len);
         lens[k] = len;
         for (int i = 0; i < 3; ++i) fe_to_u64x4(i < len ? co[i] : c->H.zero(), coeffs + ((size_t)k * 3 + i) * 4);
