@@ -49,6 +49,14 @@ static void run(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, siz
                 r = Field<F>::reduce_wide(w);
                 break;
             }
+            case 10: r = Field<F>::reduce_once(Field<F>::sub_lazy(x, y)); break;  // x - y + p, then canonical
+            case 11: {  // (2y - x + p) * (2y - x + p) lazily, reduced once (only where 3p < 2^256)
+                Wide w = Field<F>::wide_zero();
+                Fe v = F::SLACK3P ? Field<F>::line2_lazy(x, y) : Field<F>::sub(Field<F>::dbl(y), x);
+                Field<F>::mac_wide(w, v, v);
+                r = Field<F>::reduce_wide(w);
+                break;
+            }
             default: r = Field<F>::zero();
         }
         memcpy(out + 8 * i, r.l, 32);

@@ -55,5 +55,7 @@ def test_limb_arithmetic(shim, fid):
     n = len(a)
     assert run(shim, fid, 8, a, b) == [sum(a[(i + k) % n] * b[(i + k) % n] for k in range(4)) * rinv % p for i in range(n)]
     assert run(shim, fid, 9, a[:200], b[:200]) == [5000 * x * y * rinv % p for x, y in zip(a[:200], b[:200])]
+    assert run(shim, fid, 10, a, b) == [(x - y) % p for x, y in zip(a, b)]      # unreduced difference
+    assert run(shim, fid, 11, a, b) == [(2 * y - x) ** 2 * rinv % p for x, y in zip(a, b)]  # unreduced line value at t = 2
     # fold(a, b, r=to_mont(b)) in Montgomery arithmetic == a + b*(b-a) on raw residues
     assert run(shim, fid, 6, a, b) == [(x + y * (y - x)) % p for x, y in zip(a, b)]

@@ -79,6 +79,7 @@ ZK_HD uint64_t pack64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | 
 // INV = -p^{-1} mod 2^32.  All as 8 x u32, little-endian.
 struct Bn254Fr {
     static constexpr int ID = 0;
+    static constexpr bool SLACK3P = true;  // 3p < 2^256: values up to 3p fit the 8 limbs (unreduced operands)
     static constexpr uint32_t INV = 0xefffffffu;
     ZK_HD static constexpr uint32_t P(int i) {
         constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
@@ -95,6 +96,7 @@ struct Bn254Fr {
 };
 struct Bn254Fq {
     static constexpr int ID = 1;
+    static constexpr bool SLACK3P = true;
     static constexpr uint32_t INV = 0xe4866389u;
     ZK_HD static constexpr uint32_t P(int i) {
         constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
@@ -111,6 +113,7 @@ struct Bn254Fq {
 };
 struct Bls12381Fr {
     static constexpr int ID = 2;
+    static constexpr bool SLACK3P = false;  // 255-bit modulus: only 2p < 2^256
     static constexpr uint32_t INV = 0xffffffffu;
     ZK_HD static constexpr uint32_t P(int i) {
         constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -349,26 +352,25 @@ struct Field {
     ZK_HD static Fe mul_fixed(const Fe& x, const FixedMul& T) {
         // S = sum_i x_i * T_i < 2^289 in two interleaved accumulators:
         // ev[k] = limbs (2k, 2k+1), od[k] = limbs (2k+1, 2k+2); word 4 collects carries.
-        uint64_t ev[5], od[5];
+        uint64_t ev[4], od[4];
+        uint32_t ce = 0, co = 0;  // carries out of word 3 of either accumulator (limb 8 resp. limb 9), at most 7 each
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             ev[k] = mul_wide(T.t[0][2 * k], x.l[0]);
             od[k] = mul_wide(T.t[0][2 * k + 1], x.l[0]);
         }
-        ev[4] = 0;
-        od[4] = 0;
 #pragma unroll
         for (int i = 1; i < 8; ++i) {
             ev[0] = madw_cc(T.t[i][0], x.l[i], ev[0]);
             ev[1] = madwc_cc(T.t[i][2], x.l[i], ev[1]);
             ev[2] = madwc_cc(T.t[i][4], x.l[i], ev[2]);
             ev[3] = madwc_cc(T.t[i][6], x.l[i], ev[3]);
-            ev[4] = addc64(ev[4], 0ull);
+            ce = addc(ce, 0u);
             od[0] = madw_cc(T.t[i][1], x.l[i], od[0]);
             od[1] = madwc_cc(T.t[i][3], x.l[i], od[1]);
             od[2] = madwc_cc(T.t[i][5], x.l[i], od[2]);
             od[3] = madwc_cc(T.t[i][7], x.l[i], od[3]);
-            od[4] = addc64(od[4], 0ull);
+            co = addc(co, 0u);
         }
         // merge to 10 x 32-bit limbs: s = ev + (od << 32)
         uint32_t s[10];
@@ -380,8 +382,8 @@ struct Field {
         s[5] = addc_cc(hi32(ev[2]), lo32(od[2]));
         s[6] = addc_cc(lo32(ev[3]), hi32(od[2]));
         s[7] = addc_cc(hi32(ev[3]), lo32(od[3]));
-        s[8] = addc_cc(lo32(ev[4]), hi32(od[3]));
-        s[9] = addc(hi32(ev[4]), lo32(od[4]));
+        s[8] = addc_cc(ce, hi32(od[3]));
+        s[9] = addc(co, 0u);
         // two reduction rows: s = (s + m*p) / 2^32
 #pragma unroll
         for (int row = 0; row < 2; ++row) {
@@ -412,8 +414,38 @@ struct Field {
         for (int j = 0; j < 8; ++j) r.l[j] = s[j];
         return reduce_once(r);  // s < 2p, s[8] == 0
     }
+    // b - a + p in (0, 2p): an UNREDUCED difference (no compare / select), fine as the x of mul_fixed and as an
+    // operand of mac_wide, which only need x < 2^256
+    ZK_HD static Fe sub_lazy(const Fe& b, const Fe& a) {
+        Fe d;
+        d.l[0] = sub_cc(b.l[0], a.l[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) d.l[i] = subc_cc(b.l[i], a.l[i]);
+        d.l[0] = add_cc(d.l[0], F::P(0));  // the borrow out of limb 7 cancels against the carry out of this chain
+#pragma unroll
+        for (int i = 1; i < 7; ++i) d.l[i] = addc_cc(d.l[i], F::P(i));
+        d.l[7] = addc(d.l[7], F::P(7));
+        return d;
+    }
+    // 2*hi - lo + p in (0, 3p): the unreduced value of the pair's line at t = 2 (needs 3p < 2^256)
+    ZK_HD static Fe line2_lazy(const Fe& lo, const Fe& hi) {
+        Fe d;
+        d.l[0] = add_cc(hi.l[0], hi.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) d.l[i] = addc_cc(hi.l[i], hi.l[i]);
+        d.l[7] = addc(hi.l[7], hi.l[7]);
+        d.l[0] = sub_cc(d.l[0], lo.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) d.l[i] = subc_cc(d.l[i], lo.l[i]);
+        d.l[7] = subc(d.l[7], lo.l[7]);
+        d.l[0] = add_cc(d.l[0], F::P(0));
+#pragma unroll
+        for (int i = 1; i < 7; ++i) d.l[i] = addc_cc(d.l[i], F::P(i));
+        d.l[7] = addc(d.l[7], F::P(7));
+        return d;
+    }
     // a + r*(b - a) with the fixed-multiplicand product
-    ZK_HD static Fe fold_fixed(const Fe& a, const Fe& b, const FixedMul& T) { return add(a, mul_fixed(sub(b, a), T)); }
+    ZK_HD static Fe fold_fixed(const Fe& a, const Fe& b, const FixedMul& T) { return add(a, mul_fixed(sub_lazy(b, a), T)); }
 
     // ---- lazy sums of products ---------------------------------------------
     ZK_HD static Wide wide_zero() {

@@ -266,6 +266,12 @@ struct RoundAcc {
             for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, hi[f]);
             mac(S::of(1), m, hi[D - 1]);
         }
+        if (NPTS == 3 && D == 2 && F::SLACK3P) {
+            // the only extra point is t = 2 and both factors go straight into the lazy product: take the
+            // unreduced 2*hi - lo + p (< 3p < 2^256) and skip two modular subtractions and two additions
+            mac(S::of(2), Fd::line2_lazy(lo[0], hi[0]), Fd::line2_lazy(lo[1], hi[1]));
+            return;
+        }
         Fe cur[D], dl[D];
 #pragma unroll
         for (int f = 0; f < D; ++f) {
@@ -341,8 +347,14 @@ struct XyzAcc {
             mac(S::of(1), hi[0], hi[1]);
             z[S::of(1)] = Fd::add(z[S::of(1)], hi[2]);
         }
-        Fe x2 = Fd::sub(Fd::dbl(hi[0]), lo[0]);
-        Fe y2 = Fd::sub(Fd::dbl(hi[1]), lo[1]);
+        Fe x2, y2;
+        if (F::SLACK3P) {
+            x2 = Fd::line2_lazy(lo[0], hi[0]);
+            y2 = Fd::line2_lazy(lo[1], hi[1]);
+        } else {
+            x2 = Fd::sub(Fd::dbl(hi[0]), lo[0]);
+            y2 = Fd::sub(Fd::dbl(hi[1]), lo[1]);
+        }
         Fe z2 = Fd::sub(Fd::dbl(hi[2]), lo[2]);
         mac(S::of(2), x2, y2);
         z[S::of(2)] = Fd::add(z[S::of(2)], z2);
