@@ -42,7 +42,7 @@ int l_sc_tail(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream
     void* params[1] = {const_cast<TailArgs*>(&a)};
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        constexpr int SM = FoldSmem<K, DD, NP>::bytes; \
+        constexpr int SM = TailSmem<K, DD, NP>::bytes; \
         static bool once = (cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
         (void)once; \
         return (int)cudaLaunchCooperativeKernel((const void*)k_sc_tail<FT, K, DD, NP>, dim3(grid), dim3(BLOCK), params, SM, s); \
@@ -70,7 +70,7 @@ int l_sc_occupancy(int fused, int kind, int D, int npts) {
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         if (fused == 2) { \
-            constexpr int SM = FoldSmem<K, DD, NP>::bytes; \
+            constexpr int SM = TailSmem<K, DD, NP>::bytes; \
             cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM); \
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sc_tail<FT, K, DD, NP>, BLOCK, SM); \
         } \

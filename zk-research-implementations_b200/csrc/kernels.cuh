@@ -392,21 +392,21 @@ constexpr int FOLD_BUFS = 2;   // k_sc_fold_eval: 2 buffers x 8 vectors (the qua
 constexpr int STAGE_BYTES = 2 * 8 * BLOCK * 16;  // 64 KiB per CTA of staging for both kernels
 constexpr int FOLD_SMEM_BYTES = STAGE_BYTES + (MAXPTS - 1) * ACC_VECS * BLOCK * 16;  // + parked accumulators
 
-// K7: evaluations of the first round (no challenge to bind yet): all NPTS points.
+// K7: evaluations of the first round (no challenge to bind yet): all NPTS points.  Device function shared by
+// the stand-alone kernel and by the persistent kernel (which can start with this pass).
 template <class F, int KIND, int D, int NPTS>
-__global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ ScArgs a) {
-    extern __shared__ uint4 stage[];
-    const uint64_t half = a.n_out >> 1;
+__device__ __forceinline__ void eval_pass(const TabRef* __restrict__ in, int n_products, uint64_t n, uint4* stage, Fe* out) {
+    const uint64_t half = n >> 1;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
     const uint64_t j0 = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
-    const int T = KIND == KIND_XYZ ? 3 : a.n_products * D;
+    const int T = KIND == KIND_XYZ ? 3 : n_products * D;
     uint4* my = stage + threadIdx.x;
     // flattened prefetch sequence q = iteration * T + table
     uint64_t pj = j0;
     int pt = 0, pbuf = 0;
     auto issue = [&]() {
         if (pj < half) {
-            const TabRef& t = a.in[pt];
+            const TabRef& t = in[pt];
             uint4* dst = my + (size_t)pbuf * 4 * BLOCK;
             cp_async16(dst, t.base + pj);
             cp_async16(dst + BLOCK, t.base + t.stride + pj);
@@ -431,7 +431,6 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ Sc
         cbuf = (cbuf + 1) & (EVAL_BUFS - 1);
         issue();
     };
-    Fe out[NPTS];
     if (KIND == KIND_XYZ) {
         XyzAcc<F, false> acc;
         acc.init();
@@ -446,7 +445,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ Sc
         RoundAcc<F, D, NPTS, false> acc;
         acc.init();
         for (uint64_t j = j0; j < half; j += step) {
-            for (int p = 0; p < a.n_products; ++p) {
+            for (int p = 0; p < n_products; ++p) {
                 Fe lo[D], hi[D];
 #pragma unroll
                 for (int f = 0; f < D; ++f) take(lo[f], hi[f]);
@@ -456,6 +455,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ Sc
         acc.finish(out);
     }
     cp_async_wait<0>();
+}
+template <class F, int KIND, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK, 2) k_sc_eval(const __grid_constant__ ScArgs a) {
+    extern __shared__ uint4 stage[];
+    Fe out[NPTS];
+    eval_pass<F, KIND, D, NPTS>(a.in, a.n_products, a.n_out, stage, out);
     finish_round<F, NPTS>(out, a.fin);
 }
 
@@ -478,6 +483,10 @@ struct Staged {
 template <int KIND, int D, int NPTS>
 struct FoldSmem {
     static constexpr int bytes = (Staged<KIND, D>::value ? STAGE_BYTES : 0) + (NPTS - 1) * ACC_VECS * BLOCK * 16;
+};
+template <int KIND, int D, int NPTS>
+struct TailSmem {  // the persistent kernel may start with the evaluation pass, which stages through 64 KiB
+    static constexpr int bytes = FoldSmem<KIND, D, NPTS>::bytes > STAGE_BYTES ? FoldSmem<KIND, D, NPTS>::bytes : STAGE_BYTES;
 };
 template <class F, int KIND, int D, int NPTS>
 __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
@@ -627,6 +636,7 @@ struct TailArgs {
     unsigned int base_seq;
     long long timeout_clocks;
     uint64_t stop_n;           // leave after publishing the round whose tables have <= stop_n entries (0: run to the end)
+    int first_eval;            // 1: start with round 0 (all NPTS sums of the unbound tables) and take rt0 from the mailbox
 };
 
 template <class F, int KIND, int D, int NPTS>
@@ -636,7 +646,25 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
     __shared__ FixedMul s_rt;
     __shared__ unsigned int s_abort;
     uint64_t n_in = a.n_in;
-    for (unsigned int it = 0;; ++it) {
+    if (threadIdx.x == 0) s_abort = 0;
+    if (a.first_eval) {  // round 0 inside the launch: message 1 = s(0..d) of the unbound tables
+        const uint64_t ctas = ((n_in >> 1) + BLOCK - 1) / BLOCK;
+        const unsigned int n_active = ctas < 1 ? 1u : (ctas < gridDim.x ? (unsigned int)ctas : gridDim.x);
+        if (blockIdx.x < n_active) {
+            Fe out[NPTS];
+            eval_pass<F, KIND, D, NPTS>(a.in, a.n_products, n_in, stage, out);
+            FinishArgs fin;
+            fin.partials = a.partials;
+            fin.ticket = a.ticket;
+            fin.result = a.mb->evals;
+            fin.result_wide = nullptr;
+            fin.flag = &a.mb->dev_seq;
+            fin.seq = a.base_seq + 1;
+            finish_round<F, NPTS>(out, fin, n_active);
+        }
+    }
+    const unsigned int it0 = a.first_eval ? 1u : 0u;
+    for (unsigned int it = it0;; ++it) {
         // ---- the challenge table of this round -> shared memory
         if (it == 0) {
             for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = (&a.rt0.t[0][0])[w];
@@ -693,7 +721,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
         }
         __syncthreads();
         const uint64_t n_out = n_in >> 1;
-        const TabRef* src = it == 0 ? a.in : a.out;
+        const TabRef* src = it == it0 ? a.in : a.out;
         if (n_out == 1) {  // last bind: publish the bound values and leave
             if (blockIdx.x == 0) {
                 const int t = threadIdx.x;

@@ -809,7 +809,7 @@ struct RoundDriver {
         if (sp->state == 0) sp->state = 1;
         return ZKB_OK;
     }
-    int32_t launch_tail(const Fe& r) {
+    int32_t launch_tail(const Fe& r, bool first_eval = false) {
         if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
         TailArgs a;
         std::memset(&a, 0, sizeof a);
@@ -820,7 +820,8 @@ struct RoundDriver {
         a.n_tables = (int)sp->sel.size();
         a.n_products = sp->kP;
         a.n_in = sp->cur_n;
-        c->fmb.make(c->H, r, &a.rt0);
+        if (!first_eval) c->fmb.make(c->H, r, &a.rt0);
+        a.first_eval = first_eval ? 1 : 0;
         for (int i = 0; i < 8; ++i) a.cpow[i] = c->fmb.c[i];
         a.mb = c->mb;
         a.relay = c->d_relay;
@@ -829,12 +830,13 @@ struct RoundDriver {
         a.base_seq = base;
         a.timeout_clocks = 6000000000ll;  // ~3 s
         stop_n = a.stop_n = sp->sharded ? gather_n() : small_cap();
-        const uint64_t quads = sp->cur_n / 4 ? sp->cur_n / 4 : 1;
+        const uint64_t quads = first_eval ? sp->cur_n / 2 : (sp->cur_n / 4 ? sp->cur_n / 4 : 1);
         const int grid = grid_for(c, quads, sc_occ(c, 2, sp->kind, sp->kD, sp->npts));
         ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
         a.partials = c->d_partials;
         ZK_CUDA(c, cudaMemsetAsync(&c->d_relay->seq, 0, 2 * sizeof(unsigned int), c->stream));
-        prof_begin(c, ZKB_K_SC_TAIL, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)));
+        prof_begin(c, ZKB_K_SC_TAIL, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)) +
+                                         (first_eval ? 32.0 * (double)sp->sel.size() * (double)sp->cur_n : 0.0));
         int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, a, grid, c->stream);
         if (e < 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_tail: shape not instantiated");
         if (e != 0) {
@@ -853,6 +855,23 @@ struct RoundDriver {
             ZK_TRY(launch_small(true, c->H.zero()));
             ZK_TRY(wait_dev(base + (++pubs)));
             for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i] = c->mb->evals[i];
+            sp->have_evals = true;
+            return ZKB_OK;
+        }
+        // round 0 inside the persistent kernel: one launch for the whole sumcheck
+        sp->have_evals = true;  // (tail_ok asks for it; set for real below)
+        // (only for latency-bound sizes: for large tables the stand-alone k_sc_eval measured 3% faster)
+        const bool tail_first = sp->cur_n >= 4 && sp->cur_n <= (1ull << 18) && tail_ok();
+        sp->have_evals = false;
+        if (tail_first) {
+            ZK_TRY(launch_tail(c->H.zero(), true));
+            ZK_TRY(wait_dev(base + (++pubs)));
+            for (int i = 0; i < sp->npts; ++i) evals[i] = c->mb->evals[i];
+            if (sp->sharded && !c->shm.allreduce(c->H, evals, sp->npts)) {
+                abort();
+                ZK_FAIL(c, ZKB_ERR_NCCL, "shared-memory exchange: a peer rank stopped answering");
+            }
+            for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
             sp->have_evals = true;
             return ZKB_OK;
         }
