@@ -218,6 +218,10 @@ def main():
     import numpy as np
     import torch
 
+    if not os.path.exists(os.path.join(ROOT, PKG, "libzkb200.so")) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        import __graft_entry__
+
+        __graft_entry__.build()  # fresh checkout: the library is a build artefact
     z = importlib.import_module(PKG)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -25,7 +25,13 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def zkb():
-    """The product package (hyphenated directory name -> importlib)."""
+    """The product package (hyphenated directory name -> importlib).  The shared library is a build artefact
+    (git-ignored): compile it first if this is a fresh checkout.  There is still no fallback: if the build
+    fails the tests fail."""
+    if not os.path.exists(os.path.join(ROOT, PKG, "libzkb200.so")):
+        import __graft_entry__
+
+        __graft_entry__.build()
     return importlib.import_module(PKG)
 
 
