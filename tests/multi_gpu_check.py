@@ -58,6 +58,16 @@ def main():
         ev = sh[0].evaluate(rs) == so[0].evaluate(rs) == O.mle_evaluate(fid, full[0], rs)
         pl, pl1 = S.prove(sh[0], absorb_table=False), S.prove(so[0], absorb_table=False)
         same_p = (pl.claimed_sum, pl.proof_polynomials) == (pl1.claimed_sum, pl1.proof_polynomials)
+        # repeat the sharded proof: the shared-memory exchange and the mailbox must give the same bytes every time
+        rep_ok = True
+        rawp = S.RawGkrProver(sp)
+        rawp.prove(T(fid))
+        want = rawp.coeffs.copy()
+        for _ in range(int(os.environ.get("ZKB_REPEAT", "20"))):
+            rawp.coeffs[:] = 0
+            rawp.prove(T(fid))
+            rep_ok &= bool(np.array_equal(rawp.coeffs, want))
+        same &= rep_ok
         line = f"rank {rank}: n={n} P={P} D={D} thr={thr}: sharded==single {same}, ==oracle {same_o}, generate {same_g}, evaluate {ev}, plain {same_p}"
         print(line, flush=True)
         ok &= same and same_o and same_g and ev and same_p

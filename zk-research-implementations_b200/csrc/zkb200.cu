@@ -250,6 +250,10 @@ struct zkb_ctx {
     // staging for uploads / downloads
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    // double-buffered upload: H2D copies on their own stream overlap the layout kernels
+    cudaStream_t copy_stream = nullptr;
+    void* up_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_entry = nullptr;
     // handles
     uint64_t next_handle = 1;
     std::unordered_map<uint64_t, Table> mles;
@@ -954,11 +958,10 @@ int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, ui
 }
 
 // ------------------------------------------------------------------ MLE helpers
+constexpr uint64_t UP_CHUNK = 1ull << 19;  // elements per upload chunk (16 MiB)
 int32_t upload_aos(zkb_ctx* c, const uint64_t* aos, uint64_t n_src, uint64_t first, uint64_t stride, uint64_t n_dst,
                    int conv, Table* out) {
     ZK_TRY(alloc_table(c, n_dst, out));
-    // chunked: stage up to 2^21 source elements (64 MiB) at a time
-    const uint64_t chunk_dst = stride > 1 ? n_dst : (n_dst < (1ull << 21) ? n_dst : (1ull << 21));
     (void)n_src;
     if (stride > 1) {
         // strided shard: copy only this rank's elements with a 2D copy (32-byte rows)
@@ -970,15 +973,40 @@ int32_t upload_aos(zkb_ctx* c, const uint64_t* aos, uint64_t n_src, uint64_t fir
         ZK_TRY(check_launch(c, "k_aos_to_planar"));
         return ZKB_OK;
     }
-    ZK_TRY(ensure_stage(c, (size_t)chunk_dst * 32));
-    for (uint64_t off = 0; off < n_dst; off += chunk_dst) {
-        const uint64_t m = (n_dst - off < chunk_dst) ? n_dst - off : chunk_dst;
-        ZK_CUDA(c, cudaMemcpyAsync(c->stage, (const uint8_t*)aos + (first + off) * 32, (size_t)m * 32, cudaMemcpyHostToDevice,
-                                   c->stream));
+    if (n_dst <= UP_CHUNK) {  // small table: one copy, one kernel, one stream
+        ZK_TRY(ensure_stage(c, (size_t)n_dst * 32));
+        ZK_CUDA(c, cudaMemcpyAsync(c->stage, (const uint8_t*)aos + first * 32, (size_t)n_dst * 32, cudaMemcpyHostToDevice, c->stream));
+        prof_begin(c, ZKB_K_LAYOUT, 64.0 * (double)n_dst);
+        c->K->aos_to_planar(c->stage, out->ref(), n_dst, 0, 1, conv, grid_for(c, n_dst, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_aos_to_planar"));
+        return ZKB_OK;
+    }
+    // large table: 16 MiB chunks through two staging buffers; the copy engine never waits for a layout kernel
+    if (!c->copy_stream) {
+        ZK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            ZK_CUDA(c, cudaMalloc(&c->up_stage[b], (size_t)UP_CHUNK * 32));
+            ZK_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+            ZK_CUDA(c, cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming));
+        }
+        ZK_CUDA(c, cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+    }
+    ZK_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));  // earlier users of the staging buffers are ordered before us
+    ZK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
+    uint64_t i = 0;
+    for (uint64_t off = 0; off < n_dst; off += UP_CHUNK, ++i) {
+        const uint64_t m = (n_dst - off < UP_CHUNK) ? n_dst - off : UP_CHUNK;
+        const int b = (int)(i & 1);
+        if (i >= 2) ZK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+        ZK_CUDA(c, cudaMemcpyAsync(c->up_stage[b], (const uint8_t*)aos + (first + off) * 32, (size_t)m * 32, cudaMemcpyHostToDevice,
+                                   c->copy_stream));
+        ZK_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        ZK_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
         TabRef dst{out->base + off, out->stride};
         prof_begin(c, ZKB_K_LAYOUT, 64.0 * (double)m);
-        c->K->aos_to_planar(c->stage, dst, m, 0, 1, conv, grid_for(c, m, 8), c->stream);
+        c->K->aos_to_planar(c->up_stage[b], dst, m, 0, 1, conv, grid_for(c, m, 8), c->stream);
         ZK_TRY(check_launch(c, "k_aos_to_planar"));
+        ZK_CUDA(c, cudaEventRecord(c->ev_free[b], c->stream));
     }
     return ZKB_OK;
 }
@@ -1383,6 +1411,16 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     if (c->stage) cudaFreeAsync(c->stage, c->stream);
     if (c->d_partials) cudaFreeAsync(c->d_partials, c->stream);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(c->up_stage[b]);
+            cudaEventDestroy(c->ev_copied[b]);
+            cudaEventDestroy(c->ev_free[b]);
+        }
+        cudaEventDestroy(c->ev_entry);
+        cudaStreamDestroy(c->copy_stream);
+    }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     c->shm.close_();
     prof_drain(c);
