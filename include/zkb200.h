@@ -79,7 +79,7 @@ int32_t zkb_ctx_sync(zkb_ctx* ctx);
  * (ZKB_K_*), the number of launches, their summed duration and their summed ALGORITHMIC bytes
  * (compulsory reads + writes, DESIGN.md "Kernels") since profiling was enabled. */
 enum { ZKB_K_SC_EVAL = 0, ZKB_K_SC_FOLD_EVAL = 1, ZKB_K_FOLD_TABLES = 2, ZKB_K_FINAL_BIND = 3, ZKB_K_FOLD = 4,
-       ZKB_K_LAYOUT = 5, ZKB_K_GKR_BUILD = 6, ZKB_K_OTHER = 7, ZKB_K_SC_TAIL = 8, ZKB_K_SC_SMALL = 9, ZKB_K_COUNT = 10 };
+       ZKB_K_LAYOUT = 5, ZKB_K_GKR_BUILD = 6, ZKB_K_OTHER = 7, ZKB_K_SC_TAIL = 8, ZKB_K_SC_SMALL = 9, ZKB_K_SC_TAIL_MID = 10, ZKB_K_COUNT = 11 };
 int32_t zkb_ctx_profile(zkb_ctx* ctx, int32_t enable);
 int32_t zkb_ctx_profile_read(zkb_ctx* ctx, int32_t kernel_id, uint64_t* launches, double* ms, double* alg_bytes);
 const char* zkb_kernel_name(int32_t kernel_id);

@@ -269,23 +269,23 @@ struct RoundAcc {
         if (NPTS == 3 && D == 2 && F::SLACK3P) {
             // the only extra point is t = 2 and both factors go straight into the lazy product: take the
             // unreduced 2*hi - lo + p (< 3p < 2^256) and skip two modular subtractions and two additions
-            mac(S::of(2), Fd::line2_lazy(lo[0], hi[0]), Fd::line2_lazy(lo[1], hi[1]));
-            return;
-        }
-        Fe cur[D], dl[D];
+            mac(S::of(2), Fd::line2_lazy(lo[0], hi[0]), Fd::line2_lazy(lo[D - 1], hi[D - 1]));
+        } else {
+            Fe cur[D], dl[D];
 #pragma unroll
-        for (int f = 0; f < D; ++f) {
-            dl[f] = Fd::sub(hi[f], lo[f]);
-            cur[f] = hi[f];
-        }
+            for (int f = 0; f < D; ++f) {
+                dl[f] = Fd::sub(hi[f], lo[f]);
+                cur[f] = hi[f];
+            }
 #pragma unroll
-        for (int t = 2; t < NPTS; ++t) {
+            for (int t = 2; t < NPTS; ++t) {
 #pragma unroll
-            for (int f = 0; f < D; ++f) cur[f] = Fd::add(cur[f], dl[f]);
-            Fe m = cur[0];
+                for (int f = 0; f < D; ++f) cur[f] = Fd::add(cur[f], dl[f]);
+                Fe m = cur[0];
 #pragma unroll
-            for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, cur[f]);
-            mac(S::of(t), m, cur[D - 1]);
+                for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, cur[f]);
+                mac(S::of(t), m, cur[D - 1]);
+            }
         }
     }
     __device__ __forceinline__ void finish(Fe* out) {

@@ -704,6 +704,7 @@ int32_t sp_final_values(zkb_ctx* c, SumPolyState* sp, Fe* vals) {
 //     challenges through the host mailbox);
 //   * tables that fit in shared memory: the single-CTA kernel k_sc_small, which can also
 //     produce round 0 itself, so a small sumcheck is exactly one launch.
+constexpr uint64_t MID_N = 1ull << 17;
 struct RoundDriver {
     zkb_ctx* c;
     SumPolyState* sp;
@@ -833,13 +834,18 @@ struct RoundDriver {
         begin_mailbox();
         a.base_seq = base;
         a.timeout_clocks = 6000000000ll;  // ~3 s
-        stop_n = a.stop_n = sp->sharded ? gather_n() : small_cap();
+        // Throughput-bound rounds (tables > 2^17 entries) and latency-bound rounds run as two launches of the same
+        // kernel, so that each launch (and its profile entry) belongs to one regime.
+        stop_n = sp->sharded ? gather_n() : small_cap();
+        const bool big = sp->cur_n > MID_N;
+        if (big && stop_n < MID_N) stop_n = MID_N;
+        a.stop_n = stop_n;
         const uint64_t quads = first_eval ? sp->cur_n / 2 : (sp->cur_n / 4 ? sp->cur_n / 4 : 1);
         const int grid = grid_for(c, quads, sc_occ(c, 2, sp->kind, sp->kD, sp->npts));
         ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
         a.partials = c->d_partials;
         ZK_CUDA(c, cudaMemsetAsync(&c->d_relay->seq, 0, 2 * sizeof(unsigned int), c->stream));
-        prof_begin(c, ZKB_K_SC_TAIL, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)) +
+        prof_begin(c, big ? ZKB_K_SC_TAIL : ZKB_K_SC_TAIL_MID, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)) +
                                          (first_eval ? 32.0 * (double)sp->sel.size() * (double)sp->cur_n : 0.0));
         int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, a, grid, c->stream);
         if (e < 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_tail: shape not instantiated");
@@ -1469,7 +1475,8 @@ int32_t zkb_ctx_profile_read(zkb_ctx* c, int32_t k, uint64_t* launches, double* 
 }
 const char* zkb_kernel_name(int32_t k) {
     static const char* names[ZKB_K_COUNT] = {"k_sc_eval", "k_sc_fold_eval", "k_fold_tables", "k_final_bind", "k_fold",
-                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other", "k_sc_tail", "k_sc_small"};
+                                             "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other", "k_sc_tail", "k_sc_small",
+                                             "k_sc_tail (tables <= 2^17)"};
     return (k >= 0 && k < ZKB_K_COUNT) ? names[k] : "?";
 }
 

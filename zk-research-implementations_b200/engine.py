@@ -234,7 +234,7 @@ class Context:
     def profile_read(self) -> dict:
         """{kernel name: (launches, total ms, total algorithmic bytes)} since profile(True)."""
         out = {}
-        for k in range(10):
+        for k in range(11):
             n, ms, by = C.c_uint64(), C.c_double(), C.c_double()
             _ck(self, lib().zkb_ctx_profile_read(self._h, k, C.byref(n), C.byref(ms), C.byref(by)))
             if n.value:
