@@ -377,9 +377,10 @@ def main():
     roof = {
         "bound": "hbm", "kernel": dom + "<BN254Fr,PROD,D=2,NPTS=3>", "achieved": achieved, "peak": peaks["hbm_gbs"],
         "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        # ncu --set full on the 2^24 -> 2^23 round (profiles/r01_ncu_full_c_cpasync_staged.csv): dram read + write bytes
-        "traffic": 1073828000 + 507612928, "traffic_note": "per launch of the largest round (algorithmic 1610612736 B); "
-                   "kernel replay cannot re-run a kernel that handshakes with the host, so ncu captures use --tail-log2 0",
+        # ncu --set full on the 2^24 -> 2^23 round (profiles/r01_ncu_full_e_final.csv): dram read + write bytes
+        "traffic": 1073921000 + 509659904, "traffic_note": "per launch of the largest round (algorithmic 1610612736 B), the same "
+                   "round_pass code launched once per round: under Nsight Compute launches are synchronous, so a kernel that "
+                   "waits for the host's next challenge cannot run and the engine falls back to one launch per round",
         "launches": dl, "kernel_ms_per_step": dms / args.steps, "alg_bytes_per_step": dby / args.steps,
         "share_of_step": (dms / args.steps) / ms_step,
         "note": "the persistent kernel's duration includes its per-round waits for the host transcript (mailbox); "
