@@ -416,3 +416,39 @@ def test_fullsize_evaluate_linearity(zkb, ctxs):
     bits = [(idx >> (n - 1 - k)) & 1 for k in range(n)]
     from oracle import c_oracle
     assert a.evaluate(bits) == arr_to_ints(c_oracle.synth_table(fid, 5, 0, n, first=idx, count=1))[0]
+
+
+# ------------------------------------------------------------------------ error behaviour through the C ABI
+def test_abi_error_codes_on_device(zkb, ctxs):
+    """The reference's panics arrive as status codes (and as the same strings through the mirror); bad handles and
+    null pointers are rejected instead of crashing."""
+    import ctypes as C
+
+    E = zkb.engine
+    L = E.lib()
+    ctx = ctxs(0, 1)
+    h = C.c_uint64()
+    three = ctx.mont([1, 2, 3])
+    assert L.zkb_mle_upload(ctx.handle, three.ctypes.data, 3, C.byref(h)) == -2          # "Invalid evaluations"
+    assert L.zkb_mle_upload(ctx.handle, None, 4, C.byref(h)) == -1                        # null pointer
+    assert L.zkb_mle_free(ctx.handle, 0xDEADBEEF) == -1                                   # unknown handle
+    m = zkb.MultilinearPoly(ctx, [1, 2, 3, 4])
+    out = (C.c_uint64 * 4)()
+    one = ctx.mont([5])
+    assert L.zkb_mle_evaluate(ctx.handle, m.handle, E._p(one), 1, out) == -3              # "Invalid number of values"
+    assert L.zkb_mle_partial_evaluate(ctx.handle, m.handle, 2, E._p(one), C.byref(h)) == -3
+    m8 = zkb.MultilinearPoly(ctx, list(range(8)))
+    arr = (C.c_uint64 * 2)(m.handle, m8.handle)
+    assert L.zkb_sumpoly_create(ctx.handle, arr, 1, 2, C.byref(h)) == -4                  # "all evaluations must have same length"
+    assert L.zkb_mle_binary(ctx.handle, m.handle, m8.handle, 0, C.byref(h)) == -4
+    big = (C.c_uint64 * 20)(*([m.handle] * 20))
+    assert L.zkb_sumpoly_create(ctx.handle, big, 10, 2, C.byref(h)) == -9                 # more than 16 tables
+    assert L.zkb_sumpoly_create(ctx.handle, big, 1, 5, C.byref(h)) == -9                  # degree > 4
+    assert b"16 tables" in L.zkb_ctx_last_error(ctx.handle) or b"degree" in L.zkb_ctx_last_error(ctx.handle)
+    gates = (C.c_uint32 * 2)(4, 4)
+    ops = (C.c_uint8 * 8)(*([0] * 8))
+    assert L.zkb_circuit_create(ctx.handle, 2, gates, ops, C.byref(h)) == -11             # not expressible by the reference wiring
+    # a failed call leaves the context usable
+    assert m.evaluate([0, 1]) == 2
+    with pytest.raises(zkb.ZkbError):
+        zkb.Context(7, 0, 0)                                                              # unknown field id
