@@ -450,5 +450,6 @@ def test_abi_error_codes_on_device(zkb, ctxs):
     assert L.zkb_circuit_create(ctx.handle, 2, gates, ops, C.byref(h)) == -11             # not expressible by the reference wiring
     # a failed call leaves the context usable
     assert m.evaluate([0, 1]) == 2
-    with pytest.raises(zkb.ZkbError):
-        zkb.Context(7, 0, 0)                                                              # unknown field id
+    raw = C.c_void_p()
+    assert L.zkb_ctx_create(7, 0, 0, C.byref(raw)) == -1                                  # unknown field id
+    assert L.zkb_ctx_create(0, 99, 0, C.byref(raw)) == -6                                 # no such device
