@@ -519,20 +519,65 @@ struct Field {
         mul_wide16(a, b, ev, od);
         wide_add(acc, ev, od);
     }
+    // x * R^-1 mod p for any 256-bit x (Montgomery reduction without a multiplication): eight rows of
+    // "m = t0 * inv; t = (t + m*p) >> 32".  Result < p + 1, fully reduced on return.
+    ZK_HD static Fe redc256(const Fe& x) {
+        uint32_t s[9];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = x.l[j];
+        s[8] = 0;
+#pragma unroll
+        for (int row = 0; row < 8; ++row) {
+            const uint32_t m = mul_lo(s[0], F::INV);
+            s[0] = mad_lo_cc(F::P(0), m, s[0]);
+            s[1] = madc_hi_cc(F::P(0), m, s[1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) {
+                s[j] = madc_lo_cc(F::P(j), m, s[j]);
+                s[j + 1] = madc_hi_cc(F::P(j), m, s[j + 1]);
+            }
+            s[8] = addc(s[8], 0u);
+            s[1] = mad_lo_cc(F::P(1), m, s[1]);
+            s[2] = madc_hi_cc(F::P(1), m, s[2]);
+#pragma unroll
+            for (int j = 3; j < 8; j += 2) {
+                s[j] = madc_lo_cc(F::P(j), m, s[j]);
+                s[j + 1] = madc_hi_cc(F::P(j), m, s[j + 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = s[j + 1];  // s[0] is zero now: divide by 2^32
+            s[8] = 0;
+        }
+        Fe r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.l[j] = s[j];
+        return reduce_once(r);
+    }
+    // any 256-bit x -> x mod p by repeated conditional subtraction (2^256 < 6p for BN254, < 3p for BLS12-381)
+    ZK_HD static Fe mod_p(const Fe& x) {
+        Fe r = x;
+#pragma unroll
+        for (int k = 0; k < (F::SLACK3P ? 5 : 2); ++k) r = reduce_once(r);
+        return r;
+    }
     // acc * R^-1 mod p, fully reduced: acc = A0 + A1*2^256 + A2*2^512 ->
-    // A0*R^-1 + A1 + A2*R  =  mul(1, A0) + mul(R, A1) + mul(R^2, A2)   (mul = Montgomery product).
-    // The chunks A_k may exceed p: they go in as the limb-iterated operand `b`, for which mul() only
-    // needs b < 2^256 (its row invariant T < a + p depends on the full operand `a` alone).
+    // A0*R^-1 + A1 + A2*R  =  redc256(A0) + (A1 mod p) + mul(R^2, A2)   (mul = Montgomery product; the chunk
+    // A2 goes in as the limb-iterated operand, for which mul() only needs b < 2^256).  A2 is zero until about
+    // 27 products have been accumulated, so short sums skip the multiplication.
     ZK_HD static Fe reduce_wide(const Wide& acc) {
-        Fe a0, a1, a2 = zero(), u = zero();
+        Fe a0, a1;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             a0.l[i] = acc.l[i];
             a1.l[i] = acc.l[8 + i];
         }
-        a2.l[0] = acc.l[16];
-        u.l[0] = 1;
-        return add(add(mul(u, a0), mul(one(), a1)), mul(r2(), a2));
+        Fe r = add(redc256(a0), mod_p(a1));
+        if (acc.l[16] != 0) {
+            Fe a2 = zero();
+            a2.l[0] = acc.l[16];
+            r = add(r, mul(r2(), a2));
+        }
+        return r;
     }
 
 

@@ -48,6 +48,7 @@ struct FinishArgs {
     unsigned long long* result_wide;  // optional [NPTS][8] limbs zero-extended to u64 (NCCL sum operand)
     volatile unsigned int* flag;      // optional mailbox flag (mapped host memory): set to `seq` after `result`
     unsigned int seq;
+    unsigned long long* stamp;        // optional: %globaltimer right before the result is published
 };
 
 struct ScArgs {
@@ -66,6 +67,11 @@ struct ChalList {
 
 enum { KIND_PROD = 0, KIND_XYZ = 1 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // ----------------------------------------------------------- load / store
 __device__ __forceinline__ Fe ld_fe(const TabRef& t, uint64_t i) {
     uint4 a = t.base[i];
@@ -131,6 +137,7 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a, unsig
                     for (int k = 0; k < 8; ++k) a.result_wide[p * 8 + k] = acc[p].l[k];
                 }
             }
+            if (a.stamp) *a.stamp = gtime();
             __threadfence_system();
             if (a.flag) *a.flag = a.seq;
         }
@@ -172,6 +179,7 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a, unsig
             }
         }
         *a.ticket = 0u;
+        if (a.stamp) *a.stamp = gtime();
         __threadfence_system();
         if (a.flag) *a.flag = a.seq;
     }
@@ -615,6 +623,8 @@ struct alignas(64) TailMailbox {
     volatile unsigned int dev_seq;
     volatile unsigned int dev_error;  // 1 = timed out waiting for the host
     unsigned int pad1[14];
+    // diagnostics (ZKB200_TRACE=1): device %globaltimer stamps of the last round, see RoundDriver::trace
+    unsigned long long ts[8];
 };
 struct TailRelay {  // device memory: CTA 0 re-publishes the host's message for the other CTAs
     FixedMul rt;
@@ -660,6 +670,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             fin.result_wide = nullptr;
             fin.flag = &a.mb->dev_seq;
             fin.seq = a.base_seq + 1;
+            fin.stamp = nullptr;
             finish_round<F, NPTS>(out, fin, n_active);
         }
     }
@@ -688,6 +699,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
                     else if (clock64() - t0 > a.timeout_clocks) status = 3;
                 }
                 if (status == 1) {
+                    if (lane == 0) a.mb->ts[0] = gtime();
                     Fe r;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) r.l[k] = __shfl_sync(0xffffffffu, word, k);
@@ -698,7 +710,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
                     }
                     __threadfence();
                     __syncwarp();
-                    if (lane == 0) *reinterpret_cast<volatile unsigned int*>(&a.relay->seq) = want;
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile unsigned int*>(&a.relay->seq) = want;
+                        a.mb->ts[1] = gtime();
+                    }
                 } else if (lane == 0) {
                     if (status == 3) {
                         a.mb->dev_error = 1;
@@ -741,7 +756,9 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
         const unsigned int n_active = ctas < 1 ? 1u : (ctas < gridDim.x ? (unsigned int)ctas : gridDim.x);
         if (blockIdx.x < n_active) {
             Fe out[NPTS - 1];
+            if (blockIdx.x == 0 && threadIdx.x == 0) a.mb->ts[2] = gtime();
             round_pass<F, KIND, D, NPTS>(src, a.out, a.n_products, n_out, s_rt, stage, out);
+            if (blockIdx.x == 0 && threadIdx.x == 0) a.mb->ts[3] = gtime();
             FinishArgs fin;
             fin.partials = a.partials;
             fin.ticket = a.ticket;
@@ -749,6 +766,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             fin.result_wide = nullptr;
             fin.flag = &a.mb->dev_seq;
             fin.seq = a.base_seq + it + 1;
+            fin.stamp = &a.mb->ts[4];
             finish_round<F, NPTS - 1>(out, fin, n_active);
         }
         n_in = n_out;

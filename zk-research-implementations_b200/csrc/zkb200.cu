@@ -16,6 +16,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -273,6 +274,9 @@ struct zkb_ctx {
     unsigned int tail_seq = 0;
     uint32_t tail_log2 = 40;                 // every unsharded round after the first runs in a persistent kernel
     uint32_t small_bytes = SMALL_SMEM_MAX;   // shared-memory budget of k_sc_small (0 = off)
+    // ZKB200_TRACE=1: where a persistent-kernel round spends its time (printed at zkb_ctx_destroy)
+    bool trace = false;
+    double tr_n = 0, tr_host = 0, tr_rtt = 0, tr_relay = 0, tr_spread = 0, tr_pass = 0, tr_reduce = 0;
     std::unordered_map<std::string, int> occ_cache;
     // per-launch event timing (zkb_ctx_profile)
     bool prof = false;
@@ -438,6 +442,7 @@ int32_t prep_finish(zkb_ctx* c, int grid, int npts, bool sharded, FinishArgs* f)
     ZK_TRY(ensure_partials(c, (size_t)grid * npts));
     f->partials = c->d_partials;
     f->ticket = c->d_ticket;
+    f->stamp = nullptr;
     if (sharded && !c->use_shm) {
         f->result = c->d_res;
         f->result_wide = c->d_wide;
@@ -714,6 +719,19 @@ struct RoundDriver {
     unsigned int sent = 0;   // challenges delivered through the mailbox so far
     unsigned int pubs = 0;   // messages consumed from it so far
     uint64_t stop_n = 0;     // k_sc_tail leaves once the tables have <= stop_n entries
+    unsigned long long t_recv = 0;
+    static double tsc_per_us() {
+        static double v = 0;
+        if (v == 0) {
+            timespec a, b;
+            clock_gettime(CLOCK_MONOTONIC, &a);
+            unsigned long long t0 = __builtin_ia32_rdtsc();
+            do clock_gettime(CLOCK_MONOTONIC, &b);
+            while ((b.tv_sec - a.tv_sec) * 1e9 + (b.tv_nsec - a.tv_nsec) < 2e6);
+            v = (double)(__builtin_ia32_rdtsc() - t0) / (((b.tv_sec - a.tv_sec) * 1e9 + (b.tv_nsec - a.tv_nsec)) * 1e-3);
+        }
+        return v;
+    }
     Fe poly[MAXPTS];         // coefficients of the current round polynomial, if the caller interpolated it already
     int poly_len = -1;
 
@@ -894,6 +912,12 @@ struct RoundDriver {
         const bool go_small = !live && small_ok();
         if (!live && !go_small && !tail_ok()) return sp_bind_and_next(c, sp, r, evals, finals);
         const bool was_live = live;
+        const bool tracing = c->trace && was_live && !small;
+        unsigned long long t_send = 0;
+        if (tracing) {
+            t_send = __builtin_ia32_rdtsc();
+            if (t_recv) c->tr_host += (double)(t_send - t_recv) / tsc_per_us();
+        }
         if (was_live) send(r);  // first, so the device works while the host finishes the claim chain
         if (poly_len < 0) poly_len = c->interp[sp->npts].interpolate(sp->last_evals, poly);
         const Fe claim = uni_evaluate(c->H, poly, poly_len, r);
@@ -903,6 +927,22 @@ struct RoundDriver {
             else ZK_TRY(launch_tail(r));
         }
         ZK_TRY(wait_dev(base + (++pubs)));
+        t_recv = c->trace ? __builtin_ia32_rdtsc() : 0;
+        if (tracing) {
+            const unsigned long long* ts = c->mb->ts;
+            // CTA 0's stamps are not ordered with the publishing CTA's flag: they may belong to the previous round,
+            // so only differences of stamps written by the same thread are exact; the others are clamped
+            auto d = [](unsigned long long a, unsigned long long b) {
+                const long long x = (long long)(a - b);
+                return x < 0 || x > 100000000ll ? 0.0 : (double)x * 1e-3;
+            };
+            c->tr_n += 1;
+            c->tr_rtt += (double)(t_recv - t_send) / tsc_per_us();
+            c->tr_relay += d(ts[1], ts[0]);
+            c->tr_spread += d(ts[2], ts[1]);
+            c->tr_pass += d(ts[3], ts[2]);
+            c->tr_reduce += d(ts[4], ts[3]);
+        }
         sp->cur_n /= 2;
         if (sp->cur_n == 1) {
             live = false;  // the kernel leaves after publishing the bound values
@@ -1392,12 +1432,17 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
         c->tail_log2 = 0;
         c->small_bytes = 0;
     }
+    c->trace = getenv("ZKB200_TRACE") != nullptr;
     *out = c.release();
     return ZKB_OK;
 }
 
 int32_t zkb_ctx_destroy(zkb_ctx* c) {
     if (!c) return ZKB_ERR_BAD_ARG;
+    if (c->trace && c->tr_n > 0)
+        fprintf(stderr, "[zkb200 trace] k_sc_tail rounds=%.0f  per round (us): host %.2f | send->result %.2f = relay %.2f + fan-out %.2f + pass(CTA0) %.2f + reduce/publish %.2f + pcie/poll %.2f\n",
+                c->tr_n, c->tr_host / c->tr_n, c->tr_rtt / c->tr_n, c->tr_relay / c->tr_n, c->tr_spread / c->tr_n, c->tr_pass / c->tr_n,
+                c->tr_reduce / c->tr_n, (c->tr_rtt - c->tr_relay - c->tr_spread - c->tr_pass - c->tr_reduce) / c->tr_n);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->sps) sp_release(c, kv.second.get());
