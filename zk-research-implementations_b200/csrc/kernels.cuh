@@ -647,6 +647,7 @@ struct TailArgs {
     long long timeout_clocks;
     uint64_t stop_n;           // leave after publishing the round whose tables have <= stop_n entries (0: run to the end)
     int first_eval;            // 1: start with round 0 (all NPTS sums of the unbound tables) and take rt0 from the mailbox
+    unsigned long long* dbg;   // optional [2 * gridDim]: per-CTA start/end %globaltimer of the pass of round `it == 1`
 };
 
 template <class F, int KIND, int D, int NPTS>
@@ -757,8 +758,13 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
         if (blockIdx.x < n_active) {
             Fe out[NPTS - 1];
             if (blockIdx.x == 0 && threadIdx.x == 0) a.mb->ts[2] = gtime();
+            if (a.dbg && it == 1 && threadIdx.x == 0) a.dbg[2 * blockIdx.x] = gtime();
             round_pass<F, KIND, D, NPTS>(src, a.out, a.n_products, n_out, s_rt, stage, out);
             if (blockIdx.x == 0 && threadIdx.x == 0) a.mb->ts[3] = gtime();
+            if (a.dbg && it == 1) {
+                __syncthreads();
+                if (threadIdx.x == 0) a.dbg[2 * blockIdx.x + 1] = gtime();
+            }
             FinishArgs fin;
             fin.partials = a.partials;
             fin.ticket = a.ticket;

@@ -275,7 +275,9 @@ struct zkb_ctx {
     uint32_t tail_log2 = 40;                 // every unsharded round after the first runs in a persistent kernel
     uint32_t small_bytes = SMALL_SMEM_MAX;   // shared-memory budget of k_sc_small (0 = off)
     // ZKB200_TRACE=1: where a persistent-kernel round spends its time (printed at zkb_ctx_destroy)
-    bool trace = false;
+    bool trace = false, trace_verbose = false, dbg_done = false;
+    unsigned long long* d_dbg = nullptr;
+    int dbg_grid = 0;
     double tr_n = 0, tr_host = 0, tr_rtt = 0, tr_relay = 0, tr_spread = 0, tr_pass = 0, tr_reduce = 0;
     std::unordered_map<std::string, int> occ_cache;
     // per-launch event timing (zkb_ctx_profile)
@@ -863,6 +865,13 @@ struct RoundDriver {
         ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
         a.partials = c->d_partials;
         ZK_CUDA(c, cudaMemsetAsync(&c->d_relay->seq, 0, 2 * sizeof(unsigned int), c->stream));
+        if (c->trace_verbose && big && !c->dbg_done) {
+            ZK_CUDA(c, cudaMalloc((void**)&c->d_dbg, sizeof(unsigned long long) * 2 * 1024));
+            ZK_CUDA(c, cudaMemsetAsync(c->d_dbg, 0, sizeof(unsigned long long) * 2 * 1024, c->stream));
+            a.dbg = c->d_dbg;
+            c->dbg_grid = grid;
+            c->dbg_done = true;
+        }
         prof_begin(c, big ? ZKB_K_SC_TAIL : ZKB_K_SC_TAIL_MID, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)) +
                                          (first_eval ? 32.0 * (double)sp->sel.size() * (double)sp->cur_n : 0.0));
         int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, a, grid, c->stream);
@@ -942,6 +951,9 @@ struct RoundDriver {
             c->tr_spread += d(ts[2], ts[1]);
             c->tr_pass += d(ts[3], ts[2]);
             c->tr_reduce += d(ts[4], ts[3]);
+            if (c->trace_verbose)
+                fprintf(stderr, "[zkb200 trace] n_in=2^%d send->result %.2f us: relay %.2f fan-out %.2f pass(CTA0) %.2f reduce/publish %.2f\n",
+                        ilog2_u64(sp->cur_n), (double)(t_recv - t_send) / tsc_per_us(), d(ts[1], ts[0]), d(ts[2], ts[1]), d(ts[3], ts[2]), d(ts[4], ts[3]));
         }
         sp->cur_n /= 2;
         if (sp->cur_n == 1) {
@@ -1433,12 +1445,24 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
         c->small_bytes = 0;
     }
     c->trace = getenv("ZKB200_TRACE") != nullptr;
+    c->trace_verbose = c->trace && std::atoi(getenv("ZKB200_TRACE")) >= 2;
     *out = c.release();
     return ZKB_OK;
 }
 
 int32_t zkb_ctx_destroy(zkb_ctx* c) {
     if (!c) return ZKB_ERR_BAD_ARG;
+    if (c->d_dbg) {
+        std::vector<unsigned long long> h(2 * 1024);
+        cudaMemcpy(h.data(), c->d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int b = 0; b < c->dbg_grid; ++b) t0 = h[2 * b] < t0 ? h[2 * b] : t0;
+        fprintf(stderr, "[zkb200 trace] per-CTA pass of the second round (start, end in us after the first start):\n");
+        for (int b = 0; b < c->dbg_grid; ++b)
+            fprintf(stderr, "%s%d:%.0f-%.0f", b % 12 ? " " : "\n  ", b, (double)(h[2 * b] - t0) * 1e-3, (double)(h[2 * b + 1] - t0) * 1e-3);
+        fprintf(stderr, "\n");
+        cudaFree(c->d_dbg);
+    }
     if (c->trace && c->tr_n > 0)
         fprintf(stderr, "[zkb200 trace] k_sc_tail rounds=%.0f  per round (us): host %.2f | send->result %.2f = relay %.2f + fan-out %.2f + pass(CTA0) %.2f + reduce/publish %.2f + pcie/poll %.2f\n",
                 c->tr_n, c->tr_host / c->tr_n, c->tr_rtt / c->tr_n, c->tr_relay / c->tr_n, c->tr_spread / c->tr_n, c->tr_pass / c->tr_n,
