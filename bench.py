@@ -197,6 +197,50 @@ def gkr_leg(z, ctx_unused, args):
                         "from pinned host memory (prove_ms) or pageable memory (prove_ms_pageable_input)" % (log_in, L, log_in - 1)}
 
 
+def gkr_uniform_leg(z, args):
+    """BASELINE configs[2] AS WRITTEN (SURVEY 8d C3 ii): 16 layers of 2^20 add/mul gates each with random wiring over
+    2^20 inputs -- not expressible by the reference's (2i, 2i+1) wiring, so this runs the general-wiring extension
+    (zkb_gkr_prove_wired; same protocol, log2(outputs) challenges for the output MLE).  The 2^20-element output layer is
+    part of the proof: its download and its Keccak absorption on the host are inside prove_ms."""
+    import numpy as np
+    import torch
+    from oracle import c_oracle as O
+
+    lg, L = args.gkr_uniform_log_gates, args.gkr_uniform_layers
+    G = 1 << lg
+    rng = np.random.default_rng(11)
+    ctx = z.Context(z.BN254_FR, 0, z.MODE_COMPAT)
+    spec = [(rng.integers(0, 2, size=G, dtype=np.uint8), rng.integers(0, G, size=G, dtype=np.uint32),
+             rng.integers(0, G, size=G, dtype=np.uint32)) for _ in range(L)]
+    circ = z.gkr_circuit.WiredCircuit(ctx, G, spec)
+    inputs = z.engine.to_mont(z.BN254_FR, O.synth_table(0, SEED + 2, 0, lg))
+    pinned = torch.from_numpy(inputs.view(np.int64)).pin_memory()
+    prover = z.gkr_protocol.RawWiredGkrProver(circ, pinned.numpy().view(np.uint64))
+    reps = max(2, min(args.steps, 5))
+    prover.prove()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        prover.prove()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    ctx.profile(True)
+    prover.prove()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    t0 = time.perf_counter()
+    ok = prover.verify()
+    verify_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    z.engine.keccak256(b"\0" * (32 * G))
+    keccak_ms = (time.perf_counter() - t0) * 1e3
+    circ.free()
+    ctx.close()
+    return {"prove_ms": ms, "verify_ms": verify_ms, "verify_accepts": ok, "host_keccak_of_output_layer_ms": keccak_ms,
+            "kernel_ms": {k: round(v[1], 4) for k, v in prof.items()}, "launches": sum(v[0] for v in prof.values()),
+            "rounds": int(prover.total), "layers": L, "gates_per_layer": G,
+            "workload": "configs[2] as written: %d layers x 2^%d gates, random wiring, 2^%d inputs, BN254 Fr, general-wiring "
+                        "extension (the reference's fixed wiring cannot express uniform layers); pinned input; KZG excluded" % (L, lg, lg)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +250,8 @@ def main():
     ap.add_argument("--n-vars", type=int, default=N_VARS_PER_GPU, help="variables per GPU shard")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gkr-log-inputs", type=int, default=21)
+    ap.add_argument("--gkr-uniform-log-gates", type=int, default=20, help="0 = skip the uniform-layer GKR leg")
+    ap.add_argument("--gkr-uniform-layers", type=int, default=16)
     ap.add_argument("--products", type=int, default=1, help="ProductPolys in the SumPoly (default: BASELINE configs[1])")
     ap.add_argument("--factors", type=int, default=2, help="factors per ProductPoly")
     ap.add_argument("--tail-log2", type=int, default=None, help="persistent-kernel threshold (0 = one launch per round)")
@@ -405,6 +451,8 @@ def main():
     }
     if world == 1:
         line["gkr"] = gkr_leg(z, ctx, args)
+        if args.gkr_uniform_log_gates > 0:
+            line["gkr_uniform"] = gkr_uniform_leg(z, args)
     if world == 1 and not args.no_cpu_baseline:
         n_s = pick_cpu_sample(6.0)
         v, cores, dt = cpu_port_run(n_s, 2)

@@ -219,6 +219,29 @@ int32_t zkb_gkr_verify(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, ui
                        int32_t* accepted);
 uint32_t zkb_gkr_total_rounds(uint32_t n_layers, const uint32_t* gates_per_layer);
 
+/* ------------------------------------------- general wiring (EXTENSION beyond the reference) */
+/* The reference wires gate i to (2i, 2i+1) of the layer below (gkr_circuit.rs:76-78,132), so every layer halves and
+ * the output layer has 1-2 gates (gkr_protocol.rs:235).  BASELINE.json configs[2] ("2^20 gates per layer and 16
+ * layers") needs gates that read arbitrary wires in1[g], in2[g] and a wide output layer.  These entry points run
+ * the reference's protocol (gkr_protocol.rs:31-91,128-227: same transcript order, round polynomials, claim merge
+ * alpha*o1+beta*o2 and openings) on such circuits; the only change is that initiate_protocol (:229-241) draws
+ * log2(max(outputs,2)) consecutive challenges for the output MLE instead of one.  With in1 = 2g, in2 = 2g+1 and
+ * <= 2 outputs the proof bytes equal zkb_gkr_prove's.
+ * gates_per_layer: input side first, each a power of two; layer l reads the n_inputs inputs (l = 0) or the
+ * gates_per_layer[l-1] outputs of layer l-1; ops / in1 / in2 are concatenated per gate in layer order.
+ * The handle works with zkb_circuit_evaluate / zkb_circuit_free. */
+int32_t zkb_circuit_create_wired(zkb_ctx* ctx, uint32_t n_layers, const uint32_t* gates_per_layer, uint64_t n_inputs,
+                                 const uint8_t* ops, const uint32_t* in1, const uint32_t* in2, zkb_circ* out);
+/* Total sumcheck rounds of a proof over circuit `c` (either kind). */
+int32_t zkb_circuit_total_rounds(zkb_ctx* ctx, zkb_circ c, uint32_t* n_rounds);
+/* As zkb_gkr_prove; w0 receives n_w0 = max(outputs, 2) elements (the whole output layer). */
+int32_t zkb_gkr_prove_wired(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, uint64_t n_inputs, uint64_t* w0,
+                            uint64_t n_w0, uint64_t* coeffs, int32_t* lens, uint64_t* challenges, uint64_t* claimed,
+                            uint64_t final_openings[8], uint32_t* n_rounds);
+int32_t zkb_gkr_verify_wired(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mont, uint64_t n_inputs, const uint64_t* w0,
+                             uint64_t n_w0, const uint64_t* coeffs, const int32_t* lens, const uint64_t* claimed,
+                             const uint64_t final_openings[8], int32_t* accepted);
+
 /* ------------------------------------------------------------ microbenchmarks */
 /* Device-timed multiplier throughput (fills the IMAD-roofline denominator).
  * variant: 0/1 = IMAD.WIDE multiplier with 1/2 independent chains per thread, 2/3 = 32-bit lo/hi

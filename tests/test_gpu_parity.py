@@ -361,6 +361,90 @@ def test_gkr_reference_test_circuit(zkb, ctxs):
     assert zkb.gkr_protocol.verify(pr, c, inputs)
 
 
+def wired_pair(zkb, ctx, rng, n_inputs, gates_per_layer):
+    """The same random general-wiring circuit for the oracle and for the device."""
+    layers, spec, w = [], [], n_inputs
+    for G in gates_per_layer:
+        ops = [rng.randrange(2) for _ in range(G)]
+        in1 = [rng.randrange(w) for _ in range(G)]
+        in2 = [rng.randrange(w) for _ in range(G)]
+        layers.append(R.WiredLayer(ops, in1, in2, w))
+        spec.append((ops, in1, in2))
+        w = G
+    return R.WiredCircuit(layers), zkb.gkr_circuit.WiredCircuit(ctx, n_inputs, spec)
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_wired_gkr_matches_oracle(zkb, ctxs, fid, p):
+    """General wiring + wide output layer (extension for BASELINE configs[2]): device == oracle, bit for bit."""
+    ctx = ctxs(fid, 0)
+    G = zkb.gkr_protocol
+    rng = random.Random(7000 + fid)
+    shapes = [(2, [1]), (2, [4]), (4, [4, 4]), (8, [4, 8, 2]), (4, [8, 4, 4, 1]), (16, [16, 16, 16]), (64, [128, 32, 64]),
+              (256, [256, 256, 256])]
+    if fid == 0:
+        shapes += [(1 << 12, [1 << 13, 1 << 12]), (1 << 14, [1 << 14])]  # persistent-kernel and multi-launch regimes
+    for nin, gates in shapes:
+        oc, dc = wired_pair(zkb, ctx, rng, nin, gates)
+        inputs = [rng.randrange(p) for _ in range(nin)]
+        assert dc.evaluate(inputs) == oc.evaluate(inputs, p)
+        ref = R.wired_prove_sparse(oc, inputs, p)
+        pr = G.prove_wired(dc, inputs)
+        assert pr.output_poly == ref.output_poly
+        assert [[q.coefficients for q in layer] for layer in pr.proof_polynomials] == ref.proof_polynomials, (nin, gates)
+        assert pr.claimed_evaluations == ref.claimed_evaluations
+        assert pr.final_openings == ref.final_openings
+        assert G.verify_wired(pr, dc, inputs)
+        assert R.wired_verify_sparse(ref, oc, inputs, p)
+        if pr.proof_polynomials[-1][0].coefficients:
+            saved = list(pr.proof_polynomials[-1][0].coefficients)
+            pr.proof_polynomials[-1][0].coefficients[0] = (saved[0] + 1) % p
+            assert not G.verify_wired(pr, dc, inputs)
+            pr.proof_polynomials[-1][0].coefficients = saved
+        out = list(pr.output_poly)
+        pr.output_poly[-1] = (out[-1] + 1) % p
+        assert not G.verify_wired(pr, dc, inputs)
+        pr.output_poly = out
+        bad_inputs = list(inputs)
+        bad_inputs[-1] = (bad_inputs[-1] + 1) % p
+        assert not G.verify_wired(pr, dc, bad_inputs)
+        assert G.verify_wired(pr, dc, inputs)
+        dc.free()
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_wired_reduces_to_reference_wiring_on_device(zkb, ctxs, fid, p):
+    """in1 = 2g, in2 = 2g+1, <= 2 outputs: zkb_gkr_prove_wired produces the bytes of zkb_gkr_prove."""
+    ctx = ctxs(fid, 0)
+    G = zkb.gkr_protocol
+    rng = random.Random(7100 + fid)
+    for n_layers, out_gates in ((1, 1), (1, 2), (3, 1), (6, 2), (9, 1)):
+        gates, ops = tree_circuit(rng, n_layers, out_gates)
+        inputs = [rng.randrange(p) for _ in range(2 * gates[0])]
+        struct = [[zkb.Operation(o) for o in layer] for layer in ops]
+        c = zkb.gkr_circuit.Circuit(ctx, struct)
+        w = zkb.gkr_circuit.WiredCircuit.binary_tree(ctx, struct)
+        a, b = G.prove(c, inputs), G.prove_wired(w, inputs)
+        assert a.output_poly == b.output_poly and a.claimed_evaluations == b.claimed_evaluations
+        assert [[q.coefficients for q in l] for l in a.proof_polynomials] == [[q.coefficients for q in l] for l in b.proof_polynomials]
+        assert a.final_openings == b.final_openings and a.challenges == b.challenges
+        assert G.verify_wired(a, w, inputs) and G.verify(b, c, inputs)
+        c.free()
+        w.free()
+
+
+def test_wired_shape_errors(zkb, ctxs):
+    ctx = ctxs(0, 0)
+    W = zkb.gkr_circuit.WiredCircuit
+    for nin, spec in [(3, [([0], [0], [1])]),                      # inputs not a power of two
+                      (4, [([0, 1, 0], [0, 1, 2], [1, 2, 3])]),    # 3 gates
+                      (4, [([0, 1], [0, 4], [1, 2])]),             # wire out of range
+                      (4, [([0], [0], [1]), ([1], [0], [0])])]:    # a layer above a single gate
+        with pytest.raises(zkb.ZkbError) as ei:
+            W(ctx, nin, spec)
+        assert ei.value.status == -11
+
+
 def test_circuit_shape_errors(zkb, ctxs):
     ctx = ctxs(0, 0)
     Op = zkb.Operation

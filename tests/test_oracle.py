@@ -160,3 +160,51 @@ def test_openmp_matches_single_thread(oracle):
     b1 = oracle.sumcheck_prove(0, tabs[0])
     oracle.set_threads(1)
     assert a == b and a1 == b1
+
+
+# ------------------------------------------------------------- general wiring (extension, SURVEY 8d C3 ii)
+def random_wired(rng, n_inputs, gates_per_layer):
+    layers, w = [], n_inputs
+    for G in gates_per_layer:
+        layers.append(R.WiredLayer([rng.choice([R.ADD, R.MUL]) for _ in range(G)], [rng.randrange(w) for _ in range(G)],
+                                   [rng.randrange(w) for _ in range(G)], w))
+        w = G
+    return R.WiredCircuit(layers)
+
+
+def proof_fields(pr):
+    return (pr.output_poly, pr.proof_polynomials, pr.claimed_evaluations, pr.final_openings)
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_wired_reduces_to_reference_wiring(fid, p):
+    """With in1 = 2g, in2 = 2g+1 and <= 2 outputs the general-wiring prover IS the reference's."""
+    rng = random.Random(77 + fid)
+    for depth, outg in [(1, 1), (1, 2), (2, 1), (3, 2), (4, 1)]:
+        struct, nin = random_circuit(rng, depth, outg)
+        inp = [rng.randrange(p) for _ in range(nin)]
+        ref = R.gkr_protocol_prove_dense(R.Circuit(struct), inp, p)
+        wc = R.WiredCircuit.binary_tree(struct)
+        assert proof_fields(R.wired_prove_dense(wc, inp, p)) == proof_fields(ref)
+        assert proof_fields(R.wired_prove_sparse(wc, inp, p)) == proof_fields(ref)
+        assert R.wired_verify_sparse(ref, wc, inp, p)
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_wired_sparse_equals_dense(fid, p):
+    rng = random.Random(88 + fid)
+    for nin, gates in [(2, [1]), (2, [4]), (4, [4, 4]), (8, [4, 8, 2]), (4, [8, 4, 4, 1]), (8, [8, 8])]:
+        wc = random_wired(rng, nin, gates)
+        inp = [rng.randrange(p) for _ in range(nin)]
+        dense = R.wired_prove_dense(wc, inp, p)
+        sparse = R.wired_prove_sparse(wc, inp, p)
+        assert proof_fields(dense) == proof_fields(sparse), (nin, gates)
+        assert len(dense.output_poly) == max(gates[-1], 2)
+        assert R.wired_verify_sparse(sparse, wc, inp, p)
+        bad = R.GkrProof(list(sparse.output_poly), [[list(c_) for c_ in l] for l in sparse.proof_polynomials],
+                         list(sparse.claimed_evaluations), sparse.final_openings)
+        bad.output_poly[0] = (bad.output_poly[0] + 1) % p
+        assert not R.wired_verify_sparse(bad, wc, inp, p)
+        bad_inp = list(inp)
+        bad_inp[-1] = (bad_inp[-1] + 1) % p
+        assert not R.wired_verify_sparse(sparse, wc, bad_inp, p)

@@ -133,6 +133,12 @@ void l_eq_split(const ChalList& r, int n, int n_hi, TabRef hi, TabRef lo, int gr
 void l_gkr_phase1(const GkrP1Args& a, int grid, cudaStream_t s) { k_gkr_phase1<FT><<<grid, BLOCK, 0, s>>>(a); }
 void l_gkr_phase2(const GkrP2Args& a, int grid, cudaStream_t s) { k_gkr_phase2<FT><<<grid, BLOCK, 0, s>>>(a); }
 void l_gkr_wiring(const GkrWiringArgs& a, int grid, cudaStream_t s) { k_gkr_wiring<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_gkr_w_phase1(const GkrW1Args& a, int grid, cudaStream_t s) { k_gkr_w_phase1<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_gkr_w_phase2(const GkrW2Args& a, int grid, cudaStream_t s) { k_gkr_w_phase2<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_gkr_w_wiring(const GkrWWiringArgs& a, int grid, cudaStream_t s) { k_gkr_w_wiring<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_layer_eval_w(TabRef in, TabRef out, const uint8_t* ops, const uint32_t* in1, const uint32_t* in2, uint64_t n_gates, int grid, cudaStream_t s) {
+    k_layer_eval_w<FT><<<grid, BLOCK, 0, s>>>(in, out, ops, in1, in2, n_gates);
+}
 void l_bench_mul(int variant, Fe* out, uint32_t iters, int grid, cudaStream_t s) {
     Fe seed = Field<FT>::r2();
     if (variant == 0) k_bench_mul<FT, 1, false><<<grid, BLOCK, 0, s>>>(out, iters, seed);
@@ -152,7 +158,7 @@ void h_modulus(Fe& p) {
 const FieldKernels TABLE = {
     FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
-    l_gkr_phase2, l_gkr_wiring, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
+    l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };
 }  // namespace
 

@@ -1283,6 +1283,116 @@ __global__ void __launch_bounds__(BLOCK) k_gkr_phase2(const GkrP2Args a) {
     }
 }
 
+// ----------------------------------------------------------------- general wiring (extension, SURVEY F8 ii)
+// Gate g of a layer reads wires in1[g], in2[g] of the layer below (width W, any power of two).  The phase tables
+// are gathered through CSR lists of the gates by first / second input, made on the host at circuit creation:
+//   phase 1: H1[b]  = sum_{g: in1[g]=b} coef[g] * (Add ? 1 : W[in2[g]]),  HA2[b] = sum_{g Add, in1[g]=b} coef[g]*W[in2[g]]
+//   phase 2: C[c]   = sum_{g: in2[g]=c} coef[g]*eq(u,in1[g]) * (Add ? 1 : W(u)),  D[c] = sum_{g Add, in2[g]=c} coef[g]*eq(u,in1[g])*W(u)
+// with coef[g] = alpha*eq(ra1, g) + beta*eq(ra2, g) (output layer: eq(r0, g)).  With in1 = 2g, in2 = 2g+1 these are
+// exactly the tables of k_gkr_phase1 / k_gkr_phase2.
+struct WiredCoef {
+    TabRef a1_hi, a1_lo, a2_hi, a2_lo;
+    int n_lo;
+    int two;  // 0: coef = eq(ra1, g) (output layer); 1: alpha*eq(ra1,g) + beta*eq(ra2,g)
+    Fe alpha, beta;
+};
+template <class F>
+__device__ __forceinline__ Fe wired_coef(const WiredCoef& w, uint64_t g) {
+    typedef Field<F> Fd;
+    Fe e1 = eq_lookup<F>(w.a1_hi, w.a1_lo, w.n_lo, g);
+    if (!w.two) return e1;
+    Fe e2 = eq_lookup<F>(w.a2_hi, w.a2_lo, w.n_lo, g);
+    return Fd::add(Fd::mul(w.alpha, e1), Fd::mul(w.beta, e2));
+}
+struct GkrW1Args {
+    TabRef W, H1, HA2, coef;
+    WiredCoef wc;
+    const uint8_t* ops;
+    const uint32_t *in2, *off1, *lst1;
+    uint64_t width;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_w_phase1(const GkrW1Args a) {
+    typedef Field<F> Fd;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; b < a.width; b += step) {
+        Fe h1 = Fd::zero(), ha2 = Fd::zero();
+        for (uint32_t e = a.off1[b]; e < a.off1[b + 1]; ++e) {
+            const uint32_t g = a.lst1[e];
+            const Fe c = wired_coef<F>(a.wc, g);
+            st_fe(a.coef, g, c);
+            const Fe cw = Fd::mul(c, ld_fe(a.W, a.in2[g]));
+            if (a.ops[g]) h1 = Fd::add(h1, cw);
+            else {
+                h1 = Fd::add(h1, c);
+                ha2 = Fd::add(ha2, cw);
+            }
+        }
+        st_fe(a.H1, b, h1);
+        st_fe(a.HA2, b, ha2);
+    }
+}
+struct GkrW2Args {
+    TabRef C, D, coef;
+    TabRef eu_hi, eu_lo;
+    int n_lo;
+    const uint8_t* ops;
+    const uint32_t *in1, *off2, *lst2;
+    uint64_t width;
+    Fe Wu;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_w_phase2(const GkrW2Args a) {
+    typedef Field<F> Fd;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t cc = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; cc < a.width; cc += step) {
+        Fe C = Fd::zero(), D = Fd::zero();
+        for (uint32_t e = a.off2[cc]; e < a.off2[cc + 1]; ++e) {
+            const uint32_t g = a.lst2[e];
+            const Fe v = Fd::mul(ld_fe(a.coef, g), eq_lookup<F>(a.eu_hi, a.eu_lo, a.n_lo, a.in1[g]));
+            const Fe wv = Fd::mul(a.Wu, v);
+            if (a.ops[g]) C = Fd::add(C, wv);
+            else {
+                C = Fd::add(C, v);
+                D = Fd::add(D, wv);
+            }
+        }
+        st_fe(a.C, cc, C);
+        st_fe(a.D, cc, D);
+    }
+}
+struct GkrWWiringArgs {
+    WiredCoef wc;
+    TabRef eu_hi, eu_lo, ew_hi, ew_lo;
+    int n_lo_w;
+    const uint8_t* ops;
+    const uint32_t *in1, *in2;
+    uint64_t n_gates;
+    FinishArgs fin;
+};
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_w_wiring(const GkrWWiringArgs a) {
+    typedef Field<F> Fd;
+    Fe acc[2] = {Fd::zero(), Fd::zero()};
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.n_gates; g += step) {
+        const Fe c = wired_coef<F>(a.wc, g);
+        const Fe t = Fd::mul(c, Fd::mul(eq_lookup<F>(a.eu_hi, a.eu_lo, a.n_lo_w, a.in1[g]), eq_lookup<F>(a.ew_hi, a.ew_lo, a.n_lo_w, a.in2[g])));
+        if (a.ops[g]) acc[1] = Fd::add(acc[1], t);
+        else acc[0] = Fd::add(acc[0], t);
+    }
+    finish_round<F, 2>(acc, a.fin);
+}
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_layer_eval_w(TabRef in, TabRef out, const uint8_t* __restrict__ ops, const uint32_t* __restrict__ in1,
+                                                       const uint32_t* __restrict__ in2, uint64_t n_gates) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < n_gates; g += step) {
+        Fe x = ld_fe(in, in1[g]), y = ld_fe(in, in2[g]);
+        st_fe(out, g, ops[g] ? Field<F>::mul(x, y) : Field<F>::add(x, y));
+    }
+}
+
 // Element `idx` of each listed table -> out[t] (final bound values, openings).
 struct GatherArgs {
     TabRef t[MAXT];

@@ -121,6 +121,12 @@ struct CircuitState {
     SumPolyState sp;          // the XYZ sumcheck state (work tables reused across layers)
     void* aos_stage = nullptr;
     size_t aos_stage_bytes = 0;
+    // general wiring (zkb_circuit_create_wired; an extension beyond the reference's fixed (2i, 2i+1) wiring)
+    bool wired = false;
+    uint64_t n_inputs = 0;
+    std::vector<uint64_t> width;  // wires below each layer
+    std::vector<size_t> csroff;   // offset of each layer's CSR row pointers (width + 1 each)
+    uint32_t *d_in1 = nullptr, *d_in2 = nullptr, *d_lst1 = nullptr, *d_lst2 = nullptr, *d_off1 = nullptr, *d_off2 = nullptr;
 };
 }  // namespace
 
@@ -1187,7 +1193,10 @@ int32_t circuit_check_shape(zkb_ctx* c, uint32_t n_layers, const uint32_t* g) {
 }
 
 int32_t circuit_run(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont, uint64_t n_inputs) {
-    if (n_inputs != 2ull * cs->gates[0]) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: inputs must be 2 x gates of the first layer");
+    if (cs->wired) {
+        if (n_inputs != cs->n_inputs) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: wrong number of inputs");
+    } else if (n_inputs != 2ull * cs->gates[0])
+        ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: inputs must be 2 x gates of the first layer");
     // inputs: AoS Montgomery -> planar
     if (cs->aos_stage_bytes < n_inputs * 32) {
         if (cs->aos_stage) cudaFreeAsync(cs->aos_stage, c->stream);
@@ -1199,6 +1208,12 @@ int32_t circuit_run(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont, u
     ZK_TRY(check_launch(c, "k_aos_to_planar"));
     for (int l = 0; l < cs->L; ++l) {
         const Table& in = l == 0 ? cs->inputs : cs->vals[l - 1];
+        if (cs->wired) {
+            c->K->layer_eval_w(in.ref(), cs->vals[l].ref(), cs->d_ops + cs->opoff[l], cs->d_in1 + cs->opoff[l], cs->d_in2 + cs->opoff[l],
+                               cs->gates[l], grid_for(c, cs->gates[l], 8), c->stream);
+            ZK_TRY(check_launch(c, "k_layer_eval_w"));
+            continue;
+        }
         c->K->layer_eval(in.ref(), cs->vals[l].ref(), cs->d_ops + cs->opoff[l], cs->gates[l], grid_for(c, cs->gates[l], 8), c->stream);
         ZK_TRY(check_launch(c, "k_layer_eval"));
     }
@@ -1327,6 +1342,136 @@ int32_t gkr_prove_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont
         prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * (double)G * 5.0);
         c->K->gkr_phase2(p2, grid_for(c, G, 8), c->stream);
         ZK_TRY(check_launch(c, "k_gkr_phase2"));
+        ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + (round_base + nb) * 12, lens + round_base + nb,
+                         challenges ? challenges + (round_base + nb) * 4 : nullptr, v.data(), &Wv));
+        round_base += 2 * (size_t)nb;
+        rb = u;
+        rc = v;
+        o1 = Wu;
+        o2 = Wv;
+        if (idx < L - 1) {  // :80-89
+            tr.append_elements(&o1, 1);
+            alpha = tr.challenge();
+            tr.append_elements(&o2, 1);
+            beta = tr.challenge();
+            fe_to_u64x4(o1, claimed + (size_t)idx * 8);
+            fe_to_u64x4(o2, claimed + (size_t)idx * 8 + 4);
+        }
+    }
+    fe_to_u64x4(o1, final_openings);
+    fe_to_u64x4(o2, final_openings + 4);
+    if (n_rounds_out) *n_rounds_out = (uint32_t)round_base;
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------ general wiring (extension)
+// The reference fixes gate i's inputs to wires (2i, 2i+1) (gkr_circuit.rs:76-78,132), which forces every layer to
+// be half as wide as the one below and the output layer to 1-2 gates.  BASELINE configs[2] ("2^20 gates per layer
+// and 16 layers") needs arbitrary wiring in1[g], in2[g] and a wide output layer; the protocol is the reference's
+// (same transcript order, same round polynomials, claim merge and openings), with the single output challenge
+// r0 replaced by log2(outputs) consecutive challenges.  With in1 = 2g, in2 = 2g+1 and <= 2 outputs this path
+// produces the bytes of gkr_prove_impl (asserted in tests/test_gpu_parity.py).
+void wired_coef_args(CircuitState* cs, int idx, const Fe& alpha, const Fe& beta, int n_lo, WiredCoef* wc) {
+    std::memset(wc, 0, sizeof *wc);
+    wc->a1_hi = cs->eq[0].ref();
+    wc->a1_lo = cs->eq[1].ref();
+    wc->a2_hi = cs->eq[2].ref();
+    wc->a2_lo = cs->eq[3].ref();
+    wc->n_lo = n_lo;
+    wc->two = idx > 0;
+    wc->alpha = alpha;
+    wc->beta = beta;
+}
+
+int32_t gkr_prove_wired_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* inputs_mont, uint64_t n_inputs, uint64_t* w0_out,
+                             uint64_t* coeffs, int32_t* lens, uint64_t* challenges, uint64_t* claimed, uint64_t* final_openings,
+                             uint32_t* n_rounds_out) {
+    ZK_TRY(circuit_run(c, cs, inputs_mont, n_inputs));
+    const int L = cs->L;
+    const HostField& H = c->H;
+    TranscriptImpl tr;
+    tr.H = H;
+    // initiate_protocol (:229-241) with one challenge per output variable
+    const uint64_t Gout = cs->gates[L - 1], n0 = Gout < 2 ? 2 : Gout;
+    const int k0 = ilog2_u64(n0);
+    std::vector<Fe> r0(k0);
+    Fe m0;
+    if (Gout == 1) {
+        Fe w0[2] = {H.zero(), H.zero()};
+        ZK_TRY(read_elems(c, cs->vals[L - 1], 0, 1, w0));
+        fe_to_u64x4(w0[0], w0_out);
+        fe_to_u64x4(w0[1], w0_out + 4);
+        tr.append_elements(w0, 2);
+        r0[0] = tr.challenge();
+        m0 = H.add(w0[0], H.mul(r0[0], H.sub(w0[1], w0[0])));
+    } else {
+        ZK_TRY(download_aos(c, cs->vals[L - 1], w0_out, 0));
+        std::vector<Fe> buf(Gout < 4096 ? Gout : 4096);
+        for (uint64_t i = 0; i < Gout; i += 4096) {  // canonical bytes in bounded pieces
+            const uint64_t m = Gout - i < 4096 ? Gout - i : 4096;
+            for (uint64_t j = 0; j < m; ++j) buf[j] = fe_from_u64x4(w0_out + (i + j) * 4);
+            tr.append_elements(buf.data(), (size_t)m);
+        }
+        for (int i = 0; i < k0; ++i) r0[i] = tr.challenge();
+        ZK_TRY(evaluate_table(c, cs->vals[L - 1], r0.data(), (uint32_t)k0, &m0));
+    }
+    tr.append_elements(&m0, 1);
+
+    Fe alpha = H.zero(), beta = H.zero();
+    std::vector<Fe> rb, rc;
+    size_t round_base = 0;
+    Fe o1 = H.zero(), o2 = H.zero();
+    for (int idx = 0; idx < L; ++idx) {
+        const int l = L - 1 - idx;
+        const uint64_t G = cs->gates[l], nw = cs->width[l];
+        const int nb = ilog2_u64(nw);
+        const Table& W = l == 0 ? cs->inputs : cs->vals[l - 1];
+        int n_lo = 0;
+        if (idx == 0) {
+            ZK_TRY(eq_tables(c, r0.data(), k0, &cs->eq[0], &cs->eq[1], &n_lo));
+        } else {
+            if ((1ull << rb.size()) != G) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "gkr: challenge count does not match the layer width");
+            ZK_TRY(eq_tables(c, rb.data(), (int)rb.size(), &cs->eq[0], &cs->eq[1], &n_lo));
+            ZK_TRY(eq_tables(c, rc.data(), (int)rc.size(), &cs->eq[2], &cs->eq[3], &n_lo));
+        }
+        GkrW1Args p1;
+        std::memset(&p1, 0, sizeof p1);
+        p1.W = W.ref();
+        p1.H1 = cs->H1.ref();
+        p1.HA2 = cs->HA2.ref();
+        p1.coef = cs->coef.ref();
+        wired_coef_args(cs, idx, alpha, beta, n_lo, &p1.wc);
+        p1.ops = cs->d_ops + cs->opoff[l];
+        p1.in2 = cs->d_in2 + cs->opoff[l];
+        p1.off1 = cs->d_off1 + cs->csroff[l];
+        p1.lst1 = cs->d_lst1 + cs->opoff[l];
+        p1.width = nw;
+        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * ((double)G * 3.0 + (double)nw * 2.0));
+        c->K->gkr_w_phase1(p1, grid_for(c, nw, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_gkr_w_phase1"));
+        std::vector<Fe> u(nb), v(nb);
+        Fe Wu, Wv;
+        ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + round_base * 12, lens + round_base,
+                         challenges ? challenges + round_base * 4 : nullptr, u.data(), &Wu));
+        int n_lo_u = 0;
+        ZK_TRY(eq_tables(c, u.data(), nb, &cs->eq[4], &cs->eq[5], &n_lo_u));
+        GkrW2Args p2;
+        std::memset(&p2, 0, sizeof p2);
+        p2.C = cs->H1.ref();
+        p2.D = cs->HA2.ref();
+        p2.coef = cs->coef.ref();
+        p2.eu_hi = cs->eq[4].ref();
+        p2.eu_lo = cs->eq[5].ref();
+        p2.n_lo = n_lo_u;
+        p2.ops = cs->d_ops + cs->opoff[l];
+        p2.in1 = cs->d_in1 + cs->opoff[l];
+        p2.off2 = cs->d_off2 + cs->csroff[l];
+        p2.lst2 = cs->d_lst2 + cs->opoff[l];
+        p2.width = nw;
+        p2.Wu = Wu;
+        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * ((double)G * 2.0 + (double)nw * 2.0));
+        c->K->gkr_w_phase2(p2, grid_for(c, nw, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_gkr_w_phase2"));
         ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + (round_base + nb) * 12, lens + round_base + nb,
                          challenges ? challenges + (round_base + nb) * 4 : nullptr, v.data(), &Wv));
         round_base += 2 * (size_t)nb;
@@ -2073,6 +2218,8 @@ int32_t zkb_circuit_free(zkb_ctx* c, zkb_circ h) {
     free_table(c, &cs->coef);
     for (auto& t : cs->eq) free_table(c, &t);
     if (cs->d_ops) cudaFreeAsync(cs->d_ops, c->stream);
+    for (uint32_t* q : {cs->d_in1, cs->d_in2, cs->d_lst1, cs->d_lst2, cs->d_off1, cs->d_off2})
+        if (q) cudaFreeAsync(q, c->stream);
     if (cs->aos_stage) cudaFreeAsync(cs->aos_stage, c->stream);
     c->circs.erase(it);
     return ZKB_OK;
@@ -2214,6 +2361,226 @@ int32_t zkb_gkr_verify(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t 
         prb = u;
         prc = w;
         tr.append_elements(&o1, 1);  // :217-221 (the verifier absorbs after every layer)
+        alpha = tr.challenge();
+        tr.append_elements(&o2, 1);
+        beta = tr.challenge();
+        claim = H.add(H.mul(alpha, o1), H.mul(beta, o2));
+    }
+    free_table(c, &in_tab);
+    if (st != ZKB_OK) return st;
+    *accepted = ok ? 1 : 0;
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------ general wiring (extension beyond the reference)
+int32_t zkb_circuit_create_wired(zkb_ctx* c, uint32_t n_layers, const uint32_t* gates, uint64_t n_inputs, const uint8_t* ops,
+                                 const uint32_t* in1, const uint32_t* in2, zkb_circ* out) {
+    if (!c || !gates || !ops || !in1 || !in2 || !out) return ZKB_ERR_BAD_ARG;
+    if (n_layers < 1) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: no layers");
+    if (!is_pow2(n_inputs) || n_inputs < 2 || n_inputs > (1ull << 30)) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: the input count must be a power of two in [2, 2^30]");
+    std::unique_ptr<CircuitState> cs(new CircuitState);
+    cs->wired = true;
+    cs->L = (int)n_layers;
+    cs->n_inputs = n_inputs;
+    cs->gates.assign(gates, gates + n_layers);
+    size_t tot = 0, csr = 0;
+    uint64_t wmax = n_inputs, gmax = 1;
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        const uint64_t w = l == 0 ? n_inputs : gates[l - 1];
+        if (!is_pow2(gates[l]) || gates[l] > (1u << 30)) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: gates per layer must be a power of two");
+        if (w < 2) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: only the output layer may have a single gate");
+        cs->width.push_back(w);
+        cs->opoff.push_back(tot);
+        cs->csroff.push_back(csr);
+        tot += gates[l];
+        csr += (size_t)w + 1;
+        if (w > wmax) wmax = w;
+        if (gates[l] > gmax) gmax = gates[l];
+    }
+    cs->h_ops.assign(ops, ops + tot);
+    // CSR lists of the gates by first / second input (counting sort; gate order kept inside a row)
+    std::vector<uint32_t> off1(csr, 0), off2(csr, 0), lst1(tot), lst2(tot);
+    for (uint32_t l = 0; l < n_layers; ++l) {
+        const uint64_t w = cs->width[l];
+        const size_t go = cs->opoff[l], co = cs->csroff[l];
+        for (uint32_t g = 0; g < gates[l]; ++g) {
+            if (ops[go + g] != ZKB_OP_ADD && ops[go + g] != ZKB_OP_MUL) return ZKB_ERR_BAD_ARG;
+            if (in1[go + g] >= w || in2[go + g] >= w) ZK_FAIL(c, ZKB_ERR_CIRCUIT_SHAPE, "circuit: wire index out of range");
+            ++off1[co + in1[go + g] + 1];
+            ++off2[co + in2[go + g] + 1];
+        }
+        for (uint64_t b = 0; b < w; ++b) {
+            off1[co + b + 1] += off1[co + b];
+            off2[co + b + 1] += off2[co + b];
+        }
+        std::vector<uint32_t> p1(off1.begin() + co, off1.begin() + co + w), p2(off2.begin() + co, off2.begin() + co + w);
+        for (uint32_t g = 0; g < gates[l]; ++g) {
+            lst1[go + p1[in1[go + g]]++] = g;
+            lst2[go + p2[in2[go + g]]++] = g;
+        }
+    }
+    auto put = [&](const void* src, size_t bytes, void** dst) -> int32_t {
+        ZK_CUDA(c, cudaMallocAsync(dst, bytes, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return ZKB_OK;
+    };
+    ZK_TRY(put(cs->h_ops.data(), tot, (void**)&cs->d_ops));
+    ZK_TRY(put(in1, tot * 4, (void**)&cs->d_in1));
+    ZK_TRY(put(in2, tot * 4, (void**)&cs->d_in2));
+    ZK_TRY(put(lst1.data(), tot * 4, (void**)&cs->d_lst1));
+    ZK_TRY(put(lst2.data(), tot * 4, (void**)&cs->d_lst2));
+    ZK_TRY(put(off1.data(), csr * 4, (void**)&cs->d_off1));
+    ZK_TRY(put(off2.data(), csr * 4, (void**)&cs->d_off2));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    ZK_TRY(alloc_table(c, n_inputs, &cs->inputs));
+    cs->vals.resize(n_layers);
+    for (uint32_t l = 0; l < n_layers; ++l) ZK_TRY(alloc_table(c, gates[l], &cs->vals[l]));
+    ZK_TRY(alloc_table(c, wmax, &cs->H1));
+    ZK_TRY(alloc_table(c, wmax, &cs->HA2));
+    ZK_TRY(alloc_table(c, gmax, &cs->coef));
+    const int nmax = ilog2_u64(wmax > gmax ? wmax : gmax);
+    for (auto& t : cs->eq) ZK_TRY(alloc_table(c, 1ull << ((nmax + 1) / 2 + 1), &t));
+    ZK_TRY(sp_configure(c, &cs->sp, 1, 3, KIND_XYZ));
+    cs->sp.work.resize(3);
+    for (auto& t : cs->sp.work) ZK_TRY(alloc_table(c, wmax / 2, &t));
+    zkb_circ h = c->next_handle++;
+    c->circs[h] = std::move(cs);
+    *out = h;
+    return ZKB_OK;
+}
+
+int32_t zkb_circuit_total_rounds(zkb_ctx* c, zkb_circ h, uint32_t* n_rounds) {
+    if (!c || !n_rounds) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end()) return ZKB_ERR_BAD_ARG;
+    CircuitState* cs = it->second.get();
+    uint32_t tot = 0;
+    for (int l = 0; l < cs->L; ++l) tot += cs->wired ? 2u * (uint32_t)ilog2_u64(cs->width[l]) : layer_rounds(cs->gates[l]);
+    *n_rounds = tot;
+    return ZKB_OK;
+}
+
+int32_t zkb_gkr_prove_wired(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t n_inputs, uint64_t* w0, uint64_t n_w0,
+                            uint64_t* coeffs, int32_t* lens, uint64_t* challenges, uint64_t* claimed, uint64_t final_openings[8],
+                            uint32_t* n_rounds) {
+    if (!c || !inputs || !w0 || !coeffs || !lens || !final_openings) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end() || !it->second->wired) return ZKB_ERR_BAD_ARG;
+    CircuitState* cs = it->second.get();
+    if (cs->L > 1 && !claimed) return ZKB_ERR_BAD_ARG;
+    const uint64_t Gout = cs->gates[cs->L - 1];
+    if (n_w0 != (Gout < 2 ? 2 : Gout)) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "gkr: w0 must hold max(outputs, 2) elements");
+    return gkr_prove_wired_impl(c, cs, inputs, n_inputs, w0, coeffs, lens, challenges, claimed, final_openings, n_rounds);
+}
+
+int32_t zkb_gkr_verify_wired(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t n_inputs, const uint64_t* w0_in, uint64_t n_w0,
+                             const uint64_t* coeffs, const int32_t* lens, const uint64_t* claimed, const uint64_t final_openings[8],
+                             int32_t* accepted) {
+    if (!c || !inputs || !w0_in || !coeffs || !lens || !final_openings || !accepted) return ZKB_ERR_BAD_ARG;
+    auto it = c->circs.find(h);
+    if (it == c->circs.end() || !it->second->wired) return ZKB_ERR_BAD_ARG;
+    CircuitState* cs = it->second.get();
+    *accepted = 0;
+    const int L = cs->L;
+    if (n_inputs != cs->n_inputs) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: wrong number of inputs");
+    const uint64_t Gout = cs->gates[L - 1], n0 = Gout < 2 ? 2 : Gout;
+    if (n_w0 != n0) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "gkr: w0 must hold max(outputs, 2) elements");
+    if (L > 1 && !claimed) return ZKB_ERR_BAD_ARG;
+    const HostField& H = c->H;
+    TranscriptImpl tr;
+    tr.H = H;
+    const int k0 = ilog2_u64(n0);
+    std::vector<Fe> r0(k0);
+    Fe claim;
+    {
+        std::vector<Fe> w0(n0);
+        for (uint64_t i = 0; i < n0; ++i) w0[i] = fe_from_u64x4(w0_in + i * 4);
+        tr.append_elements(w0.data(), (size_t)n0);
+        for (int i = 0; i < k0; ++i) r0[i] = tr.challenge();
+        if (n0 <= 4096) {
+            for (int i = 0; i < k0; ++i) {
+                const size_t hlf = w0.size() / 2;
+                for (size_t j = 0; j < hlf; ++j) w0[j] = H.add(w0[j], H.mul(r0[i], H.sub(w0[j + hlf], w0[j])));
+                w0.resize(hlf);
+            }
+            claim = w0[0];
+        } else {
+            Table t0;
+            ZK_TRY(upload_aos(c, w0_in, n0, 0, 1, n0, 0, &t0));
+            int32_t st0 = evaluate_table(c, t0, r0.data(), (uint32_t)k0, &claim);
+            free_table(c, &t0);
+            ZK_TRY(st0);
+        }
+    }
+    tr.append_elements(&claim, 1);
+    Table in_tab;
+    ZK_TRY(upload_aos(c, inputs, n_inputs, 0, 1, n_inputs, 0, &in_tab));
+    Fe alpha = H.zero(), beta = H.zero();
+    std::vector<Fe> prb, prc;
+    size_t round_base = 0;
+    int32_t st = ZKB_OK;
+    bool ok = true;
+    for (int idx = 0; idx < L && ok && st == ZKB_OK; ++idx) {
+        const int l = L - 1 - idx;
+        const uint64_t G = cs->gates[l], nw = cs->width[l];
+        const int nb = ilog2_u64(nw);
+        const uint32_t nr = 2 * (uint32_t)nb;
+        std::vector<Fe> cur(nr);
+        Fe fin;
+        for (uint32_t k = 0; k < nr; ++k)
+            if (lens[round_base + k] < 0 || lens[round_base + k] > 3) { ok = false; break; }
+        if (!ok) break;
+        if (!sc_verify_rounds(H, &tr, nr, 3, coeffs + round_base * 12, lens + round_base, claim, &fin, cur.data())) { ok = false; break; }
+        round_base += nr;
+        std::vector<Fe> u(cur.begin(), cur.begin() + nb), w(cur.begin() + nb, cur.end());
+        Fe o1, o2;
+        if (idx == L - 1) {
+            st = evaluate_table(c, in_tab, u.data(), (uint32_t)nb, &o1);
+            if (st == ZKB_OK) st = evaluate_table(c, in_tab, w.data(), (uint32_t)nb, &o2);
+            if (st != ZKB_OK) break;
+            if (!H.eq(o1, fe_from_u64x4(final_openings)) || !H.eq(o2, fe_from_u64x4(final_openings + 4))) { ok = false; break; }
+        } else {
+            o1 = fe_from_u64x4(claimed + (size_t)idx * 8);
+            o2 = fe_from_u64x4(claimed + (size_t)idx * 8 + 4);
+        }
+        GkrWWiringArgs wa;
+        std::memset(&wa, 0, sizeof wa);
+        int n_lo = 0;
+        if (idx == 0) {
+            st = eq_tables(c, r0.data(), k0, &cs->eq[0], &cs->eq[1], &n_lo);
+        } else {
+            if ((1ull << prb.size()) != G) { ok = false; break; }
+            st = eq_tables(c, prb.data(), (int)prb.size(), &cs->eq[0], &cs->eq[1], &n_lo);
+            if (st == ZKB_OK) st = eq_tables(c, prc.data(), (int)prc.size(), &cs->eq[2], &cs->eq[3], &n_lo);
+        }
+        if (st != ZKB_OK) break;
+        wired_coef_args(cs, idx, alpha, beta, n_lo, &wa.wc);
+        st = eq_tables(c, u.data(), nb, &cs->eq[4], &cs->eq[5], &n_lo);
+        if (st == ZKB_OK) st = eq_tables(c, w.data(), nb, &cs->eq[6], &cs->eq[7], &n_lo);
+        if (st != ZKB_OK) break;
+        wa.eu_hi = cs->eq[4].ref();
+        wa.eu_lo = cs->eq[5].ref();
+        wa.ew_hi = cs->eq[6].ref();
+        wa.ew_lo = cs->eq[7].ref();
+        wa.n_lo_w = n_lo;
+        wa.ops = cs->d_ops + cs->opoff[l];
+        wa.in1 = cs->d_in1 + cs->opoff[l];
+        wa.in2 = cs->d_in2 + cs->opoff[l];
+        wa.n_gates = G;
+        const int grid = grid_for(c, G, 4);
+        st = prep_finish(c, grid, 2, false, &wa.fin);
+        if (st != ZKB_OK) break;
+        c->K->gkr_w_wiring(wa, grid, c->stream);
+        st = check_launch(c, "k_gkr_w_wiring");
+        if (st != ZKB_OK) break;
+        Fe am[2];
+        st = collect(c, 2, false, wa.fin, am);
+        if (st != ZKB_OK) break;
+        Fe expected = H.add(H.mul(am[0], H.add(o1, o2)), H.mul(am[1], H.mul(o1, o2)));  // :211,313,340
+        if (!H.eq(expected, fin)) { ok = false; break; }
+        prb = u;
+        prc = w;
+        tr.append_elements(&o1, 1);
         alpha = tr.challenge();
         tr.append_elements(&o2, 1);
         beta = tr.challenge();

@@ -121,6 +121,10 @@ def lib() -> C.CDLL:
         "zkb_gkr_prove": (i32, [vp, u64, vp, u64, u64p, u64p, i32p, u64p, u64p, u64p, u32p]),
         "zkb_gkr_verify": (i32, [vp, u64, vp, u64, u64p, u64p, i32p, u64p, u64p, i32p]),
         "zkb_gkr_total_rounds": (u32, [u32, u32p]),
+        "zkb_circuit_create_wired": (i32, [vp, u32, u32p, u64, u8p, u32p, u32p, u64p]),
+        "zkb_circuit_total_rounds": (i32, [vp, u64, u32p]),
+        "zkb_gkr_prove_wired": (i32, [vp, u64, vp, u64, u64p, u64, u64p, i32p, u64p, u64p, u64p, u32p]),
+        "zkb_gkr_verify_wired": (i32, [vp, u64, vp, u64, u64p, u64, u64p, i32p, u64p, u64p, i32p]),
         "zkb_bench_modmul": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
         "zkb_bench_imad": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
     }

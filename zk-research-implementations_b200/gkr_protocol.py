@@ -14,7 +14,7 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from .engine import _ck, _p, lib
-from .gkr_circuit import Circuit, Layer
+from .gkr_circuit import Circuit, Layer, WiredCircuit
 from .multilinear_polynomial import MultilinearPoly, Operation, ProductPoly, SumPoly
 from .univariate_polynomial import UnivariatePoly
 
@@ -184,3 +184,73 @@ def verify(proof: GkrProof, circuit: Circuit, inputs: Sequence[int]) -> bool:  #
                                   _p(coeffs), lens.ctypes.data_as(i32p), _p(claimed), _p(ctx.mont(list(proof.final_openings))),
                                   C.byref(ok)))
     return bool(ok.value)
+
+
+# ------------------------------------------------- general wiring (extension beyond the reference, zkb200.h)
+class RawWiredGkrProver:
+    """The bare zkb_gkr_prove_wired call on a host array of Montgomery limbs, outputs preallocated."""
+
+    def __init__(self, circuit: WiredCircuit, inputs_mont: np.ndarray):
+        self.circuit, self.ctx = circuit, circuit.ctx
+        self.inputs = np.ascontiguousarray(inputs_mont, dtype=np.uint64)
+        self.total, L = circuit.total_rounds, len(circuit.gates)
+        self.w0 = np.zeros((circuit.n_w0, 4), dtype=np.uint64)
+        self.coeffs = np.zeros((self.total, 3, 4), dtype=np.uint64)
+        self.lens = np.zeros(self.total, dtype=np.int32)
+        self.chals = np.zeros((self.total, 4), dtype=np.uint64)
+        self.claimed = np.zeros((max(L - 1, 1), 2, 4), dtype=np.uint64)
+        self.fin = np.zeros((2, 4), dtype=np.uint64)
+        self.nr = C.c_uint32()
+
+    def prove(self) -> None:
+        ctx = self.ctx
+        _ck(ctx, lib().zkb_gkr_prove_wired(ctx.handle, self.circuit.handle, self.inputs.ctypes.data, self.inputs.shape[0], _p(self.w0),
+                                           self.w0.shape[0], _p(self.coeffs), self.lens.ctypes.data_as(i32p), _p(self.chals),
+                                           _p(self.claimed), _p(self.fin), C.byref(self.nr)))
+
+    def verify(self) -> bool:
+        ctx = self.ctx
+        ok = C.c_int32()
+        _ck(ctx, lib().zkb_gkr_verify_wired(ctx.handle, self.circuit.handle, self.inputs.ctypes.data, self.inputs.shape[0], _p(self.w0),
+                                            self.w0.shape[0], _p(self.coeffs), self.lens.ctypes.data_as(i32p), _p(self.claimed),
+                                            _p(self.fin), C.byref(ok)))
+        return bool(ok.value)
+
+
+def prove_wired(circuit: WiredCircuit, inputs: Sequence[int]) -> GkrProof:
+    ctx = circuit.ctx
+    raw = RawWiredGkrProver(circuit, ctx.mont(inputs))
+    raw.prove()
+    assert raw.nr.value == raw.total
+    L = len(circuit.gates)
+    polys, ch, off = [], [], 0
+    for n in circuit.rounds_per_layer:
+        polys.append([UnivariatePoly(ctx.unmont(raw.coeffs[off + k, : raw.lens[off + k]]), ctx.field) for k in range(n)])
+        ch.append(ctx.unmont(raw.chals[off: off + n]))
+        off += n
+    ce = ctx.unmont(raw.claimed[: L - 1].reshape(-1, 4)) if L > 1 else []
+    return GkrProof(ctx.unmont(raw.w0), polys, [(ce[2 * i], ce[2 * i + 1]) for i in range(L - 1)], tuple(ctx.unmont(raw.fin)), ch)
+
+
+def verify_wired(proof: GkrProof, circuit: WiredCircuit, inputs: Sequence[int]) -> bool:
+    ctx = circuit.ctx
+    rpl, total, L = circuit.rounds_per_layer, circuit.total_rounds, len(circuit.gates)
+    if len(proof.proof_polynomials) != L or [len(x) for x in proof.proof_polynomials] != rpl:
+        return False
+    if len(proof.claimed_evaluations) != L - 1 or len(proof.output_poly) != circuit.n_w0:
+        return False
+    raw = RawWiredGkrProver(circuit, ctx.mont(inputs))
+    k = 0
+    for layer in proof.proof_polynomials:
+        for q in layer:
+            if len(q.coefficients) > 3:
+                return False
+            raw.lens[k] = len(q.coefficients)
+            if q.coefficients:
+                raw.coeffs[k, : raw.lens[k]] = ctx.mont(q.coefficients)
+            k += 1
+    if L > 1:
+        raw.claimed[: L - 1] = ctx.mont([x for pr in proof.claimed_evaluations for x in pr]).reshape(L - 1, 2, 4)
+    raw.w0[:] = ctx.mont(proof.output_poly)
+    raw.fin[:] = ctx.mont(list(proof.final_openings))
+    return raw.verify()
