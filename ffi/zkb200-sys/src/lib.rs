@@ -101,6 +101,11 @@ extern "C" {
     pub fn zkb_gkr_prove(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *mut u64, coeffs: *mut u64, lens: *mut i32, challenges: *mut u64, claimed: *mut u64, final_openings: *mut u64, n_rounds: *mut u32) -> i32;
     pub fn zkb_gkr_verify(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *const u64, coeffs: *const u64, lens: *const i32, claimed: *const u64, final_openings: *const u64, accepted: *mut i32) -> i32;
     pub fn zkb_gkr_total_rounds(n_layers: u32, gates_per_layer: *const u32) -> u32;
+    // general wiring (extension beyond the reference's fixed (2i, 2i+1) wiring; zkb200.h)
+    pub fn zkb_circuit_create_wired(ctx: *mut zkb_ctx, n_layers: u32, gates_per_layer: *const u32, n_inputs: u64, ops: *const u8, in1: *const u32, in2: *const u32, out: *mut zkb_circ) -> i32;
+    pub fn zkb_circuit_total_rounds(ctx: *mut zkb_ctx, c: zkb_circ, n_rounds: *mut u32) -> i32;
+    pub fn zkb_gkr_prove_wired(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *mut u64, n_w0: u64, coeffs: *mut u64, lens: *mut i32, challenges: *mut u64, claimed: *mut u64, final_openings: *mut u64, n_rounds: *mut u32) -> i32;
+    pub fn zkb_gkr_verify_wired(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *const u64, n_w0: u64, coeffs: *const u64, lens: *const i32, claimed: *const u64, final_openings: *const u64, accepted: *mut i32) -> i32;
 
     pub fn zkb_bench_modmul(ctx: *mut zkb_ctx, variant: i32, iters: u32, modmuls_per_s: *mut f64) -> i32;
     pub fn zkb_bench_imad(ctx: *mut zkb_ctx, mode: i32, iters: u32, ops_per_s: *mut f64) -> i32;

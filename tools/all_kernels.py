@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""One pass over EVERY kernel of the engine at a representative size, for Nsight Compute (north star: "ncu evidence
+for every kernel").  The persistent kernels cannot run under ncu (launches are synchronous there, so a kernel that
+waits for the host would never be answered): the engine detects ncu and launches the same round_pass device code once
+per round (k_sc_fold_eval), which is what this script's capture shows.  `--kernel-id ::regex:^k_:1` keeps the first
+(largest) launch of each instantiation.  Numbers printed by a run under ncu are not bench values."""
+import ctypes as C, importlib, os, random, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+z = importlib.import_module("zk-research-implementations_b200")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+p = z.engine.MODULI[0]
+rng = random.Random(1)
+S, T = z.sum_check_protocol, z.fiat_shamir.Transcript
+GKR_ONLY = os.environ.get("ALLK_GKR_ONLY") == "1"
+for mode, shapes in () if GKR_ONLY else ((z.MODE_FULL, [(1, 1), (1, 2), (1, 3), (2, 3), (1, 4)]), (z.MODE_COMPAT, [(2, 2)])):
+    ctx = z.Context(z.BN254_FR, 0, mode)
+    ctx.set_tail_threshold(0)
+    ctx.set_small_threshold(0)
+    for P_, D_ in shapes:
+        tabs = [z.MultilinearPoly.generate(ctx, 5, t, n) for t in range(P_ * D_)]
+        sp = z.SumPoly(ctx, [z.ProductPoly.from_polys(ctx, tabs[q * D_:(q + 1) * D_]) for q in range(P_)])
+        raw = S.RawGkrProver(sp)
+        raw.prove(T(z.BN254_FR))
+        sp.free()
+        for t in tabs:
+            t.free()
+    if mode == z.MODE_FULL:
+        # MultilinearPoly: partial_evaluate (bit 0 and an inner bit), evaluate, multi_partial_evaluate, + - *, scale, tensor
+        a, b = z.MultilinearPoly.generate(ctx, 6, 0, n), z.MultilinearPoly.generate(ctx, 6, 1, n)
+        r = rng.randrange(p)
+        a.partial_evaluate(0, r).free()
+        a.partial_evaluate(3, r).free()
+        a.evaluate([rng.randrange(p) for _ in range(n)])
+        a.multi_partial_evaluate([rng.randrange(p) for _ in range(4)]).free()
+        (a + b).free()
+        (a * b).free()
+        a.scale(r).free()
+        s1, s2 = z.MultilinearPoly.generate(ctx, 6, 2, n // 2), z.MultilinearPoly.generate(ctx, 6, 3, n // 2)
+        z.MultilinearPoly.tensor_add_mul_polynomials(s1, s2, z.Operation.Mul).free()
+        S.prove(a)  # plain sumcheck (absorbs the table)
+        for t in (a, b, s1, s2):
+            t.free()
+    ctx.close()
+# GKR: reference wiring (tree) and general wiring, both on 2^(n-2)-wide layers, then the verifiers
+ctx = z.Context(z.BN254_FR, 0, z.MODE_COMPAT)
+ctx.set_tail_threshold(0)
+ctx.set_small_threshold(0)
+g = n - 2
+nrng = np.random.default_rng(3)
+tree = z.gkr_circuit.Circuit(ctx, [[z.Operation(int(o)) for o in nrng.integers(0, 2, size=1 << (g - 1 - l))] for l in range(g)])
+inp = ctx.mont([rng.randrange(p) for _ in range(8)] * (1 << (g - 3)))
+pr = z.gkr_protocol.RawGkrProver(tree, inp)
+pr.prove()
+assert pr.verify()
+z.gkr_circuit.Circuit(ctx, [[z.Operation.Add] * 4, [z.Operation.Mul] * 2]).layers[0].get_add_mul_i(z.Operation.Add).free()
+G = 1 << g
+w = z.gkr_circuit.WiredCircuit(ctx, G, [(nrng.integers(0, 2, size=G, dtype=np.uint8), nrng.integers(0, G, size=G, dtype=np.uint32),
+                                         nrng.integers(0, G, size=G, dtype=np.uint32)) for _ in range(2)])
+wp = z.gkr_protocol.RawWiredGkrProver(w, inp[:G])
+wp.prove()
+assert wp.verify()
+ctx.close()
+print("all kernels launched")

@@ -1406,11 +1406,10 @@ int32_t gkr_prove_wired_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* input
         m0 = H.add(w0[0], H.mul(r0[0], H.sub(w0[1], w0[0])));
     } else {
         ZK_TRY(download_aos(c, cs->vals[L - 1], w0_out, 0));
-        std::vector<Fe> buf(Gout < 4096 ? Gout : 4096);
-        for (uint64_t i = 0; i < Gout; i += 4096) {  // canonical bytes in bounded pieces
-            const uint64_t m = Gout - i < 4096 ? Gout - i : 4096;
-            for (uint64_t j = 0; j < m; ++j) buf[j] = fe_from_u64x4(w0_out + (i + j) * 4);
-            tr.append_elements(buf.data(), (size_t)m);
+        {  // canonical bytes made on the device (fq_vec_to_bytes), hashed on the host
+            std::vector<uint8_t> bytes((size_t)Gout * 32);
+            ZK_TRY(download_aos(c, cs->vals[L - 1], bytes.data(), 2));
+            tr.append(bytes.data(), bytes.size());
         }
         for (int i = 0; i < k0; ++i) r0[i] = tr.challenge();
         ZK_TRY(evaluate_table(c, cs->vals[L - 1], r0.data(), (uint32_t)k0, &m0));
