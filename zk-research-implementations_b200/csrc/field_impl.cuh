@@ -133,8 +133,14 @@ void l_eq_split(const ChalList& r, int n, int n_hi, TabRef hi, TabRef lo, int gr
 void l_gkr_phase1(const GkrP1Args& a, int grid, cudaStream_t s) { k_gkr_phase1<FT><<<grid, BLOCK, 0, s>>>(a); }
 void l_gkr_phase2(const GkrP2Args& a, int grid, cudaStream_t s) { k_gkr_phase2<FT><<<grid, BLOCK, 0, s>>>(a); }
 void l_gkr_wiring(const GkrWiringArgs& a, int grid, cudaStream_t s) { k_gkr_wiring<FT><<<grid, BLOCK, 0, s>>>(a); }
-void l_gkr_w_phase1(const GkrW1Args& a, int grid, cudaStream_t s) { k_gkr_w_phase1<FT><<<grid, BLOCK, 0, s>>>(a); }
-void l_gkr_w_phase2(const GkrW2Args& a, int grid, cudaStream_t s) { k_gkr_w_phase2<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_gkr_w_phase1(const GkrW1Args& a, int grid_g, int grid_w, cudaStream_t s) {
+    k_gkr_w_gates1<FT><<<grid_g, BLOCK, 0, s>>>(a);
+    k_gkr_w_phase1<FT><<<grid_w, BLOCK, 0, s>>>(a);
+}
+void l_gkr_w_phase2(const GkrW2Args& a, int grid_g, int grid_w, cudaStream_t s) {
+    k_gkr_w_gates2<FT><<<grid_g, BLOCK, 0, s>>>(a);
+    k_gkr_w_phase2<FT><<<grid_w, BLOCK, 0, s>>>(a);
+}
 void l_gkr_w_wiring(const GkrWWiringArgs& a, int grid, cudaStream_t s) { k_gkr_w_wiring<FT><<<grid, BLOCK, 0, s>>>(a); }
 void l_layer_eval_w(TabRef in, TabRef out, const uint8_t* ops, const uint32_t* in1, const uint32_t* in2, uint64_t n_gates, int grid, cudaStream_t s) {
     k_layer_eval_w<FT><<<grid, BLOCK, 0, s>>>(in, out, ops, in1, in2, n_gates);

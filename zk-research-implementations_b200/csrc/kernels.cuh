@@ -1304,13 +1304,28 @@ __device__ __forceinline__ Fe wired_coef(const WiredCoef& w, uint64_t g) {
     Fe e2 = eq_lookup<F>(w.a2_hi, w.a2_lo, w.n_lo, g);
     return Fd::add(Fd::mul(w.alpha, e1), Fd::mul(w.beta, e2));
 }
+// Each phase is two launches so that the multiplications run one gate per thread (no divergence) and the
+// per-wire gather -- whose trip count varies with the wire's fan-out -- only adds:
+//   k_gkr_w_gates1: coef[g], tmp[g] = coef[g]*W[in2[g]]          k_gkr_w_phase1: H1, HA2 from coef/tmp via lst1
+//   k_gkr_w_gates2: tmp[g] = coef[g]*eq(u, in1[g])                k_gkr_w_phase2: sA, sM from tmp via lst2, then
+//                                                                  C = sA + W(u)*sM, D = W(u)*sA
 struct GkrW1Args {
-    TabRef W, H1, HA2, coef;
+    TabRef W, H1, HA2, coef, tmp;
     WiredCoef wc;
     const uint8_t* ops;
     const uint32_t *in2, *off1, *lst1;
-    uint64_t width;
+    uint64_t width, n_gates;
 };
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_w_gates1(const GkrW1Args a) {
+    typedef Field<F> Fd;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.n_gates; g += step) {
+        const Fe c = wired_coef<F>(a.wc, g);
+        st_fe(a.coef, g, c);
+        st_fe(a.tmp, g, Fd::mul(c, ld_fe(a.W, a.in2[g])));
+    }
+}
 template <class F>
 __global__ void __launch_bounds__(BLOCK) k_gkr_w_phase1(const GkrW1Args a) {
     typedef Field<F> Fd;
@@ -1319,12 +1334,10 @@ __global__ void __launch_bounds__(BLOCK) k_gkr_w_phase1(const GkrW1Args a) {
         Fe h1 = Fd::zero(), ha2 = Fd::zero();
         for (uint32_t e = a.off1[b]; e < a.off1[b + 1]; ++e) {
             const uint32_t g = a.lst1[e];
-            const Fe c = wired_coef<F>(a.wc, g);
-            st_fe(a.coef, g, c);
-            const Fe cw = Fd::mul(c, ld_fe(a.W, a.in2[g]));
+            const Fe cw = ld_fe(a.tmp, g);
             if (a.ops[g]) h1 = Fd::add(h1, cw);
             else {
-                h1 = Fd::add(h1, c);
+                h1 = Fd::add(h1, ld_fe(a.coef, g));
                 ha2 = Fd::add(ha2, cw);
             }
         }
@@ -1333,32 +1346,34 @@ __global__ void __launch_bounds__(BLOCK) k_gkr_w_phase1(const GkrW1Args a) {
     }
 }
 struct GkrW2Args {
-    TabRef C, D, coef;
+    TabRef C, D, coef, tmp;
     TabRef eu_hi, eu_lo;
     int n_lo;
     const uint8_t* ops;
     const uint32_t *in1, *off2, *lst2;
-    uint64_t width;
+    uint64_t width, n_gates;
     Fe Wu;
 };
+template <class F>
+__global__ void __launch_bounds__(BLOCK) k_gkr_w_gates2(const GkrW2Args a) {
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    for (uint64_t g = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; g < a.n_gates; g += step)
+        st_fe(a.tmp, g, Field<F>::mul(ld_fe(a.coef, g), eq_lookup<F>(a.eu_hi, a.eu_lo, a.n_lo, a.in1[g])));
+}
 template <class F>
 __global__ void __launch_bounds__(BLOCK) k_gkr_w_phase2(const GkrW2Args a) {
     typedef Field<F> Fd;
     const uint64_t step = (uint64_t)gridDim.x * BLOCK;
     for (uint64_t cc = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; cc < a.width; cc += step) {
-        Fe C = Fd::zero(), D = Fd::zero();
+        Fe sA = Fd::zero(), sM = Fd::zero();
         for (uint32_t e = a.off2[cc]; e < a.off2[cc + 1]; ++e) {
             const uint32_t g = a.lst2[e];
-            const Fe v = Fd::mul(ld_fe(a.coef, g), eq_lookup<F>(a.eu_hi, a.eu_lo, a.n_lo, a.in1[g]));
-            const Fe wv = Fd::mul(a.Wu, v);
-            if (a.ops[g]) C = Fd::add(C, wv);
-            else {
-                C = Fd::add(C, v);
-                D = Fd::add(D, wv);
-            }
+            const Fe v = ld_fe(a.tmp, g);
+            if (a.ops[g]) sM = Fd::add(sM, v);
+            else sA = Fd::add(sA, v);
         }
-        st_fe(a.C, cc, C);
-        st_fe(a.D, cc, D);
+        st_fe(a.C, cc, Fd::add(sA, Fd::mul(a.Wu, sM)));
+        st_fe(a.D, cc, Fd::mul(a.Wu, sA));
     }
 }
 struct GkrWWiringArgs {

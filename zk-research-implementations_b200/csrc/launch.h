@@ -36,8 +36,8 @@ struct FieldKernels {
     void (*gkr_phase1)(const GkrP1Args& a, int grid, cudaStream_t s);
     void (*gkr_phase2)(const GkrP2Args& a, int grid, cudaStream_t s);
     void (*gkr_wiring)(const GkrWiringArgs& a, int grid, cudaStream_t s);
-    void (*gkr_w_phase1)(const GkrW1Args& a, int grid, cudaStream_t s);
-    void (*gkr_w_phase2)(const GkrW2Args& a, int grid, cudaStream_t s);
+    void (*gkr_w_phase1)(const GkrW1Args& a, int grid_gates, int grid_wires, cudaStream_t s);  // two launches each
+    void (*gkr_w_phase2)(const GkrW2Args& a, int grid_gates, int grid_wires, cudaStream_t s);
     void (*gkr_w_wiring)(const GkrWWiringArgs& a, int grid, cudaStream_t s);
     void (*layer_eval_w)(TabRef in, TabRef out, const uint8_t* ops, const uint32_t* in1, const uint32_t* in2, uint64_t n_gates, int grid, cudaStream_t s);
     void (*bench_mul)(int variant, Fe* out, uint32_t iters, int grid, cudaStream_t s);

@@ -117,6 +117,7 @@ struct CircuitState {
     Table inputs;
     std::vector<Table> vals;  // per layer outputs
     Table H1, HA2, coef;      // phase tables (max size)
+    Table gtmp;               // general wiring: one per-gate product (coef*W[in2] / coef*eq(u,in1))
     Table eq[8];              // split eq tables: rb hi/lo, rc hi/lo, u hi/lo, w hi/lo
     SumPolyState sp;          // the XYZ sumcheck state (work tables reused across layers)
     void* aos_stage = nullptr;
@@ -1444,9 +1445,12 @@ int32_t gkr_prove_wired_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* input
         p1.in2 = cs->d_in2 + cs->opoff[l];
         p1.off1 = cs->d_off1 + cs->csroff[l];
         p1.lst1 = cs->d_lst1 + cs->opoff[l];
+        p1.tmp = cs->gtmp.ref();
         p1.width = nw;
-        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * ((double)G * 3.0 + (double)nw * 2.0));
-        c->K->gkr_w_phase1(p1, grid_for(c, nw, 8), c->stream);
+        p1.n_gates = G;
+        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * ((double)G * 5.0 + (double)nw * 2.0));
+        c->K->gkr_w_phase1(p1, grid_for(c, G, 8), grid_for(c, nw, 8), c->stream);
+        ++c->launches;
         ZK_TRY(check_launch(c, "k_gkr_w_phase1"));
         std::vector<Fe> u(nb), v(nb);
         Fe Wu, Wv;
@@ -1466,10 +1470,13 @@ int32_t gkr_prove_wired_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* input
         p2.in1 = cs->d_in1 + cs->opoff[l];
         p2.off2 = cs->d_off2 + cs->csroff[l];
         p2.lst2 = cs->d_lst2 + cs->opoff[l];
+        p2.tmp = cs->gtmp.ref();
         p2.width = nw;
+        p2.n_gates = G;
         p2.Wu = Wu;
-        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * ((double)G * 2.0 + (double)nw * 2.0));
-        c->K->gkr_w_phase2(p2, grid_for(c, nw, 8), c->stream);
+        prof_begin(c, ZKB_K_GKR_BUILD, 32.0 * ((double)G * 3.0 + (double)nw * 2.0));
+        c->K->gkr_w_phase2(p2, grid_for(c, G, 8), grid_for(c, nw, 8), c->stream);
+        ++c->launches;
         ZK_TRY(check_launch(c, "k_gkr_w_phase2"));
         ZK_TRY(xyz_phase(c, cs, W, cs->H1, cs->HA2, nw, &tr, coeffs + (round_base + nb) * 12, lens + round_base + nb,
                          challenges ? challenges + (round_base + nb) * 4 : nullptr, v.data(), &Wv));
@@ -2215,6 +2222,7 @@ int32_t zkb_circuit_free(zkb_ctx* c, zkb_circ h) {
     free_table(c, &cs->H1);
     free_table(c, &cs->HA2);
     free_table(c, &cs->coef);
+    free_table(c, &cs->gtmp);
     for (auto& t : cs->eq) free_table(c, &t);
     if (cs->d_ops) cudaFreeAsync(cs->d_ops, c->stream);
     for (uint32_t* q : {cs->d_in1, cs->d_in2, cs->d_lst1, cs->d_lst2, cs->d_off1, cs->d_off2})
@@ -2437,6 +2445,7 @@ int32_t zkb_circuit_create_wired(zkb_ctx* c, uint32_t n_layers, const uint32_t* 
     ZK_TRY(alloc_table(c, wmax, &cs->H1));
     ZK_TRY(alloc_table(c, wmax, &cs->HA2));
     ZK_TRY(alloc_table(c, gmax, &cs->coef));
+    ZK_TRY(alloc_table(c, gmax, &cs->gtmp));
     const int nmax = ilog2_u64(wmax > gmax ? wmax : gmax);
     for (auto& t : cs->eq) ZK_TRY(alloc_table(c, 1ull << ((nmax + 1) / 2 + 1), &t));
     ZK_TRY(sp_configure(c, &cs->sp, 1, 3, KIND_XYZ));
