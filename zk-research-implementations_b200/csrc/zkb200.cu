@@ -258,6 +258,8 @@ struct zkb_ctx {
     // staging for uploads / downloads
     void* stage = nullptr;
     size_t stage_bytes = 0;
+    void* hash_pin = nullptr;  // 2 x 2 MiB pinned slots for absorb_table_bytes
+    cudaEvent_t hash_ev[2] = {nullptr, nullptr};
     // double-buffered upload: H2D copies on their own stream overlap the layout kernels
     cudaStream_t copy_stream = nullptr;
     void* up_stage[2] = {nullptr, nullptr};
@@ -1178,6 +1180,37 @@ int32_t evaluate_table(zkb_ctx* c, const Table& src, const Fe* rs, uint32_t k, F
     return ZKB_OK;
 }
 
+// Canonical little-endian bytes of a whole table into the transcript.  Keccak is sequential and runs on the host
+// (about 0.4 GB/s), so the table is converted and copied in 2 MiB pieces through two pinned slots while the
+// previous piece is being hashed; no table-sized host allocation.
+int32_t absorb_table_bytes(zkb_ctx* c, const Table& t, TranscriptImpl* tr) {
+    const uint64_t chunk = 1ull << 16;  // elements per piece (2 MiB)
+    ZK_TRY(ensure_stage(c, (size_t)2 * chunk * 32));
+    if (!c->hash_pin) {
+        ZK_CUDA(c, cudaHostAlloc(&c->hash_pin, (size_t)2 * chunk * 32, cudaHostAllocDefault));
+        for (auto& e : c->hash_ev) ZK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint64_t pieces = (t.n + chunk - 1) / chunk;
+    for (uint64_t k = 0; k <= pieces; ++k) {
+        if (k < pieces) {
+            const uint64_t off = k * chunk, m = t.n - off < chunk ? t.n - off : chunk;
+            uint4* dslot = (uint4*)c->stage + (k & 1) * chunk * 2;
+            TabRef src{t.base + off, t.stride};
+            prof_begin(c, ZKB_K_LAYOUT, 64.0 * (double)m);
+            c->K->planar_to_aos(src, dslot, m, 2, grid_for(c, m, 8), c->stream);
+            ZK_TRY(check_launch(c, "k_planar_to_aos"));
+            ZK_CUDA(c, cudaMemcpyAsync((uint8_t*)c->hash_pin + (k & 1) * chunk * 32, dslot, (size_t)m * 32, cudaMemcpyDeviceToHost, c->stream));
+            ZK_CUDA(c, cudaEventRecord(c->hash_ev[k & 1], c->stream));
+        }
+        if (k > 0) {
+            const uint64_t j = k - 1, off = j * chunk, m = t.n - off < chunk ? t.n - off : chunk;
+            ZK_CUDA(c, cudaEventSynchronize(c->hash_ev[j & 1]));
+            tr->append((const uint8_t*)c->hash_pin + (j & 1) * chunk * 32, (size_t)m * 32);
+        }
+    }
+    return ZKB_OK;
+}
+
 // ------------------------------------------------------------------- GKR core
 uint32_t layer_rounds(uint32_t gates) {
     int nb = ilog2_u64(2ull * gates);
@@ -1407,11 +1440,7 @@ int32_t gkr_prove_wired_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* input
         m0 = H.add(w0[0], H.mul(r0[0], H.sub(w0[1], w0[0])));
     } else {
         ZK_TRY(download_aos(c, cs->vals[L - 1], w0_out, 0));
-        {  // canonical bytes made on the device (fq_vec_to_bytes), hashed on the host
-            std::vector<uint8_t> bytes((size_t)Gout * 32);
-            ZK_TRY(download_aos(c, cs->vals[L - 1], bytes.data(), 2));
-            tr.append(bytes.data(), bytes.size());
-        }
+        ZK_TRY(absorb_table_bytes(c, cs->vals[L - 1], &tr));  // fq_vec_to_bytes on the device, Keccak on the host
         for (int i = 0; i < k0; ++i) r0[i] = tr.challenge();
         ZK_TRY(evaluate_table(c, cs->vals[L - 1], r0.data(), (uint32_t)k0, &m0));
     }
@@ -1629,12 +1658,20 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
         free_table(c, &cs->H1);
         free_table(c, &cs->HA2);
         free_table(c, &cs->coef);
+        free_table(c, &cs->gtmp);
         for (auto& t : cs->eq) free_table(c, &t);
         if (cs->d_ops) cudaFreeAsync(cs->d_ops, c->stream);
+        for (uint32_t* q : {cs->d_in1, cs->d_in2, cs->d_lst1, cs->d_lst2, cs->d_off1, cs->d_off2})
+            if (q) cudaFreeAsync(q, c->stream);
         if (cs->aos_stage) cudaFreeAsync(cs->aos_stage, c->stream);
     }
     for (auto& kv : c->mles) free_table(c, &kv.second);
     if (c->stage) cudaFreeAsync(c->stage, c->stream);
+    if (c->hash_pin) {
+        cudaFreeHost(c->hash_pin);
+        for (auto& e : c->hash_ev)
+            if (e) cudaEventDestroy(e);
+    }
     if (c->d_partials) cudaFreeAsync(c->d_partials, c->stream);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) {
@@ -2063,10 +2100,7 @@ static int32_t absorb_table(zkb_ctx* c, const Table& t, TranscriptImpl* tr) {
     // fq_vec_to_bytes(&polynomial.evaluation) (sum_check_protocol.rs:27): canonical bytes made on the
     // device, hashed on the host.  Sharded tables are not supported here (the reference order needs the whole table).
     if (c->comm && c->world > 1) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "absorbing a sharded table into the transcript is not supported");
-    std::vector<uint8_t> bytes((size_t)t.n * 32);
-    ZK_TRY(download_aos(c, t, bytes.data(), 2));
-    tr->append(bytes.data(), bytes.size());
-    return ZKB_OK;
+    return absorb_table_bytes(c, t, tr);
 }
 
 int32_t zkb_sumcheck_prove(zkb_ctx* c, zkb_mle poly, uint32_t flags, uint64_t claimed_sum[4], uint64_t* msgs, uint64_t* challenges) {
@@ -2500,25 +2534,27 @@ int32_t zkb_gkr_verify_wired(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uin
     const int k0 = ilog2_u64(n0);
     std::vector<Fe> r0(k0);
     Fe claim;
-    {
+    if (n0 <= 4096) {
         std::vector<Fe> w0(n0);
         for (uint64_t i = 0; i < n0; ++i) w0[i] = fe_from_u64x4(w0_in + i * 4);
         tr.append_elements(w0.data(), (size_t)n0);
         for (int i = 0; i < k0; ++i) r0[i] = tr.challenge();
-        if (n0 <= 4096) {
-            for (int i = 0; i < k0; ++i) {
-                const size_t hlf = w0.size() / 2;
-                for (size_t j = 0; j < hlf; ++j) w0[j] = H.add(w0[j], H.mul(r0[i], H.sub(w0[j + hlf], w0[j])));
-                w0.resize(hlf);
-            }
-            claim = w0[0];
-        } else {
-            Table t0;
-            ZK_TRY(upload_aos(c, w0_in, n0, 0, 1, n0, 0, &t0));
-            int32_t st0 = evaluate_table(c, t0, r0.data(), (uint32_t)k0, &claim);
-            free_table(c, &t0);
-            ZK_TRY(st0);
+        for (int i = 0; i < k0; ++i) {
+            const size_t hlf = w0.size() / 2;
+            for (size_t j = 0; j < hlf; ++j) w0[j] = H.add(w0[j], H.mul(r0[i], H.sub(w0[j + hlf], w0[j])));
+            w0.resize(hlf);
         }
+        claim = w0[0];
+    } else {  // wide output layer: canonical bytes and the MLE evaluation both come from the device copy
+        Table t0;
+        ZK_TRY(upload_aos(c, w0_in, n0, 0, 1, n0, 0, &t0));
+        int32_t st0 = absorb_table_bytes(c, t0, &tr);
+        if (st0 == ZKB_OK) {
+            for (int i = 0; i < k0; ++i) r0[i] = tr.challenge();
+            st0 = evaluate_table(c, t0, r0.data(), (uint32_t)k0, &claim);
+        }
+        free_table(c, &t0);
+        ZK_TRY(st0);
     }
     tr.append_elements(&claim, 1);
     Table in_tab;
