@@ -277,6 +277,15 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # One process per GPU, each with a host thread that spins on its GPU's mailbox once per round: give every rank
+        # its own slice of the host cores so that the ranks (and their helper threads) do not migrate onto each other.
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = len(cpus) // world
+            if per >= 1:
+                os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+        except (AttributeError, OSError):
+            pass
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
