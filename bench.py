@@ -190,7 +190,22 @@ def gkr_leg(z, ctx_unused, args):
     ctx.profile(False)
     ok = prover.verify()
     ctx.close()
-    return {"prove_ms": ms, "prove_ms_pageable_input": ms_pageable, "verify_accepts": ok,
+    cpu = None
+    if not args.no_cpu_baseline:
+        # CPU figure beside it: the oracle's O(G) two-phase prover on the SAME circuit and inputs.  The reference's own
+        # dense construction (2^(3g+2)-entry add_i/mul_i tables, gkr_circuit.rs:39-65) cannot run at this size at all.
+        O.build()
+        cores = O.max_threads()
+        O.set_threads(cores)
+        flat = np.concatenate([np.array([int(o) for o in layer], dtype=np.uint8) for layer in structure])
+        t0 = time.perf_counter()
+        ref = O.gkr_prove(0, [len(layer) for layer in structure], flat, O.synth_table(0, SEED + 1, 0, log_in))
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        same = list(ref["final_openings"]) == O.arr_to_ints(z.engine.from_mont(z.BN254_FR, prover.fin))
+        cpu = {"prove_ms": cpu_ms, "cores": cores, "kind": "port",
+               "note": "oracle/zk_oracle.c two-phase (sparse) GKR prover, one run; the reference's dense construction is infeasible at this size",
+               "same_final_openings_as_device": same}
+    return {"prove_ms": ms, "prove_ms_pageable_input": ms_pageable, "verify_accepts": ok, "cpu_baseline": cpu,
             "kernel_ms": {k: round(v[1], 4) for k, v in prof.items()}, "launches": sum(v[0] for v in prof.values()), "rounds": int(prover.total), "layers": L, "inputs": 1 << log_in,
             "workload": "configs[2] (reference-legal form): binary-tree circuit, 2^%d inputs, %d layers, widest layer 2^%d gates, BN254 Fr; "
                         "KZG input commitment excluded (SURVEY F11); host wall clock around zkb_gkr_prove incl. the upload of the inputs "
