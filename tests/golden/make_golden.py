@@ -48,6 +48,29 @@ def main():
     with open(os.path.join(HERE, "proofs.json"), "w") as f:
         json.dump(out, f, indent=0)
     print("wrote", os.path.join(HERE, "proofs.json"))
+    # general wiring (extension): proofs from the DENSE construction with general indices
+    wired = []
+    for fid, p in FIELDS.items():
+        rng = random.Random(2000 + fid)
+        for nin, gates in ((2, [1]), (4, [4, 2]), (8, [4, 8, 4]), (4, [8, 4, 1])):
+            spec, w = [], nin
+            for G in gates:
+                spec.append({"ops": [rng.randrange(2) for _ in range(G)], "in1": [rng.randrange(w) for _ in range(G)],
+                             "in2": [rng.randrange(w) for _ in range(G)]})
+                w = G
+            inputs = [rng.randrange(p) for _ in range(nin)]
+            ws, w = [], nin
+            for l in spec:
+                ws.append(R.WiredLayer(l["ops"], l["in1"], l["in2"], w))
+                w = len(l["ops"])
+            pr = R.wired_prove_dense(R.WiredCircuit(ws), inputs, p)
+            wired.append({"field": fid, "n_inputs": nin, "layers": spec, "inputs": hx(inputs), "output_poly": hx(pr.output_poly),
+                          "proof_polynomials": [[hx(c) for c in layer] for layer in pr.proof_polynomials],
+                          "claimed_evaluations": [hx(ce) for ce in pr.claimed_evaluations],
+                          "final_openings": hx(pr.final_openings)})
+    with open(os.path.join(HERE, "wired_proofs.json"), "w") as f:
+        json.dump({"wired": wired}, f, indent=0)
+    print("wrote", os.path.join(HERE, "wired_proofs.json"))
 
 
 if __name__ == "__main__":

@@ -65,6 +65,21 @@ def test_gkr_golden(zkb, regime):
         c.free()
 
 
+def test_wired_gkr_golden(zkb, regime):
+    """zkb_gkr_prove_wired against the committed general-wiring proofs, in every round-driver regime."""
+    W = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wired_proofs.json")))["wired"]
+    for g in W:
+        ctx = regime(g["field"], 0)
+        c = zkb.gkr_circuit.WiredCircuit(ctx, g["n_inputs"], [(l["ops"], l["in1"], l["in2"]) for l in g["layers"]])
+        pr = zkb.gkr_protocol.prove_wired(c, ints(g["inputs"]))
+        assert pr.output_poly == ints(g["output_poly"])
+        assert [[q.coefficients for q in layer] for layer in pr.proof_polynomials] == [[ints(x) for x in layer] for layer in g["proof_polynomials"]]
+        assert [list(x) for x in pr.claimed_evaluations] == [ints(x) for x in g["claimed_evaluations"]]
+        assert list(pr.final_openings) == ints(g["final_openings"])
+        assert zkb.gkr_protocol.verify_wired(pr, c, ints(g["inputs"]))
+        c.free()
+
+
 def test_regimes_agree_on_larger_tables(zkb, ctxs, oracle):
     """n = 15, 2 x 2 and 1 x 3 shapes: every regime gives the oracle's proof."""
     import random
