@@ -53,6 +53,9 @@ extern "C" {
     pub fn zkb_ctx_comm_init(ctx: *mut zkb_ctx, rank: i32, world: i32, unique_id: *const u8) -> i32;
     pub fn zkb_ctx_set_gather_threshold(ctx: *mut zkb_ctx, log2_local_entries: u32) -> i32;
     pub fn zkb_ctx_set_tail_threshold(ctx: *mut zkb_ctx, log2_entries: u32) -> i32;
+    pub fn zkb_ctx_set_small_threshold(ctx: *mut zkb_ctx, smem_bytes: u32) -> i32;
+    pub fn zkb_ctx_set_device_transcript(ctx: *mut zkb_ctx, enable: i32) -> i32;
+    pub fn zkb_ctx_device_transcript_stats(ctx: *const zkb_ctx, launches: *mut u64, rounds_checked: *mut u64) -> i32;
 
     pub fn zkb_mle_upload(ctx: *mut zkb_ctx, aos_mont: *const u64, len: u64, out: *mut zkb_mle) -> i32;
     pub fn zkb_mle_upload_shard(ctx: *mut zkb_ctx, aos_mont_full: *const u64, len_full: u64, out: *mut zkb_mle) -> i32;

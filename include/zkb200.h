@@ -98,6 +98,16 @@ int32_t zkb_ctx_set_tail_threshold(zkb_ctx* ctx, uint32_t log2_entries);
 /* Once all tables of a sumcheck fit in `smem_bytes` of shared memory (default and maximum 200 KiB) the remaining
  * rounds run in a single-CTA kernel that keeps the tables on chip; 0 disables it. */
 int32_t zkb_ctx_set_small_threshold(zkb_ctx* ctx, uint32_t smem_bytes);
+/* Device-side Fiat-Shamir transcript (default OFF, ZKB200_DT=1 in the environment turns it on).  In the
+ * on-chip kernel above, for round polynomials of degree <= 2 (the GKR layer sumcheck and products of two factors),
+ * the GPU itself interpolates and trims the round message (univariate_polynomial_dense.rs:14-18,48-74), serialises
+ * it (fiat_shamir_transcript.rs:32-37), runs Keccak-256 and reduces the digest mod p (:23-29), so no round waits for
+ * PCIe.  The host transcript remains the source of truth: it replays every round from the sums the device reports
+ * and the call fails with ZKB_ERR_CUDA ("device transcript diverged") if a challenge differs.  Bit-identical to the
+ * host path, but measured slower on B200 (one warp needs 3.8 us per Keccak-f), hence off.
+ * _stats: how many launches ran with the device transcript and how many device challenges the host has checked. */
+int32_t zkb_ctx_set_device_transcript(zkb_ctx* ctx, int32_t enable);
+int32_t zkb_ctx_device_transcript_stats(const zkb_ctx* ctx, uint64_t* launches, uint64_t* rounds_checked);
 
 /* --------------------------------------------- MultilinearPoly (device table) */
 /* MultilinearPoly::new (multilinear_polynomial_evaluation.rs:26-37): `len` must be a power of two. */

@@ -445,6 +445,58 @@ def test_wired_shape_errors(zkb, ctxs):
         assert ei.value.status == -11
 
 
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_device_transcript(zkb, ctxs, oracle, fid, p):
+    """in the on-chip kernel the GPU runs Keccak / interpolation / trimming itself and the host only
+    replays.  Same bytes as the oracle and as the host-transcript path; the counters prove the device path ran."""
+    ctx = ctxs(fid, zkb.MODE_FULL)
+    rng = random.Random(8000 + fid)
+    S, T = zkb.sum_check_protocol, zkb.fiat_shamir.Transcript
+    try:
+        for n in (1, 2, 5, 10, 13):
+            tabs = [rand_table(rng, p, n) for _ in range(2)]
+            if n == 5:  # a round polynomial that trims: second factor zero -> every message is empty
+                tabs[1] = [0] * (1 << n)
+            if n == 2:  # degree drops: constant second factor
+                tabs[1] = [7] * (1 << n)
+            ref = oracle.gkr_sumcheck_prove(oracle.Transcript(fid), 1, 1, 2, [ints_to_arr(t) for t in tabs])
+            sp = zkb.SumPoly(ctx, [zkb.ProductPoly(ctx, tabs)])
+            out = []
+            for on in (True, False):
+                ctx.set_device_transcript(on)
+                l0, r0 = ctx.device_transcript_stats()
+                t = T(fid)
+                t.append(b"seed")  # a partly filled sponge at entry (4 bytes: not whole words -> host path) ...
+                pr = S.gkr_prove(0, sp, t)
+                t2 = T(fid)
+                t2.append(b"12345678" * 5)  # ... and one with whole words pending -> device path continues it
+                pr2 = S.gkr_prove(0, sp, t2)
+                pr3 = S.gkr_prove(0, sp, T(fid))
+                l1, r1 = ctx.device_transcript_stats()
+                if on:
+                    assert l1 > l0 and r1 - r0 >= n, (n, l0, l1, r0, r1)
+                else:
+                    assert (l1, r1) == (l0, r0)
+                out.append([([q.coefficients for q in x.proof_polynomials], x.random_challenges, x.final_values) for x in (pr, pr2, pr3)])
+                # the transcripts continue identically after the proof
+                assert t2.get_random_challenge() == _replay(zkb, fid, b"12345678" * 5, pr2)
+            assert out[0] == out[1]
+            assert out[0][2][0] == ref["coeffs"] and out[0][2][1] == ref["challenges"] and out[0][2][2] == ref["final_vals"]
+            sp.free()
+    finally:
+        ctx.set_device_transcript(False)  # the default (DESIGN.md section 7)
+
+
+def _replay(zkb, fid, seed, pr):
+    """Challenge that follows a proof on a fresh host transcript seeded like the prover's."""
+    t = zkb.fiat_shamir.Transcript(fid)
+    t.append(seed)
+    for q in pr.proof_polynomials:
+        t.append(zkb.fiat_shamir.fq_vec_to_bytes(q.coefficients))
+        t.get_random_challenge()
+    return t.get_random_challenge()
+
+
 def test_circuit_shape_errors(zkb, ctxs):
     ctx = ctxs(0, 0)
     Op = zkb.Operation

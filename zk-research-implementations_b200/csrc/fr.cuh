@@ -593,6 +593,20 @@ struct Field {
         c.l[0] = x;
         return to_mont(c);
     }
+    // a / 2 mod p (also correct on Montgomery residues: halving commutes with the factor R)
+    ZK_HD static Fe half(const Fe& a) {
+        const uint32_t m = 0u - (a.l[0] & 1u);  // odd: add p first (a + p < 2^256 for every modulus here)
+        Fe t;
+        t.l[0] = add_cc(a.l[0], F::P(0) & m);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) t.l[i] = addc_cc(a.l[i], F::P(i) & m);
+        t.l[7] = addc(a.l[7], F::P(7) & m);
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) r.l[i] = (t.l[i] >> 1) | (t.l[i + 1] << 31);
+        r.l[7] = t.l[7] >> 1;
+        return r;
+    }
     // a + r*(b - a): the fold of multilinear_polynomial_evaluation.rs:59
     ZK_HD static Fe fold(const Fe& a, const Fe& b, const Fe& r) { return add(a, mul(r, sub(b, a))); }
 };

@@ -55,6 +55,20 @@ class Keccak256 {
         reset();
     }
 
+    // The sponge as a device continuation needs it (kernels.cuh DtArgs): state with the pending bytes already
+    // XORed in, and how many 64-bit words of the rate they occupy.  False if the pending bytes are not whole words.
+    bool snapshot(uint64_t st[25], uint32_t* fill_words) const {
+        if (fill_ % 8) return false;
+        std::memcpy(st, st_, sizeof st_);
+        for (size_t i = 0; i < fill_ / 8; ++i) {
+            uint64_t lane;
+            std::memcpy(&lane, buf_ + 8 * i, 8);
+            st[i] ^= lane;
+        }
+        *fill_words = (uint32_t)(fill_ / 8);
+        return true;
+    }
+
   private:
     static constexpr size_t RATE = 136;
     uint64_t st_[25];

@@ -49,7 +49,49 @@ struct FinishArgs {
     volatile unsigned int* flag;      // optional mailbox flag (mapped host memory): set to `seq` after `result`
     unsigned int seq;
     unsigned long long* stamp;        // optional: %globaltimer right before the result is published
+    volatile unsigned int* chk;       // optional (mapped host memory, 2 words): checksum of result + seq.  With it the
+                                      // message is published WITHOUT a system fence (1.4 us on B200): the host accepts the
+                                      // sums only when the checksum matches what it reads, and re-reads otherwise
 };
+// Checksum of a device -> host round message: n field elements and the sequence number they belong to.
+__host__ __device__ __forceinline__ void msg_checksum(const Fe* v, int n, unsigned int seq, unsigned int* c0, unsigned int* c1) {
+    unsigned int x = seq * 0x9E3779B9u, y = seq ^ 0x85EBCA6Bu;
+    for (int p = 0; p < n; ++p)
+        for (int k = 0; k < 8; ++k) {
+            const unsigned int w = v[p].l[k];
+            x ^= w;
+            y = ((y << 5) | (y >> 27)) + w;
+        }
+    *c0 = x;
+    *c1 = y;
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+template <int NPTS>
+__device__ __forceinline__ void publish_result(const Fe* tot, const FinishArgs& a) {
+#pragma unroll
+    for (int p = 0; p < NPTS; ++p) {
+        a.result[p] = tot[p];
+        if (a.result_wide) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a.result_wide[p * 8 + k] = tot[p].l[k];
+        }
+    }
+    if (a.stamp) *a.stamp = gtime();
+    if (a.chk && a.flag && !a.result_wide) {
+        unsigned int c0, c1;
+        msg_checksum(tot, NPTS, a.seq, &c0, &c1);
+        a.chk[0] = c0;
+        a.chk[1] = c1;
+        *a.flag = a.seq;
+        return;
+    }
+    __threadfence_system();
+    if (a.flag) *a.flag = a.seq;
+}
 
 struct ScArgs {
     TabRef in[MAXT];
@@ -67,11 +109,6 @@ struct ChalList {
 
 enum { KIND_PROD = 0, KIND_XYZ = 1 };
 
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 // ----------------------------------------------------------- load / store
 __device__ __forceinline__ Fe ld_fe(const TabRef& t, uint64_t i) {
     uint4 a = t.base[i];
@@ -128,19 +165,7 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a, unsig
     if (n_active == 0) n_active = gridDim.x;  // CTAs [0, n_active) take part; the others must not call this
     block_sum<F, NPTS>(acc, smem);
     if (n_active == 1) {  // small tables: the CTA's sums are the round's sums
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int p = 0; p < NPTS; ++p) {
-                a.result[p] = acc[p];
-                if (a.result_wide) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) a.result_wide[p * 8 + k] = acc[p].l[k];
-                }
-            }
-            if (a.stamp) *a.stamp = gtime();
-            __threadfence_system();
-            if (a.flag) *a.flag = a.seq;
-        }
+        if (threadIdx.x == 0) publish_result<NPTS>(acc, a);
         return;
     }
     if (threadIdx.x == 0) {
@@ -170,18 +195,8 @@ __device__ __forceinline__ void finish_round(Fe* acc, const FinishArgs& a, unsig
     }
     block_sum<F, NPTS>(tot, smem);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int p = 0; p < NPTS; ++p) {
-            a.result[p] = tot[p];
-            if (a.result_wide) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) a.result_wide[p * 8 + k] = tot[p].l[k];
-            }
-        }
         *a.ticket = 0u;
-        if (a.stamp) *a.stamp = gtime();
-        __threadfence_system();
-        if (a.flag) *a.flag = a.seq;
+        publish_result<NPTS>(tot, a);
     }
 }
 
@@ -622,7 +637,8 @@ struct alignas(64) TailMailbox {
     Fe finals[MAXT];
     volatile unsigned int dev_seq;
     volatile unsigned int dev_error;  // 1 = timed out waiting for the host
-    unsigned int pad1[14];
+    volatile unsigned int dev_chk[2]; // checksum of evals + dev_seq (messages published without a system fence)
+    unsigned int pad1[12];
     // diagnostics (ZKB200_TRACE=1): device %globaltimer stamps of the last round, see RoundDriver::trace
     unsigned long long ts[8];
 };
@@ -672,6 +688,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             fin.flag = &a.mb->dev_seq;
             fin.seq = a.base_seq + 1;
             fin.stamp = nullptr;
+            fin.chk = a.mb->dev_chk;
             finish_round<F, NPTS>(out, fin, n_active);
         }
     }
@@ -773,6 +790,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             fin.flag = &a.mb->dev_seq;
             fin.seq = a.base_seq + it + 1;
             fin.stamp = &a.mb->ts[4];
+            fin.chk = a.mb->dev_chk;
             finish_round<F, NPTS - 1>(out, fin, n_active);
         }
         n_in = n_out;
@@ -789,6 +807,83 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
 // small layer is one launch.
 constexpr int SMALL_BLOCK = 512;
 constexpr int SMALL_SMEM_MAX = 200 * 1024;
+
+// ---- device-side transcript.  With `enabled`, k_sc_small derives every challenge itself: warp 0
+// interpolates the round polynomial (evaluations at 0, 1, 2 -> trimmed ascending coefficients,
+// univariate_polynomial_dense.rs:14-18,48-74), serialises it as canonical little-endian bytes
+// (fiat_shamir_transcript.rs:32-37), absorbs it into the running Keccak-256 sponge handed over by the host,
+// squeezes the digest, re-seeds the sponge with it and reduces it mod p (fiat_shamir_transcript.rs:23-29).
+// No round waits for PCIe.  Every round's sums AND the challenge drawn after them are written to a record in
+// mapped host memory; the host replays its own transcript on those sums behind the kernel and refuses the
+// proof if any challenge differs, so the host transcript stays the checked source of truth.
+constexpr int DT_MAX_ROUNDS = 32;
+struct DtRound {
+    Fe evals[MAXPTS];
+    Fe chal;
+    long long t[6];  // clock64 stamps of the transcript step (diagnostics)
+};
+struct DtArgs {
+    int enabled;
+    uint32_t fill_words;  // 64-bit words absorbed since the last permutation (already XORed into st), < 17
+    uint64_t st[25];      // Keccak-f[1600] state
+    Fe claim0;            // s_prev(r0): the running claim when the launch starts by binding r0 (first_eval == 0)
+    DtRound* rounds;      // [DT_MAX_ROUNDS] mapped host memory
+};
+__constant__ uint64_t KECCAK_RC[24] = {
+    0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
+    0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
+    0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
+    0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+__device__ const uint8_t KECCAK_RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+// One warp, lane x + 5y holds lane A[x][y] of the state as (lo, hi); lanes 25..31 follow along with lane-0 sources.
+struct KeccakWarp {
+    int c1, c2, c3, c4, dm, dp, pi, x1, x2;
+    uint32_t rho;
+    bool l0;
+    __device__ __forceinline__ void init(int lane) {
+        const int l = lane < 25 ? lane : 0, x = l % 5, y = l / 5;
+        c1 = (l + 5) % 25; c2 = (l + 10) % 25; c3 = (l + 15) % 25; c4 = (l + 20) % 25;
+        dm = 5 * y + (x + 4) % 5;
+        dp = 5 * y + (x + 1) % 5;
+        pi = (x + 3 * y) % 5 + 5 * x;  // B[x][y] = A[(x + 3y) % 5][x] rotated
+        x1 = 5 * y + (x + 1) % 5;
+        x2 = 5 * y + (x + 2) % 5;
+        rho = KECCAK_RHO[pi];          // the rotation belongs to the SOURCE lane of the pi step
+        l0 = lane == 0;
+    }
+    __device__ __forceinline__ void permute(uint32_t& lo, uint32_t& hi) const {
+        const unsigned int FULL = 0xffffffffu;
+#pragma unroll 1
+        for (int rnd = 0; rnd < 24; ++rnd) {
+            // theta
+            uint32_t cl = lo ^ __shfl_sync(FULL, lo, c1) ^ __shfl_sync(FULL, lo, c2) ^ __shfl_sync(FULL, lo, c3) ^ __shfl_sync(FULL, lo, c4);
+            uint32_t ch = hi ^ __shfl_sync(FULL, hi, c1) ^ __shfl_sync(FULL, hi, c2) ^ __shfl_sync(FULL, hi, c3) ^ __shfl_sync(FULL, hi, c4);
+            const uint32_t ml = __shfl_sync(FULL, cl, dm), mh = __shfl_sync(FULL, ch, dm);
+            const uint32_t pl = __shfl_sync(FULL, cl, dp), ph = __shfl_sync(FULL, ch, dp);
+            lo ^= ml ^ __funnelshift_l(ph, pl, 1);  // rotl64(C[x+1], 1)
+            hi ^= mh ^ __funnelshift_l(pl, ph, 1);
+            // pi (gather) then rho with the source lane's offset
+            uint32_t bl = __shfl_sync(FULL, lo, pi), bh = __shfl_sync(FULL, hi, pi);
+            if (rho & 32) {
+                const uint32_t t = bl;
+                bl = bh;
+                bh = t;
+            }
+            const uint32_t rl = __funnelshift_l(bh, bl, rho & 31), rh = __funnelshift_l(bl, bh, rho & 31);
+            // chi
+            const uint32_t l1 = __shfl_sync(FULL, rl, x1), h1 = __shfl_sync(FULL, rh, x1);
+            const uint32_t l2 = __shfl_sync(FULL, rl, x2), h2 = __shfl_sync(FULL, rh, x2);
+            lo = rl ^ (~l1 & l2);
+            hi = rh ^ (~h1 & h2);
+            if (l0) {  // iota
+                const uint64_t rc = KECCAK_RC[rnd];
+                lo ^= (uint32_t)rc;
+                hi ^= (uint32_t)(rc >> 32);
+            }
+        }
+    }
+};
 struct SmallArgs {
     TabRef in[MAXT];
     TabRef out[MAXT];   // receives the bound value at entry 0
@@ -800,6 +895,7 @@ struct SmallArgs {
     TailMailbox* mb;
     unsigned int base_seq;
     long long timeout_clocks;
+    DtArgs dt;          // device-side Fiat-Shamir transcript (NPTS == 3 shapes)
 };
 
 // integrand at t = 0, (1), 2, .. for one pair position, accumulated with modular adds
@@ -871,6 +967,106 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
         tab[(size_t)(2 * t + 1) * cap + j] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
     };
     unsigned int pubs = 0;  // messages published so far
+    // device transcript state (warp 0 only): the sponge lives in registers, one 64-bit lane per thread
+    const bool dt = NPTS == 3 && a.dt.enabled;
+    __shared__ Fe s_ev[MAXPTS], s_co[3], s_claim;
+    __shared__ uint64_t s_words[12];
+    __shared__ long long s_t[4];
+    __shared__ int s_len, s_all;
+    const int nthr = dt ? SMALL_BLOCK - 32 : SMALL_BLOCK;  // device transcript: the last warp does not fold or evaluate
+    KeccakWarp kw;
+    uint32_t k_lo = 0, k_hi = 0;
+    int k_pos = 0;
+    if (dt && warp == 0) {
+        kw.init(lane);
+        if (lane < 25) {
+            k_lo = (uint32_t)a.dt.st[lane];
+            k_hi = (uint32_t)(a.dt.st[lane] >> 32);
+        }
+        k_pos = (int)a.dt.fill_words;
+        if (lane == 0) s_claim = a.dt.claim0;
+    }
+    // One transcript step, critical part, by warp 0: the round's sums are in s_ev (`all` = every point was computed;
+    // otherwise {s(0), s(2)} and s(1) = claim - s(0)); leaves the next challenge in s_r and the coefficients in s_co.
+    auto dt_step = [&](bool all) {
+        int len = 0;
+        const long long t0 = clock64();
+        if (lane == 0) {
+            const Fe e0 = s_ev[0];
+            const Fe e1 = all ? s_ev[1] : Fd::sub(s_claim, e0);
+            const Fe e2 = all ? s_ev[2] : s_ev[1];
+            const Fe c2 = Fd::half(Fd::add(Fd::sub(e2, Fd::dbl(e1)), e0));
+            const Fe c1 = Fd::sub(Fd::sub(e1, e0), c2);
+            s_co[0] = e0;
+            s_co[1] = c1;
+            s_co[2] = c2;
+            len = !Fd::is_zero(c2) ? 3 : (!Fd::is_zero(c1) ? 2 : (!Fd::is_zero(e0) ? 1 : 0));  // trim (:14-18)
+            s_len = len;
+            s_all = all ? 1 : 0;
+        }
+        len = __shfl_sync(0xffffffffu, len, 0);
+        __syncwarp();
+        if (lane < 3) {  // canonical little-endian limbs of each coefficient (fq_vec_to_bytes): c * R^-1
+            const Fe cv = Fd::redc256(s_co[lane]);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) s_words[lane * 4 + w] = (uint64_t)cv.l[2 * w] | ((uint64_t)cv.l[2 * w + 1] << 32);
+        }
+        __syncwarp();
+        const long long t1 = clock64();
+        for (int i = 0; i < len * 4; ++i) {  // absorb; the rate is 17 words
+            const uint64_t w = s_words[i];
+            if (lane == k_pos) {
+                k_lo ^= (uint32_t)w;
+                k_hi ^= (uint32_t)(w >> 32);
+            }
+            if (++k_pos == 17) {
+                kw.permute(k_lo, k_hi);
+                k_pos = 0;
+            }
+        }
+        if (lane == k_pos) k_lo ^= 0x01u;       // Keccak (not SHA-3) padding: 0x01 .. 0x80
+        if (lane == 16) k_hi ^= 0x80000000u;
+        kw.permute(k_lo, k_hi);
+        if (lane < 4) s_words[lane] = (uint64_t)k_lo | ((uint64_t)k_hi << 32);  // the digest
+        if (lane >= 4) k_lo = k_hi = 0;         // fresh sponge seeded with the digest (:24-26)
+        k_pos = 4;
+        __syncwarp();
+        const long long t2 = clock64();
+        if (lane == 0) {
+            Fe d;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                d.l[2 * w] = (uint32_t)s_words[w];
+                d.l[2 * w + 1] = (uint32_t)(s_words[w] >> 32);
+            }
+            s_r = Fd::to_mont(Fd::mod_p(d));  // from_le_bytes_mod_order, then into Montgomery form
+            s_t[0] = t0;
+            s_t[1] = t1;
+            s_t[2] = t2;
+            s_t[3] = clock64();
+        }
+        __syncwarp();
+    };
+    // ... and the part nobody waits for, by the last warp while the others fold: the next claim s(r) (Horner) and the
+    // round's record for the host (sums, challenge), then the sequence number.
+    auto dt_post = [&]() {
+        if (tid != SMALL_BLOCK - 32) return;
+        const Fe r = s_r;
+        const int len = s_len;
+        Fe cl = Fd::zero();
+        if (len > 0) cl = s_co[len - 1];
+        for (int k = len - 2; k >= 0; --k) cl = Fd::add(Fd::mul(cl, r), s_co[k]);
+        s_claim = cl;
+        DtRound* rec = a.dt.rounds + pubs;
+        for (int p = 0; p < (s_all ? NPTS : NPTS - 1); ++p) rec->evals[p] = s_ev[p];
+        rec->chal = r;
+        for (int k = 0; k < 4; ++k) rec->t[k] = s_t[k];
+        const long long f0 = clock64();
+        __threadfence_system();
+        rec->t[4] = f0;
+        rec->t[5] = clock64();
+        a.mb->dev_seq = a.base_seq + pubs + 1;
+    };
     // CTA-wide modular sum of `n` per-thread values and publication as message pubs+1
     auto publish = [&](Fe* acc, int n) {
         for (int p = 0; p < n; ++p) {
@@ -882,15 +1078,25 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
             for (int p = 0; p < n; ++p) {
                 Fe v = lane < SMALL_BLOCK / 32 ? s_red[lane][p] : Fd::zero();
                 v = warp_sum<F>(v);
-                if (lane == 0) a.mb->evals[p] = v;
+                if (lane == 0) {
+                    s_ev[p] = v;
+                    if (!dt) a.mb->evals[p] = v;
+                }
             }
-            if (lane == 0) {
-                __threadfence_system();
-                a.mb->dev_seq = a.base_seq + (++pubs);
+            if (dt) {
+                __syncwarp();
+                dt_step(n == NPTS);
+            } else if (lane == 0) {  // no system fence: the host validates the checksum (FinishArgs::chk)
+                unsigned int c0, c1;
+                msg_checksum(s_ev, n, a.base_seq + pubs + 1, &c0, &c1);
+                a.mb->dev_chk[0] = c0;
+                a.mb->dev_chk[1] = c1;
+                a.mb->dev_seq = a.base_seq + pubs + 1;
             }
         }
-        if (warp != 0 || lane != 0) ++pubs;
         __syncthreads();
+        if (dt) dt_post();
+        ++pubs;
     };
     uint32_t m = a.n_in;
     if (a.first_eval) {  // round 0: all NPTS points of the unbound tables
@@ -898,7 +1104,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
 #pragma unroll
         for (int p = 0; p < NPTS; ++p) acc[p] = Fd::zero();
         const uint32_t half = m >> 1;
-        for (uint32_t j = tid; j < half; j += SMALL_BLOCK) {
+        for (uint32_t j = tid; tid < nthr && j < half; j += nthr) {
             for (int p = 0; p < (KIND == KIND_XYZ ? 1 : a.n_products); ++p) {
                 Fe lo[KD], hi[KD];
 #pragma unroll
@@ -912,7 +1118,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
         publish(acc, NPTS);
     }
     for (unsigned int chal = a.first_eval ? 1u : 0u;; ++chal) {
-        if (chal > 0) {  // challenge number `chal` from the host mailbox
+        if (chal > 0 && !dt) {  // challenge number `chal` from the host mailbox
             if (warp == 0) {
                 const unsigned int want = a.base_seq + chal;
                 const volatile uint32_t* line = reinterpret_cast<const volatile uint32_t*>(a.mb);
@@ -944,7 +1150,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
         const Fe r = s_r;
         // fold: one output entry per thread, in place (entry j reads j and j + n_out, writes j)
         const uint32_t n_out = m >> 1;
-        for (uint32_t idx = tid; idx < (uint32_t)T * n_out; idx += SMALL_BLOCK) {
+        for (uint32_t idx = tid; tid < nthr && idx < (uint32_t)T * n_out; idx += nthr) {
             const uint32_t t = idx / n_out, j = idx - t * n_out;
             st(t, j, Fd::fold(ld(t, j), ld(t, j + n_out), r));
         }
@@ -965,7 +1171,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
 #pragma unroll
         for (int p = 0; p < NPTS - 1; ++p) acc[p] = Fd::zero();
         const uint32_t half = m >> 1;
-        for (uint32_t j = tid; j < half; j += SMALL_BLOCK) {
+        for (uint32_t j = tid; tid < nthr && j < half; j += nthr) {
             for (int p = 0; p < (KIND == KIND_XYZ ? 1 : a.n_products); ++p) {
                 Fe lo[KD], hi[KD];
 #pragma unroll

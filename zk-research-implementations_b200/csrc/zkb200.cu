@@ -283,6 +283,10 @@ struct zkb_ctx {
     unsigned int tail_seq = 0;
     uint32_t tail_log2 = 40;                 // every unsharded round after the first runs in a persistent kernel
     uint32_t small_bytes = SMALL_SMEM_MAX;   // shared-memory budget of k_sc_small (0 = off)
+    bool dt_enabled = false;                 // k_sc_small derives the challenges itself (device transcript), host replays;
+                                             // off by default: measured slower than the host path
+    DtRound* dt_rounds = nullptr;            // mapped host memory, DT_MAX_ROUNDS records
+    uint64_t dt_launches = 0, dt_rounds_checked = 0;
     // ZKB200_TRACE=1: where a persistent-kernel round spends its time (printed at zkb_ctx_destroy)
     bool trace = false, trace_verbose = false, dbg_done = false;
     unsigned long long* d_dbg = nullptr;
@@ -454,6 +458,7 @@ int32_t prep_finish(zkb_ctx* c, int grid, int npts, bool sharded, FinishArgs* f)
     f->partials = c->d_partials;
     f->ticket = c->d_ticket;
     f->stamp = nullptr;
+    f->chk = nullptr;
     if (sharded && !c->use_shm) {
         f->result = c->d_res;
         f->result_wide = c->d_wide;
@@ -745,6 +750,8 @@ struct RoundDriver {
     }
     Fe poly[MAXPTS];         // coefficients of the current round polynomial, if the caller interpolated it already
     int poly_len = -1;
+    TranscriptImpl* tr = nullptr;  // the caller's transcript: lets k_sc_small continue it on the device (device transcript)
+    bool dt = false;               // the live k_sc_small derives its own challenges; the host only checks them
 
     RoundDriver(zkb_ctx* ctx, SumPolyState* s) : c(ctx), sp(s) {}
     ~RoundDriver() { abort(); }
@@ -776,10 +783,13 @@ struct RoundDriver {
     }
     int32_t wait_dev(unsigned int want) {
         uint32_t spins = 0;
-        while (c->mb->dev_seq != want) {
+        // "not yet reached": with the device transcript the kernel does not wait for the host and may already be
+        // several messages ahead, so the sequence number is compared as a counter, not for equality
+        auto behind = [&]() { return (int32_t)(c->mb->dev_seq - want) < 0; };
+        while (behind()) {
             if ((++spins & 0x3fff) == 0) {
                 cudaError_t e = cudaStreamQuery(c->stream);
-                if (e == cudaSuccess && c->mb->dev_seq != want) {
+                if (e == cudaSuccess && behind()) {
                     live = false;
                     ZK_FAIL(c, ZKB_ERR_CUDA, c->mb->dev_error ? "persistent round kernel timed out waiting for the host" : "persistent round kernel exited early");
                 }
@@ -795,6 +805,24 @@ struct RoundDriver {
         }
         asm volatile("" ::: "memory");
         return ZKB_OK;
+    }
+    // The persistent kernels publish a round's sums without a system fence (kernels.cuh FinishArgs::chk): the sequence
+    // number may become visible before the sums, so they are taken only once their checksum matches.
+    int32_t read_msg(Fe* out, int n, unsigned int seq) {
+        for (uint32_t spins = 0;; ++spins) {
+            for (int i = 0; i < n; ++i) out[i] = c->mb->evals[i];
+            const unsigned int g0 = c->mb->dev_chk[0], g1 = c->mb->dev_chk[1];
+            unsigned int c0, c1;
+            msg_checksum(out, n, seq, &c0, &c1);
+            if (c0 == g0 && c1 == g1) return ZKB_OK;
+            if (spins > 50000000u) {
+                abort();
+                ZK_FAIL(c, ZKB_ERR_CUDA, "round message from the device never became consistent");
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
     }
     void begin_mailbox() {
         c->tail_seq += 64;
@@ -814,10 +842,21 @@ struct RoundDriver {
         asm volatile("" ::: "memory");
         c->mb->host_seq = want;  // x86 keeps store order: the payload is visible before the sequence number
     }
-    int32_t launch_small(bool first_eval, const Fe& r) {
+    int32_t launch_small(bool first_eval, const Fe& r, const Fe* claim = nullptr) {
         if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
         SmallArgs a;
         std::memset(&a, 0, sizeof a);
+        // Device transcript: the sponge as it stands now (after the challenge r was drawn, or before round 0) moves
+        // to the kernel; the host keeps its own copy and replays every round behind the device.
+        dt = false;
+        if (tr && c->dt_enabled && c->dt_rounds && sp->npts == 3 && (first_eval || claim) && ilog2_u64(sp->cur_n) + 1 <= DT_MAX_ROUNDS &&
+            tr->hasher.snapshot(a.dt.st, &a.dt.fill_words)) {
+            dt = true;
+            a.dt.enabled = 1;
+            if (claim) a.dt.claim0 = *claim;
+            a.dt.rounds = c->dt_rounds;
+            ++c->dt_launches;
+        }
         for (size_t i = 0; i < sp->sel.size(); ++i) {
             a.in[i] = sp->cur(sp->sel[i]).ref();
             a.out[i] = (sp->state == 2 ? sp->gath[sp->sel[i]] : sp->work[sp->sel[i]]).ref();
@@ -900,7 +939,9 @@ struct RoundDriver {
         if (sp->cur_n >= 2 && small_ok() && sc_occ(c, 0, sp->kind, sp->kD, sp->npts) > 0) {
             ZK_TRY(launch_small(true, c->H.zero()));
             ZK_TRY(wait_dev(base + (++pubs)));
-            for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i] = c->mb->evals[i];
+            if (dt) for (int i = 0; i < sp->npts; ++i) evals[i] = c->dt_rounds[pubs - 1].evals[i];
+            else ZK_TRY(read_msg(evals, sp->npts, base + pubs));
+            for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
             sp->have_evals = true;
             return ZKB_OK;
         }
@@ -912,7 +953,7 @@ struct RoundDriver {
         if (tail_first) {
             ZK_TRY(launch_tail(c->H.zero(), true));
             ZK_TRY(wait_dev(base + (++pubs)));
-            for (int i = 0; i < sp->npts; ++i) evals[i] = c->mb->evals[i];
+            ZK_TRY(read_msg(evals, sp->npts, base + pubs));
             if (sp->sharded && !c->shm.allreduce(c->H, evals, sp->npts)) {
                 abort();
                 ZK_FAIL(c, ZKB_ERR_NCCL, "shared-memory exchange: a peer rank stopped answering");
@@ -936,12 +977,24 @@ struct RoundDriver {
             t_send = __builtin_ia32_rdtsc();
             if (t_recv) c->tr_host += (double)(t_send - t_recv) / tsc_per_us();
         }
-        if (was_live) send(r);  // first, so the device works while the host finishes the claim chain
+        if (was_live && small && dt) {
+            // the device drew this challenge itself after the round the host has just absorbed: they must agree
+            if (!c->H.eq(c->dt_rounds[pubs - 1].chal, r)) {
+                abort();
+                ZK_FAIL(c, ZKB_ERR_CUDA, "device transcript diverged from the host transcript");
+            }
+            ++c->dt_rounds_checked;
+            if (c->trace_verbose) {
+                const long long* t = c->dt_rounds[pubs - 1].t;
+                fprintf(stderr, "[zkb200 trace] device transcript step: interpolate+serialise %lld, absorb+keccak %lld, challenge %lld cycles; claim+record %lld, system fence %lld\n",
+                        t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+            }
+        } else if (was_live) send(r);  // first, so the device works while the host finishes the claim chain
         if (poly_len < 0) poly_len = c->interp[sp->npts].interpolate(sp->last_evals, poly);
         const Fe claim = uni_evaluate(c->H, poly, poly_len, r);
         poly_len = -1;
         if (!was_live) {
-            if (go_small) ZK_TRY(launch_small(false, r));
+            if (go_small) ZK_TRY(launch_small(false, r, &claim));
             else ZK_TRY(launch_tail(r));
         }
         ZK_TRY(wait_dev(base + (++pubs)));
@@ -980,7 +1033,8 @@ struct RoundDriver {
             ZK_FAIL(c, ZKB_ERR_BAD_ARG, "round driver: early stop inside the persistent kernel");
         }
         Fe got[MAXPTS];
-        for (int t = 0; t < sp->npts - 1; ++t) got[t] = c->mb->evals[t];
+        if (small && dt) for (int t = 0; t < sp->npts - 1; ++t) got[t] = c->dt_rounds[pubs - 1].evals[t];
+        else ZK_TRY(read_msg(got, sp->npts - 1, base + pubs));
         if (sp->sharded && !c->shm.allreduce(c->H, got, sp->npts - 1)) {
             abort();
             ZK_FAIL(c, ZKB_ERR_NCCL, "shared-memory exchange: a peer rank stopped answering");
@@ -1003,6 +1057,7 @@ int32_t sp_prove(zkb_ctx* c, SumPolyState* sp, TranscriptImpl* tr, int slots, ui
     Fe evals[MAXPTS], co[MAXPTS];
     if (n_rounds == 0) return sp_final_values(c, sp, final_vals);
     RoundDriver drv(c, sp);
+    if (!as_evals) drv.tr = tr;
     ZK_TRY(drv.first(evals));
     for (int k = 0; k < n_rounds; ++k) {
         int len;
@@ -1281,6 +1336,7 @@ int32_t xyz_phase(zkb_ctx* c, CircuitState* cs, const Table& X, const Table& Y, 
     const RoundInterpolator& ip = c->interp[3];
     Fe evals[3], co[3], fin[3];
     RoundDriver drv(c, sp);
+    drv.tr = tr;
     ZK_TRY(drv.first(evals));
     for (int k = 0; k < nb; ++k) {
         int len = ip.interpolate(evals, co);
@@ -1626,6 +1682,18 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
     }
     c->trace = getenv("ZKB200_TRACE") != nullptr;
     c->trace_verbose = c->trace && std::atoi(getenv("ZKB200_TRACE")) >= 2;
+    // device transcript of k_sc_small: per-round records in mapped host memory
+    {
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, sizeof(DtRound) * DT_MAX_ROUNDS, cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            c->dt_enabled = false;
+        } else {
+            std::memset(hp, 0, sizeof(DtRound) * DT_MAX_ROUNDS);
+            c->dt_rounds = (DtRound*)hp;
+        }
+        if (getenv("ZKB200_DT")) c->dt_enabled = std::atoi(getenv("ZKB200_DT")) != 0 && c->dt_rounds;
+    }
     *out = c.release();
     return ZKB_OK;
 }
@@ -1694,6 +1762,7 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     cudaFreeHost(c->h_res);
     cudaFreeHost(c->h_wide);
     cudaFreeHost((void*)c->mb);
+    if (c->dt_rounds) cudaFreeHost(c->dt_rounds);
     cudaFree(c->d_relay);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1762,6 +1831,17 @@ int32_t zkb_ctx_comm_init(zkb_ctx* c, int32_t rank, int32_t world, const uint8_t
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* c, uint32_t log2_entries) {
     if (!c) return ZKB_ERR_BAD_ARG;
     c->tail_log2 = log2_entries;
+    return ZKB_OK;
+}
+int32_t zkb_ctx_set_device_transcript(zkb_ctx* c, int32_t enable) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    c->dt_enabled = enable != 0 && c->dt_rounds != nullptr;
+    return ZKB_OK;
+}
+int32_t zkb_ctx_device_transcript_stats(const zkb_ctx* c, uint64_t* launches, uint64_t* rounds_checked) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    if (launches) *launches = c->dt_launches;
+    if (rounds_checked) *rounds_checked = c->dt_rounds_checked;
     return ZKB_OK;
 }
 int32_t zkb_ctx_set_small_threshold(zkb_ctx* c, uint32_t smem_bytes) {

@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
         "zkb_ctx_set_gather_threshold": (i32, [vp, u32]),
         "zkb_ctx_set_tail_threshold": (i32, [vp, u32]),
         "zkb_ctx_set_small_threshold": (i32, [vp, u32]),
+        "zkb_ctx_set_device_transcript": (i32, [vp, i32]),
+        "zkb_ctx_device_transcript_stats": (i32, [vp, u64p, u64p]),
         "zkb_mle_upload": (i32, [vp, vp, u64, u64p]),
         "zkb_mle_upload_shard": (i32, [vp, vp, u64, u64p]),
         "zkb_mle_generate": (i32, [vp, u64, u64, u32, u64p]),
@@ -255,6 +257,14 @@ class Context:
 
     def set_small_threshold(self, smem_bytes: int) -> None:
         _ck(self, lib().zkb_ctx_set_small_threshold(self._h, smem_bytes))
+
+    def set_device_transcript(self, enable: bool) -> None:
+        _ck(self, lib().zkb_ctx_set_device_transcript(self._h, 1 if enable else 0))
+
+    def device_transcript_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _ck(self, lib().zkb_ctx_device_transcript_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def set_gather_threshold(self, log2_local: int) -> None:
         _ck(self, lib().zkb_ctx_set_gather_threshold(self._h, log2_local))
