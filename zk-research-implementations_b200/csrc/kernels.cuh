@@ -642,36 +642,6 @@ struct alignas(64) TailMailbox {
     // diagnostics (ZKB200_TRACE=1): device %globaltimer stamps of the last round, see RoundDriver::trace
     unsigned long long ts[8];
 };
-// Wait (one warp) for the host's message number `want` in the mailbox line.  The line is read over PCIe (about 1.8 us
-// per read): the warp keeps POLL_DEPTH reads in flight, issued a fraction of that apart, and examines them in order as
-// they return, so the answer is noticed after ~0.6 of a round trip on average instead of a whole one; reads still in
-// flight when it leaves are simply dropped.  Returns 1 = got it (`word`: this lane's word of the line), 2 = abort,
-// 3 = timeout.
-constexpr int POLL_DEPTH = 4;
-__device__ __forceinline__ unsigned int poll_mailbox(const volatile uint32_t* line, unsigned int want, long long timeout_clocks, int lane,
-                                                     uint32_t& word) {
-    const long long t0 = clock64();
-    uint32_t w[POLL_DEPTH];
-#pragma unroll
-    for (int k = 0; k < POLL_DEPTH; ++k) {
-        w[k] = lane < 16 ? line[lane] : 0u;  // one coalesced 64-byte read
-        if (k + 1 < POLL_DEPTH) __nanosleep(400);
-    }
-    for (;;) {
-#pragma unroll
-        for (int k = 0; k < POLL_DEPTH; ++k) {
-            word = w[k];
-            const uint32_t seq = __shfl_sync(0xffffffffu, word, 8);
-            const uint32_t ab = __shfl_sync(0xffffffffu, word, 9);
-            const uint32_t chk = __shfl_sync(0xffffffffu, word, 10);
-            const uint32_t x = __reduce_xor_sync(0xffffffffu, lane < 8 ? word : 0u);
-            if (ab) return 2;
-            if (seq == want && (x ^ (want * 0x9E3779B9u)) == chk) return 1;
-            if (clock64() - t0 > timeout_clocks) return 3;
-            w[k] = lane < 16 ? line[lane] : 0u;
-        }
-    }
-}
 struct TailRelay {  // device memory: CTA 0 re-publishes the host's message for the other CTAs
     FixedMul rt;
     unsigned int seq;
@@ -732,8 +702,20 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             const unsigned int want = a.base_seq + it;
             if (blockIdx.x == 0 && threadIdx.x < 32) {  // relay warp: host mailbox -> device memory
                 const int lane = threadIdx.x;
+                const volatile uint32_t* line = reinterpret_cast<const volatile uint32_t*>(a.mb);
+                const long long t0 = clock64();
                 uint32_t word = 0;
-                const unsigned int status = poll_mailbox(reinterpret_cast<const volatile uint32_t*>(a.mb), want, a.timeout_clocks, lane, word);
+                unsigned int status = 0;  // 1 = got it, 2 = abort, 3 = timeout
+                while (status == 0) {
+                    word = lane < 16 ? line[lane] : 0u;  // one coalesced 64-byte read over PCIe
+                    const uint32_t seq = __shfl_sync(0xffffffffu, word, 8);
+                    const uint32_t ab = __shfl_sync(0xffffffffu, word, 9);
+                    const uint32_t chk = __shfl_sync(0xffffffffu, word, 10);
+                    const uint32_t x = __reduce_xor_sync(0xffffffffu, lane < 8 ? word : 0u);
+                    if (ab) status = 2;
+                    else if (seq == want && (x ^ (want * 0x9E3779B9u)) == chk) status = 1;
+                    else if (clock64() - t0 > a.timeout_clocks) status = 3;
+                }
                 if (status == 1) {
                     if (lane == 0) a.mb->ts[0] = gtime();
                     Fe r;
@@ -1139,8 +1121,20 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
         if (chal > 0 && !dt) {  // challenge number `chal` from the host mailbox
             if (warp == 0) {
                 const unsigned int want = a.base_seq + chal;
+                const volatile uint32_t* line = reinterpret_cast<const volatile uint32_t*>(a.mb);
+                const long long t0 = clock64();
                 uint32_t word = 0;
-                const unsigned int status = poll_mailbox(reinterpret_cast<const volatile uint32_t*>(a.mb), want, a.timeout_clocks, lane, word);
+                unsigned int status = 0;
+                while (status == 0) {
+                    word = lane < 16 ? line[lane] : 0u;
+                    const uint32_t seq = __shfl_sync(0xffffffffu, word, 8);
+                    const uint32_t ab = __shfl_sync(0xffffffffu, word, 9);
+                    const uint32_t chk = __shfl_sync(0xffffffffu, word, 10);
+                    const uint32_t x = __reduce_xor_sync(0xffffffffu, lane < 8 ? word : 0u);
+                    if (ab) status = 2;
+                    else if (seq == want && (x ^ (want * 0x9E3779B9u)) == chk) status = 1;
+                    else if (clock64() - t0 > a.timeout_clocks) status = 3;
+                }
                 if (lane < 8) s_r.l[lane] = word;
                 if (lane == 0) {
                     s_status = status;
