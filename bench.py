@@ -474,7 +474,8 @@ def main():
         "gpu_launches": launches, "roofline": roof, "clocks": clocks,
     }
     if world == 1:
-        line["gkr"] = gkr_leg(z, ctx, args)
+        if args.gkr_log_inputs > 0:
+            line["gkr"] = gkr_leg(z, ctx, args)
         if args.gkr_uniform_log_gates > 0:
             line["gkr_uniform"] = gkr_uniform_leg(z, args)
     if world == 1 and not args.no_cpu_baseline:
