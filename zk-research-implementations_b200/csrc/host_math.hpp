@@ -15,6 +15,88 @@
 
 namespace zkb {
 
+// Keccak-f[1600], fully unrolled with the 25 lanes in locals (two rounds per loop iteration so that no lane moves).
+// Built twice: for the baseline x86-64 ISA and for BMI1/BMI2 (andn, rorx); picked once at run time.  The transcript
+// hashes at most a few hundred bytes per round, but whole tables when the reference absorbs them
+// (sum_check_protocol.rs:27, the output layer in gkr_protocol.rs:233), where this permutation is the entire cost.
+namespace keccak_detail {
+static inline uint64_t rotl(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+#define KECCAK_ROUND(A,E,rc) do { \
+  uint64_t c0=A##0^A##5^A##10^A##15^A##20, c1=A##1^A##6^A##11^A##16^A##21, c2=A##2^A##7^A##12^A##17^A##22, c3=A##3^A##8^A##13^A##18^A##23, c4=A##4^A##9^A##14^A##19^A##24; \
+  uint64_t d0=c4^rotl(c1,1), d1=c0^rotl(c2,1), d2=c1^rotl(c3,1), d3=c2^rotl(c4,1), d4=c3^rotl(c0,1); \
+  { uint64_t b0=(A##0^d0), b1=rotl((A##6^d1),44), b2=rotl((A##12^d2),43), b3=rotl((A##18^d3),21), b4=rotl((A##24^d4),14); \
+    E##0 = b0 ^ (~b1 & b2) ^ (rc); \
+    E##1 = b1 ^ (~b2 & b3); \
+    E##2 = b2 ^ (~b3 & b4); \
+    E##3 = b3 ^ (~b4 & b0); \
+    E##4 = b4 ^ (~b0 & b1); \
+  } \
+  { uint64_t b0=rotl((A##3^d3),28), b1=rotl((A##9^d4),20), b2=rotl((A##10^d0),3), b3=rotl((A##16^d1),45), b4=rotl((A##22^d2),61); \
+    E##5 = b0 ^ (~b1 & b2); \
+    E##6 = b1 ^ (~b2 & b3); \
+    E##7 = b2 ^ (~b3 & b4); \
+    E##8 = b3 ^ (~b4 & b0); \
+    E##9 = b4 ^ (~b0 & b1); \
+  } \
+  { uint64_t b0=rotl((A##1^d1),1), b1=rotl((A##7^d2),6), b2=rotl((A##13^d3),25), b3=rotl((A##19^d4),8), b4=rotl((A##20^d0),18); \
+    E##10 = b0 ^ (~b1 & b2); \
+    E##11 = b1 ^ (~b2 & b3); \
+    E##12 = b2 ^ (~b3 & b4); \
+    E##13 = b3 ^ (~b4 & b0); \
+    E##14 = b4 ^ (~b0 & b1); \
+  } \
+  { uint64_t b0=rotl((A##4^d4),27), b1=rotl((A##5^d0),36), b2=rotl((A##11^d1),10), b3=rotl((A##17^d2),15), b4=rotl((A##23^d3),56); \
+    E##15 = b0 ^ (~b1 & b2); \
+    E##16 = b1 ^ (~b2 & b3); \
+    E##17 = b2 ^ (~b3 & b4); \
+    E##18 = b3 ^ (~b4 & b0); \
+    E##19 = b4 ^ (~b0 & b1); \
+  } \
+  { uint64_t b0=rotl((A##2^d2),62), b1=rotl((A##8^d3),55), b2=rotl((A##14^d4),39), b3=rotl((A##15^d0),41), b4=rotl((A##21^d1),2); \
+    E##20 = b0 ^ (~b1 & b2); \
+    E##21 = b1 ^ (~b2 & b3); \
+    E##22 = b2 ^ (~b3 & b4); \
+    E##23 = b3 ^ (~b4 & b0); \
+    E##24 = b4 ^ (~b0 & b1); \
+  } \
+} while (0)
+
+#define ZK_KECCAK_BODY \
+    static const uint64_t RC[24] = { \
+        0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull, \
+        0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull, \
+        0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, \
+        0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull, \
+        0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull}; \
+    uint64_t a0 = st[0], a1 = st[1], a2 = st[2], a3 = st[3], a4 = st[4], a5 = st[5], a6 = st[6], a7 = st[7], a8 = st[8], a9 = st[9], \
+             a10 = st[10], a11 = st[11], a12 = st[12], a13 = st[13], a14 = st[14], a15 = st[15], a16 = st[16], a17 = st[17], \
+             a18 = st[18], a19 = st[19], a20 = st[20], a21 = st[21], a22 = st[22], a23 = st[23], a24 = st[24]; \
+    uint64_t e0, e1, e2, e3, e4, e5, e6, e7, e8, e9, e10, e11, e12, e13, e14, e15, e16, e17, e18, e19, e20, e21, e22, e23, e24; \
+    for (int r = 0; r < 24; r += 2) { \
+        KECCAK_ROUND(a, e, RC[r]); \
+        KECCAK_ROUND(e, a, RC[r + 1]); \
+    } \
+    st[0] = a0; st[1] = a1; st[2] = a2; st[3] = a3; st[4] = a4; st[5] = a5; st[6] = a6; st[7] = a7; st[8] = a8; st[9] = a9; \
+    st[10] = a10; st[11] = a11; st[12] = a12; st[13] = a13; st[14] = a14; st[15] = a15; st[16] = a16; st[17] = a17; \
+    st[18] = a18; st[19] = a19; st[20] = a20; st[21] = a21; st[22] = a22; st[23] = a23; st[24] = a24;
+inline void permute_plain(uint64_t* st) { ZK_KECCAK_BODY }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("bmi,bmi2"))) inline void permute_bmi(uint64_t* st) { ZK_KECCAK_BODY }
+#endif
+#undef ZK_KECCAK_BODY
+#undef KECCAK_ROUND
+}  // namespace keccak_detail
+typedef void (*keccak_fn)(uint64_t*);
+inline keccak_fn keccak_f1600() {
+    static const keccak_fn fn = [] {
+#if defined(__x86_64__) && defined(__GNUC__)
+        if (__builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2")) return (keccak_fn)keccak_detail::permute_bmi;
+#endif
+        return (keccak_fn)keccak_detail::permute_plain;
+    }();
+    return fn;
+}
+
 // ------------------------------------------------------------- Keccak-256
 // sha3 0.10.8 `Keccak256` = Keccak[r=1088,c=512] with the ORIGINAL 0x01 padding
 // (not SHA3's 0x06).  Sponge state is 25 lanes; absorption is sequential.
@@ -84,35 +166,7 @@ class Keccak256 {
         }
         permute();
     }
-    void permute() {
-        static const uint64_t RC[24] = {
-            0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull,
-            0x000000000000808bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
-            0x000000000000008aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000aull,
-            0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull, 0x8000000000008003ull,
-            0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
-            0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
-        // rho offsets indexed [x + 5y]
-        static const int RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
-        uint64_t* a = st_;
-        for (int rnd = 0; rnd < 24; ++rnd) {
-            uint64_t c[5], b[25];
-            for (int x = 0; x < 5; ++x) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
-            for (int x = 0; x < 5; ++x) {
-                uint64_t d = c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1);
-                for (int y = 0; y < 25; y += 5) a[y + x] ^= d;
-            }
-            for (int x = 0; x < 5; ++x)
-                for (int y = 0; y < 5; ++y) {
-                    int r = RHO[x + 5 * y];
-                    uint64_t v = a[x + 5 * y];
-                    b[y + 5 * ((2 * x + 3 * y) % 5)] = r ? rotl(v, r) : v;
-                }
-            for (int y = 0; y < 25; y += 5)
-                for (int x = 0; x < 5; ++x) a[y + x] = b[y + x] ^ (~b[y + (x + 1) % 5] & b[y + (x + 2) % 5]);
-            a[0] ^= RC[rnd];
-        }
-    }
+    void permute() { keccak_f1600()(st_); }
 };
 
 // ------------------------------------------------------- host field helper
