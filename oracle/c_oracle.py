@@ -57,6 +57,8 @@ def lib():
         _lib.zko_circuit_evaluate.argtypes = [C.c_int, C.c_int, u32p, u8p, u64p, C.c_size_t, u64p]
         _lib.zko_gkr_prove.argtypes = [C.c_int, C.c_int, u32p, u8p, u64p, C.c_size_t, u64p, u64p, i32p, u64p, u64p,
                                        u64p]
+        _lib.zko_gkr_prove_wired.argtypes = [C.c_int, C.c_int, u32p, C.c_size_t, u8p, u32p, u32p, u64p, u64p, u64p, i32p, u64p,
+                                             u64p, u64p]
         _lib.zko_vec_op.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p, C.c_size_t]
         _lib.zko_set_threads.argtypes = [C.c_int]
         _lib.zko_max_threads.restype = C.c_int
@@ -267,6 +269,42 @@ def gkr_prove(field: int, gates: Sequence[int], ops: np.ndarray, inputs: np.ndar
         off += nr
     ce = arr_to_ints(claimed[: L - 1]) if L > 1 else []
     return dict(output_poly=arr_to_ints(w0), proof_polynomials=polys,
+                claimed_evaluations=[(ce[2 * i], ce[2 * i + 1]) for i in range(L - 1)],
+                final_openings=tuple(arr_to_ints(fin)), challenges=ch)
+
+
+def gkr_prove_wired(field: int, n_inputs: int, layers, inputs: np.ndarray, want_challenges: bool = True):
+    """General wiring (extension): layers = [(ops, in1, in2), ...] input side first.  -> dict as gkr_prove."""
+    g = np.array([len(l[0]) for l in layers], dtype=np.uint32)
+    ops = np.ascontiguousarray(np.concatenate([np.asarray(l[0], dtype=np.uint8) for l in layers]))
+    in1 = np.ascontiguousarray(np.concatenate([np.asarray(l[1], dtype=np.uint32) for l in layers]))
+    in2 = np.ascontiguousarray(np.concatenate([np.asarray(l[2], dtype=np.uint32) for l in layers]))
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+    L = len(g)
+    widths = [int(n_inputs)] + [int(x) for x in g[:-1]]
+    rounds_per_layer = [2 * (w.bit_length() - 1) for w in widths[::-1]]
+    total = sum(rounds_per_layer)
+    n0 = max(int(g[-1]), 2)
+    w0 = np.zeros((n0, 4), dtype=np.uint64)
+    coeffs = np.zeros((total, 3, 4), dtype=np.uint64)
+    lens = np.zeros(total, dtype=np.int32)
+    chals = np.zeros((total, 4), dtype=np.uint64)
+    claimed = np.zeros((max(L - 1, 1), 2, 4), dtype=np.uint64)
+    fin = np.zeros((2, 4), dtype=np.uint64)
+    rc = lib().zko_gkr_prove_wired(field, L, g.ctypes.data_as(u32p), int(n_inputs), ops.ctypes.data_as(u8p), in1.ctypes.data_as(u32p),
+                                   in2.ctypes.data_as(u32p), _p(inputs), _p(w0), _p(coeffs), lens.ctypes.data_as(i32p), _p(chals),
+                                   _p(claimed), _p(fin))
+    if rc < 0:
+        raise ValueError(f"zko_gkr_prove_wired rc={rc}")
+    assert rc == total, (rc, total)
+    polys, ch, off = [], [], 0
+    for nr in rounds_per_layer:
+        polys.append([arr_to_ints(coeffs[off + k, : lens[off + k]]) for k in range(nr)])
+        if want_challenges:
+            ch.append(arr_to_ints(chals[off: off + nr]))
+        off += nr
+    ce = arr_to_ints(claimed[: L - 1]) if L > 1 else []
+    return dict(output_poly=arr_to_ints(w0) if n0 <= (1 << 16) else w0, proof_polynomials=polys,
                 claimed_evaluations=[(ce[2 * i], ce[2 * i + 1]) for i in range(L - 1)],
                 final_openings=tuple(arr_to_ints(fin)), challenges=ch)
 

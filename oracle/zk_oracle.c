@@ -932,6 +932,145 @@ int zko_gkr_prove(int field, int n_layers, const uint32_t* gates, const u8* ops,
     return round_base;
 }
 
+/* General wiring (EXTENSION beyond the reference; see oracle/pyref.py wired_prove_sparse, which is asserted equal to the
+ * dense general-index construction on small circuits): gate g of layer l reads wires in1[g], in2[g] of the layer
+ * below (the inputs for l = 0); every width a power of two; the output layer may be wide, in which case
+ * initiate_protocol (:229-241) draws log2(outputs) consecutive challenges.  Everything else is gkr_protocol::prove
+ * :31-91 in its two-phase form.  ops/in1/in2 are concatenated per gate in layer order (input side first).
+ * w0_out: max(outputs, 2) elements.  Returns the total number of rounds, or <0 on a malformed circuit. */
+int zko_gkr_prove_wired(int field, int n_layers, const uint32_t* gates, size_t n_inputs, const u8* ops, const uint32_t* in1,
+                        const uint32_t* in2, const u64* inputs, u64* w0_out, u64* coeffs, int32_t* lens, u64* chals,
+                        u64* claimed, u64 final_out[8]) {
+    const fctx* F = &FIELDS[field];
+    if (n_layers < 1 || n_inputs < 2 || (n_inputs & (n_inputs - 1))) return -1;
+    size_t* opoff = (size_t*)malloc(sizeof(size_t) * (size_t)n_layers);
+    size_t* width = (size_t*)malloc(sizeof(size_t) * (size_t)n_layers);
+    {
+        size_t off = 0;
+        for (int l = 0; l < n_layers; ++l) {
+            size_t G = gates[l];
+            width[l] = l == 0 ? n_inputs : gates[l - 1];
+            if (!G || (G & (G - 1)) || width[l] < 2) return -2;
+            opoff[l] = off;
+            for (size_t g = 0; g < G; ++g)
+                if (in1[off + g] >= width[l] || in2[off + g] >= width[l]) return -3;
+            off += G;
+        }
+    }
+    zko_transcript* t = zko_transcript_new(field);
+    fe* in = load_table(F, inputs, n_inputs);
+    fe** lo = (fe**)malloc(sizeof(fe*) * (size_t)n_layers);
+    for (int l = 0; l < n_layers; ++l) { /* Circuit::evaluate :127-143 with general wiring */
+        const fe* cur = l == 0 ? in : lo[l - 1];
+        size_t G = gates[l];
+        lo[l] = (fe*)malloc(G * sizeof(fe));
+#pragma omp parallel for schedule(static)
+        for (size_t g = 0; g < G; ++g) {
+            fe a = cur[in1[opoff[l] + g]], b = cur[in2[opoff[l] + g]];
+            lo[l][g] = ops[opoff[l] + g] ? f_mul(F, a, b) : f_add(F, a, b);
+        }
+    }
+    const size_t Gout = gates[n_layers - 1], n0 = Gout < 2 ? 2 : Gout;
+    const int k0 = ilog2u(n0);
+    fe* w0 = (fe*)calloc(n0, sizeof(fe));
+    memcpy(w0, lo[n_layers - 1], Gout * sizeof(fe));
+    for (size_t i = 0; i < n0; ++i) f_from_mont(F, w0[i], w0_out + 4 * i);
+    tr_append_fe(t, w0, n0);
+    fe r0[40];
+    for (int i = 0; i < k0; ++i) r0[i] = tr_challenge(t);
+    fe m0 = mle_evaluate(F, w0, (uint32_t)k0, r0);
+    free(w0);
+    tr_append_fe(t, &m0, 1);
+
+    fe alpha = f_zero(), beta = f_zero();
+    fe rb[40], rc[40];
+    int nrb = 0, round_base = 0;
+    fe o1 = f_zero(), o2 = f_zero();
+    for (int idx = 0; idx < n_layers; ++idx) {
+        const int l = n_layers - 1 - idx;
+        const size_t G = gates[l], nw = width[l];
+        const u8* lops = ops + opoff[l];
+        const uint32_t *a1 = in1 + opoff[l], *a2 = in2 + opoff[l];
+        const fe* W = l == 0 ? in : lo[l - 1];
+        const int nb = ilog2u(nw);
+        fe* coef = (fe*)malloc(G * sizeof(fe));
+        if (idx == 0) {
+            fe* e = eq_table(F, r0, k0);
+            for (size_t g = 0; g < G; ++g) coef[g] = e[g];
+            free(e);
+        } else {
+            if (((size_t)1 << nrb) != G) return -5;
+            fe* ea = eq_table(F, rb, nrb);
+            fe* eb = eq_table(F, rc, nrb);
+            for (size_t g = 0; g < G; ++g) coef[g] = f_add(F, f_mul(F, alpha, ea[g]), f_mul(F, beta, eb[g]));
+            free(ea);
+            free(eb);
+        }
+        fe* X = (fe*)malloc(nw * sizeof(fe));
+        fe* H1 = (fe*)calloc(nw, sizeof(fe));
+        fe* HA2 = (fe*)calloc(nw, sizeof(fe));
+        memcpy(X, W, nw * sizeof(fe));
+        for (size_t g = 0; g < G; ++g) {
+            const size_t b = a1[g], c = a2[g];
+            const fe cw = f_mul(F, coef[g], W[c]);
+            if (lops[g] == 0) {
+                H1[b] = f_add(F, H1[b], coef[g]);
+                HA2[b] = f_add(F, HA2[b], cw);
+            } else {
+                H1[b] = f_add(F, H1[b], cw);
+            }
+        }
+        fe u[40], v[40], Wu, Wv;
+        sumcheck_xy_z(t, X, H1, HA2, nb, coeffs + (size_t)round_base * 12, lens + round_base, chals + (size_t)round_base * 4, u, &Wu);
+        fe* eu = eq_table(F, u, nb);
+        fe* C = (fe*)calloc(nw, sizeof(fe));
+        fe* D = (fe*)calloc(nw, sizeof(fe));
+        memcpy(X, W, nw * sizeof(fe));
+        for (size_t g = 0; g < G; ++g) {
+            const size_t b = a1[g], c = a2[g];
+            const fe val = f_mul(F, coef[g], eu[b]);
+            if (lops[g] == 0) {
+                C[c] = f_add(F, C[c], val);
+                D[c] = f_add(F, D[c], f_mul(F, Wu, val));
+            } else {
+                C[c] = f_add(F, C[c], f_mul(F, Wu, val));
+            }
+        }
+        sumcheck_xy_z(t, X, C, D, nb, coeffs + (size_t)(round_base + nb) * 12, lens + round_base + nb,
+                      chals + (size_t)(round_base + nb) * 4, v, &Wv);
+        round_base += 2 * nb;
+        free(eu);
+        free(C);
+        free(D);
+        free(X);
+        free(H1);
+        free(HA2);
+        free(coef);
+        memcpy(rb, u, sizeof(fe) * (size_t)nb);
+        memcpy(rc, v, sizeof(fe) * (size_t)nb);
+        nrb = nb;
+        o1 = Wu;
+        o2 = Wv;
+        if (idx < n_layers - 1) {
+            tr_append_fe(t, &o1, 1);
+            alpha = tr_challenge(t);
+            tr_append_fe(t, &o2, 1);
+            beta = tr_challenge(t);
+            f_from_mont(F, o1, claimed + (size_t)idx * 8);
+            f_from_mont(F, o2, claimed + (size_t)idx * 8 + 4);
+        }
+    }
+    f_from_mont(F, o1, final_out);
+    f_from_mont(F, o2, final_out + 4);
+    for (int l = 0; l < n_layers; ++l) free(lo[l]);
+    free(lo);
+    free(opoff);
+    free(width);
+    free(in);
+    zko_transcript_free(t);
+    return round_base;
+}
+
 /* Elementwise field ops for checking device helpers: op 0 add, 1 sub, 2 mul */
 void zko_vec_op(int field, int op, const u64* a, const u64* b, u64* out, size_t n) {
     const fctx* F = &FIELDS[field];

@@ -412,6 +412,26 @@ def test_wired_gkr_matches_oracle(zkb, ctxs, fid, p):
         dc.free()
 
 
+def test_wired_gkr_large_vs_c_oracle(zkb, ctxs, oracle):
+    """2^16-wide uniform layers with random wiring (all three round-driver regimes per phase): device == C oracle."""
+    ctx = ctxs(0, 0)
+    p = R.BN254_FR
+    nrng = np.random.default_rng(17)
+    G = 1 << 16
+    spec = [(nrng.integers(0, 2, size=G, dtype=np.uint8), nrng.integers(0, G, size=G, dtype=np.uint32),
+             nrng.integers(0, G, size=G, dtype=np.uint32)) for _ in range(3)]
+    inputs = oracle.synth_table(0, 41, 0, 16)
+    ref = oracle.gkr_prove_wired(0, G, spec, inputs)
+    dc = zkb.gkr_circuit.WiredCircuit(ctx, G, spec)
+    pr = zkb.gkr_protocol.prove_wired(dc, arr_to_ints(inputs))
+    assert pr.output_poly == ref["output_poly"]
+    assert [[q.coefficients for q in layer] for layer in pr.proof_polynomials] == ref["proof_polynomials"]
+    assert pr.claimed_evaluations == ref["claimed_evaluations"] and pr.final_openings == ref["final_openings"]
+    assert pr.challenges == ref["challenges"]
+    assert zkb.gkr_protocol.verify_wired(pr, dc, arr_to_ints(inputs))
+    dc.free()
+
+
 @pytest.mark.parametrize("fid,p", FIELDS)
 def test_wired_reduces_to_reference_wiring_on_device(zkb, ctxs, fid, p):
     """in1 = 2g, in2 = 2g+1, <= 2 outputs: zkb_gkr_prove_wired produces the bytes of zkb_gkr_prove."""

@@ -208,3 +208,23 @@ def test_wired_sparse_equals_dense(fid, p):
         bad_inp = list(inp)
         bad_inp[-1] = (bad_inp[-1] + 1) % p
         assert not R.wired_verify_sparse(sparse, wc, bad_inp, p)
+
+
+@pytest.mark.parametrize("fid,p", FIELDS)
+def test_wired_c_oracle_matches_python(oracle, fid, p):
+    """The two restatements of the general-wiring prover (C two-phase, Python two-phase == Python dense) agree."""
+    rng = random.Random(99 + fid)
+    for nin, gates in [(2, [1]), (2, [4]), (8, [4, 8, 2]), (4, [8, 4, 4, 1]), (64, [128, 32, 64]), (256, [256, 256])]:
+        wc = random_wired(rng, nin, gates)
+        inp = [rng.randrange(p) for _ in range(nin)]
+        ref = R.wired_prove_sparse(wc, inp, p)
+        c = oracle.gkr_prove_wired(fid, nin, [(l.ops, l.in1, l.in2) for l in wc.layers], ints_to_arr(inp))
+        assert c["output_poly"] == ref.output_poly and c["proof_polynomials"] == ref.proof_polynomials
+        assert c["claimed_evaluations"] == ref.claimed_evaluations and c["final_openings"] == ref.final_openings
+    # and on the reference's own wiring the C wired prover is the C tree prover
+    struct, nin = random_circuit(rng, 5, 2)
+    inp = [rng.randrange(p) for _ in range(nin)]
+    ops = np.array([o for l in struct for o in l], dtype=np.uint8)
+    a = oracle.gkr_prove(fid, [len(l) for l in struct], ops, ints_to_arr(inp))
+    b = oracle.gkr_prove_wired(fid, nin, [(l, [2 * g for g in range(len(l))], [2 * g + 1 for g in range(len(l))]) for l in struct], ints_to_arr(inp))
+    assert a == b
