@@ -64,7 +64,18 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout_s: float) -> None:
+        """Block until nvidia-smi has delivered its first line: its start-up (process spawn, NVML initialisation, which
+        touches every GPU of the box) must not fall into the timed region."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self) -> None:
+        """Samples from here on are 'under load'."""
+        self.t_mark = time.perf_counter()
 
     def stop(self) -> dict:
         if not self.proc:
@@ -77,7 +88,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        rows = [r for t, r in self.rows if t >= t_mark] or [r for _, r in self.rows]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -360,10 +373,15 @@ def main():
 
     # ---------------------------------------------------------------- resident (`value`)
     raw = S.RawGkrProver(sp)  # the bare C-ABI call; outputs are Montgomery limbs as a Rust caller receives them
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first(2.0)
+    barrier()
+    if sampler:
+        sampler.mark()
     for _ in range(warmup):
         raw.prove(T(z.BN254_FR))
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     ctx.profile(True)
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
