@@ -90,6 +90,9 @@ const char* zkb_kernel_name(int32_t kernel_id);
  * 128-byte ncclUniqueId produced by zkb_comm_unique_id on rank 0 and broadcast by the launcher. */
 int32_t zkb_comm_unique_id(uint8_t out[128]);
 int32_t zkb_ctx_comm_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8_t unique_id[128]);
+/* Local (per-rank) table size, as log2 entries, at which the shards are all-gathered and the remaining rounds run on
+ * every rank alone.  0 (default) = automatic: as soon as the replicated table fits the on-chip kernel, or 2^14 when
+ * the ranks' hosts cannot exchange the round sums through shared memory. */
 int32_t zkb_ctx_set_gather_threshold(zkb_ctx* ctx, uint32_t log2_local_entries);
 /* Rounds whose tables have at most 2^log2_entries entries run inside ONE persistent cooperative kernel that
  * exchanges round sums / challenges with the host transcript through a mailbox in mapped host memory

@@ -33,7 +33,7 @@ def main():
     solo = z.Context(fid, local, z.MODE_FULL)  # no communicator: the single-GPU engine on the whole table
     S, T = z.sum_check_protocol, z.fiat_shamir.Transcript
     ok = True
-    for n, P, D, thr in ((6, 1, 2, 1), (10, 2, 3, 3), (14, 1, 2, 12), (16, 2, 2, 8), (18, 1, 3, 12)):
+    for n, P, D, thr in ((6, 1, 2, 1), (10, 2, 3, 3), (14, 1, 2, 12), (16, 2, 2, 8), (18, 1, 3, 12), (15, 1, 2, 0), (17, 2, 3, 0)):  # 0 = automatic
         ctx.set_gather_threshold(thr)
         full = [O.synth_table(fid, 77 + n, t, n) for t in range(P * D)]
         mont = [z.engine.to_mont(fid, f) for f in full]

@@ -272,7 +272,7 @@ struct zkb_ctx {
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, log2world = 0;
-    uint32_t gather_log2 = 14;
+    uint32_t gather_log2 = 0;                // 0 = automatic (gather_threshold_n)
     ShmComm shm;
     bool use_shm = false;
     RoundInterpolator interp[MAXPTS + 1];
@@ -579,6 +579,20 @@ int32_t sp_ensure_work(zkb_ctx* c, SumPolyState* sp) {
 }
 
 // C2: gather every rank's shard of every table and interleave to global order.
+// Local table size at which the shards are gathered (C2).  Automatic: as soon as the REPLICATED table fits the on-chip
+// kernel, so the rounds after the gather are one k_sc_small launch; with the per-round NCCL fallback (no shared
+// memory between the ranks' hosts) every sharded round is a launch and an all-reduce, so gather early instead.
+uint64_t gather_threshold_n(const zkb_ctx* c, const SumPolyState* sp) {
+    if (c->gather_log2) return 1ull << c->gather_log2;
+    if (c->use_shm && c->small_bytes && sp->rest.empty() && !sp->sel.empty()) {
+        const uint64_t budget = c->small_bytes < (uint32_t)SMALL_SMEM_MAX ? c->small_bytes : (uint32_t)SMALL_SMEM_MAX;
+        uint64_t n = 1;
+        while (2 * n * sp->sel.size() * 32 <= budget) n *= 2;
+        const uint64_t g = n >> c->log2world;
+        if (g >= 2) return g;
+    }
+    return 1ull << 14;
+}
 int32_t sp_gather(zkb_ctx* c, SumPolyState* sp) {
     const int T = (int)sp->src.size();
     const uint64_t nl = sp->cur_n, G = (uint64_t)c->world;
@@ -607,7 +621,7 @@ int32_t sp_gather(zkb_ctx* c, SumPolyState* sp) {
 // Fold every table with r; if `evals` != NULL also return the next round's evaluations (one pass).
 int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, Fe* final_vals) {
     if (sp->cur_n < 2) ZK_FAIL(c, ZKB_ERR_ARITY, "bind: no variable left");
-    if (sp->sharded && sp->cur_n <= (1ull << (c->gather_log2 < 1 ? 1 : c->gather_log2))) ZK_TRY(sp_gather(c, sp));
+    if (sp->sharded && sp->cur_n <= gather_threshold_n(c, sp)) ZK_TRY(sp_gather(c, sp));
     const int T = (int)sp->src.size();
     if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
     const uint64_t n_out = sp->cur_n / 2;
@@ -771,7 +785,7 @@ struct RoundDriver {
         return n >= 2 ? n : 0;
     }
     bool small_ok() const { return sp->cur_n >= 2 && sp->cur_n <= small_cap(); }
-    uint64_t gather_n() const { return 1ull << (c->gather_log2 < 1 ? 1 : c->gather_log2); }
+    uint64_t gather_n() const { return gather_threshold_n(c, sp); }
     bool tail_ok() const {
         // products of >= 3 factors: the persistent kernel spills with the challenge table in shared memory,
         // so their large (throughput-bound) rounds stay one launch each
@@ -1851,7 +1865,7 @@ int32_t zkb_ctx_set_small_threshold(zkb_ctx* c, uint32_t smem_bytes) {
 }
 int32_t zkb_ctx_set_gather_threshold(zkb_ctx* c, uint32_t log2_local_entries) {
     if (!c) return ZKB_ERR_BAD_ARG;
-    c->gather_log2 = log2_local_entries < 1 ? 1 : log2_local_entries;
+    c->gather_log2 = log2_local_entries;  // 0 = automatic
     return ZKB_OK;
 }
 
