@@ -86,8 +86,10 @@ const char* zkb_kernel_name(int32_t kernel_id);
 
 /* Multi-GPU (one process per GPU).  The table is sharded on LOW index bits: rank j of 2^g holds entries
  * i with i mod 2^g == j, so both halves of every bound variable stay local.  Per round the
- * (d+1) partial sums are combined with one ncclAllReduce over widened limbs.  `unique_id` is the
- * 128-byte ncclUniqueId produced by zkb_comm_unique_id on rank 0 and broadcast by the launcher. */
+ * (d+1) partial sums of the ranks are combined by their host threads through a POSIX shared-memory segment
+ * (ranks of one box; about 1 us) or, when that segment cannot be opened (ZKB200_NO_SHM=1, several hosts), with one
+ * ncclAllReduce over zero-extended limbs; NCCL over NVLink carries the all-gather of the shrunken tables.
+ * `unique_id` is the 128-byte ncclUniqueId produced by zkb_comm_unique_id on rank 0 and broadcast by the launcher. */
 int32_t zkb_comm_unique_id(uint8_t out[128]);
 int32_t zkb_ctx_comm_init(zkb_ctx* ctx, int32_t rank, int32_t world, const uint8_t unique_id[128]);
 /* Local (per-rank) table size, as log2 entries, at which the shards are all-gathered and the remaining rounds run on
