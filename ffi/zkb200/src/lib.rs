@@ -7,6 +7,7 @@
 //! `F` must be one of the three 4-limb Montgomery fields the library instantiates.  The element <-> limb
 //! cast relies on ark-ff 0.5's layout `Fp<MontBackend<C, 4>, 4>(BigInt<4>([u64; 4]), PhantomData)`.
 pub mod field;
+pub mod gkr;
 pub mod multilinear_polynomial;
 pub mod sum_check_protocol;
 
