@@ -751,6 +751,18 @@ static fe* eq_table(const fctx* F, const fe* r, int n) {
     t[0] = f_one(F);
     for (int k = 0; k < n; ++k) {
         size_t len = (size_t)1 << k;
+        if (len >= 4096) { /* large level: out of place so that the iterations are independent */
+            fe* prev = (fe*)malloc(len * sizeof(fe));
+            memcpy(prev, t, len * sizeof(fe));
+#pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < len; ++i) {
+                fe hi = f_mul(F, prev[i], r[k]);
+                t[2 * i] = f_sub(F, prev[i], hi);
+                t[2 * i + 1] = hi;
+            }
+            free(prev);
+            continue;
+        }
         for (size_t i = len; i-- > 0;) {
             fe hi = f_mul(F, t[i], r[k]);
             t[2 * i] = f_sub(F, t[i], hi);
@@ -769,13 +781,25 @@ static void sumcheck_xy_z(zko_transcript* t, fe* X, fe* Y, fe* Z, int n, u64* co
     for (int k = 0; k < n; ++k) {
         size_t h = len / 2;
         fe s0 = f_zero(), s1 = f_zero(), s2 = f_zero();
-        for (size_t i = 0; i < h; ++i) {
-            fe x0 = X[i], x1 = X[i + h], y0 = Y[i], y1 = Y[i + h], z0 = Z[i], z1 = Z[i + h];
-            fe x2 = f_sub(F, f_add(F, x1, x1), x0), y2 = f_sub(F, f_add(F, y1, y1), y0),
-               z2 = f_sub(F, f_add(F, z1, z1), z0);
-            s0 = f_add(F, s0, f_add(F, f_mul(F, x0, y0), z0));
-            s1 = f_add(F, s1, f_add(F, f_mul(F, x1, y1), z1));
-            s2 = f_add(F, s2, f_add(F, f_mul(F, x2, y2), z2));
+        /* modular sums are order-independent (canonical residues), so the OpenMP split gives the same bits */
+#pragma omp parallel if (h >= 4096)
+        {
+            fe a0 = f_zero(), a1 = f_zero(), a2 = f_zero();
+#pragma omp for schedule(static) nowait
+            for (size_t i = 0; i < h; ++i) {
+                fe x0 = X[i], x1 = X[i + h], y0 = Y[i], y1 = Y[i + h], z0 = Z[i], z1 = Z[i + h];
+                fe x2 = f_sub(F, f_add(F, x1, x1), x0), y2 = f_sub(F, f_add(F, y1, y1), y0),
+                   z2 = f_sub(F, f_add(F, z1, z1), z0);
+                a0 = f_add(F, a0, f_add(F, f_mul(F, x0, y0), z0));
+                a1 = f_add(F, a1, f_add(F, f_mul(F, x1, y1), z1));
+                a2 = f_add(F, a2, f_add(F, f_mul(F, x2, y2), z2));
+            }
+#pragma omp critical
+            {
+                s0 = f_add(F, s0, a0);
+                s1 = f_add(F, s1, a1);
+                s2 = f_add(F, s2, a2);
+            }
         }
         fe ys[3] = {s0, s1, s2}, c[3];
         int cl = uni_interpolate(F, xs, ys, 3, c);
@@ -786,6 +810,7 @@ static void sumcheck_xy_z(zko_transcript* t, fe* X, fe* Y, fe* Z, int n, u64* co
         fe r = tr_challenge(t);
         rs[k] = r;
         f_from_mont(F, r, chals + 4 * (size_t)k);
+#pragma omp parallel for schedule(static) if (h >= 4096)
         for (size_t i = 0; i < h; ++i) {
             X[i] = f_add(F, X[i], f_mul(F, r, f_sub(F, X[i + h], X[i])));
             Y[i] = f_add(F, Y[i], f_mul(F, r, f_sub(F, Y[i + h], Y[i])));
@@ -864,6 +889,7 @@ int zko_gkr_prove(int field, int n_layers, const uint32_t* gates, const u8* ops,
             fe* ea = eq_table(F, rb, nrb);
             fe* eb = eq_table(F, rc, nrb);
             if (((size_t)1 << nrb) != G) return -5;
+#pragma omp parallel for schedule(static) if (G >= 4096)
             for (size_t g = 0; g < G; ++g) coef[g] = f_add(F, f_mul(F, alpha, ea[g]), f_mul(F, beta, eb[g]));
             free(ea);
             free(eb);
@@ -872,7 +898,8 @@ int zko_gkr_prove(int field, int n_layers, const uint32_t* gates, const u8* ops,
         fe* H1 = (fe*)calloc(nw, sizeof(fe));
         fe* HA2 = (fe*)calloc(nw, sizeof(fe));
         memcpy(X, W, nw * sizeof(fe));
-        for (size_t g = 0; g < G; ++g) {
+#pragma omp parallel for schedule(static) if (G >= 4096)
+        for (size_t g = 0; g < G; ++g) { /* gate g owns wires 2g, 2g+1: no two iterations touch the same entry */
             size_t b = 2 * g, c = 2 * g + 1;
             if (lops[g] == 0) {
                 H1[b] = coef[g];
@@ -888,6 +915,7 @@ int zko_gkr_prove(int field, int n_layers, const uint32_t* gates, const u8* ops,
         fe* C = (fe*)calloc(nw, sizeof(fe));
         fe* D = (fe*)calloc(nw, sizeof(fe));
         memcpy(X, W, nw * sizeof(fe));
+#pragma omp parallel for schedule(static) if (G >= 4096)
         for (size_t g = 0; g < G; ++g) {
             size_t b = 2 * g, c = 2 * g + 1;
             fe val = f_mul(F, coef[g], eu[b]);
