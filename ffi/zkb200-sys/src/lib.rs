@@ -101,6 +101,7 @@ extern "C" {
     pub fn zkb_circuit_create(ctx: *mut zkb_ctx, n_layers: u32, gates_per_layer: *const u32, ops: *const u8, out: *mut zkb_circ) -> i32;
     pub fn zkb_circuit_free(ctx: *mut zkb_ctx, c: zkb_circ) -> i32;
     pub fn zkb_circuit_evaluate(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, outputs_mont: *mut u64) -> i32;
+    pub fn zkb_layer_add_mul_i(ctx: *mut zkb_ctx, ops: *const u8, n_gates: u32, op: i32, out: *mut zkb_mle) -> i32;
     pub fn zkb_gkr_prove(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *mut u64, coeffs: *mut u64, lens: *mut i32, challenges: *mut u64, claimed: *mut u64, final_openings: *mut u64, n_rounds: *mut u32) -> i32;
     pub fn zkb_gkr_verify(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *const u64, coeffs: *const u64, lens: *const i32, claimed: *const u64, final_openings: *const u64, accepted: *mut i32) -> i32;
     pub fn zkb_gkr_total_rounds(n_layers: u32, gates_per_layer: *const u32) -> u32;

@@ -32,6 +32,13 @@ def test_library_exports_every_declared_symbol(zkb):
     assert b"sm_100a" in lib.zkb_version()
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """ffi/zkb200-sys (the binding a maintainer adds; not compilable here) must not drift from the header."""
+    rs = open(os.path.join(ROOT, "ffi", "zkb200-sys", "src", "lib.rs")).read()
+    missing = [name for name in header_symbols() if not re.search(r"pub fn %s\b" % name, rs)]
+    assert not missing, f"declared in include/zkb200.h but not in ffi/zkb200-sys/src/lib.rs: {missing}"
+
+
 def test_no_cpu_fallback(zkb):
     import torch
 
