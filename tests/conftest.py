@@ -23,12 +23,25 @@ def oracle():
     return c_oracle
 
 
+def _stale(so: str) -> bool:
+    """True if the prebuilt library was not built from the sources in the tree (the Makefile bakes csrc/src_hash.py's
+    hash into zkb_version())."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_zkb_src_hash", os.path.join(ROOT, PKG, "csrc", "src_hash.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(so, "rb") as f:
+        return ("src:" + mod.src_hash()).encode() not in f.read()
+
+
 @pytest.fixture(scope="session")
 def zkb():
     """The product package (hyphenated directory name -> importlib).  The shared library is a build artefact
     (git-ignored): compile it first if this is a fresh checkout.  There is still no fallback: if the build
     fails the tests fail."""
-    if not os.path.exists(os.path.join(ROOT, PKG, "libzkb200.so")):
+    so = os.path.join(ROOT, PKG, "libzkb200.so")
+    if not os.path.exists(so) or _stale(so):
         import __graft_entry__
 
         __graft_entry__.build()

@@ -1,6 +1,7 @@
 """Parity tests proper: the CUDA path, called through the C ABI (via the Python
 mirror of the reference's crate API), against the CPU oracle on identical
 seeded inputs.  Integer/byte work: the bar is BIT-EXACT equality."""
+import os
 import random
 
 import numpy as np
@@ -526,12 +527,10 @@ def test_circuit_shape_errors(zkb, ctxs):
 
 
 # --------------------------------------------------------------- full-size, size-independent properties
-def test_fullsize_composed_sumcheck_properties(zkb, ctxs, oracle):
-    """BASELINE config 2 (n = 24, one ProductPoly of 2 factors, full mode): too big for the oracle to replay in
-    seconds, so check (i) the host verifier accepts the transcript, (ii) the final claim equals the product of
-    the bound values, (iii) the bound values equal MLE evaluations at the challenge point (independent fold
-    kernel), and (iv) round 0 agrees with an oracle computation on a strided sample-free identity: s(0)+s(1)
-    equals the sum of products computed by the elementwise/sum kernels."""
+def test_fullsize_composed_sumcheck_matches_oracle(zkb, ctxs, oracle):
+    """BASELINE configs[1] at its full size (n = 24, one ProductPoly of 2 factors, full mode): the proof -- every
+    trimmed coefficient vector, every challenge, the bound values -- equals the CPU oracle's proof of the same
+    synthetic tables bit for bit (sum_check_protocol.rs:86-115), plus the independent-kernel properties."""
     fid, p = 0, R.BN254_FR
     ctx = ctxs(fid, 1)
     n = 24
@@ -543,6 +542,10 @@ def test_fullsize_composed_sumcheck_properties(zkb, ctxs, oracle):
     sp = zkb.SumPoly(ctx, [zkb.ProductPoly.from_polys(ctx, [a, b])])
     S = zkb.sum_check_protocol
     pr = S.gkr_prove(0, sp, zkb.fiat_shamir.Transcript(fid))
+    oracle.set_threads(max(1, len(os.sched_getaffinity(0))))
+    ref = oracle.gkr_sumcheck_prove(oracle.Transcript(fid), 1, 1, 2, [oracle.synth_table(fid, 0xB2000002, t, n) for t in range(2)])
+    assert [q.coefficients for q in pr.proof_polynomials] == ref["coeffs"]
+    assert pr.random_challenges == ref["challenges"] and pr.final_values == ref["final_vals"]
     prod = a * b
     claim = sum(prod.sum_halves()) % p
     ev0 = pr.proof_polynomials[0]
@@ -552,8 +555,56 @@ def test_fullsize_composed_sumcheck_properties(zkb, ctxs, oracle):
     assert v.final_claimed_sum == pr.final_values[0] * pr.final_values[1] % p
     assert a.evaluate(pr.random_challenges) == pr.final_values[0]
     assert b.evaluate(pr.random_challenges) == pr.final_values[1]
-    assert prod.evaluate([0] * n) == (arr_to_ints(oracle.synth_table(fid, 0xB2000002, 0, n, count=1))[0]
-                                      * arr_to_ints(oracle.synth_table(fid, 0xB2000002, 1, n, count=1))[0]) % p
+    sp.free()
+    for t in (a, b, prod):
+        t.free()
+
+
+@pytest.mark.parametrize("P,D,n", [(2, 3, 20), (1, 3, 21), (2, 2, 20)])
+def test_large_composed_shapes_match_oracle(zkb, ctxs, oracle, P, D, n):
+    """The shapes of BASELINE configs[3] (2 products x 3 factors) and of the north-star target (1 x 3) at 2^20-2^21
+    entries per table -- large enough for every regime (one launch per round, persistent kernel, on-chip kernel) --
+    against the oracle, bit for bit."""
+    fid = 0
+    ctx = ctxs(fid, 1)
+    tabs = [zkb.MultilinearPoly.generate(ctx, 0xB2000010 + P, t, n) for t in range(P * D)]
+    sp = zkb.SumPoly(ctx, [zkb.ProductPoly.from_polys(ctx, tabs[q * D:(q + 1) * D]) for q in range(P)])
+    pr = zkb.sum_check_protocol.gkr_prove(0, sp, zkb.fiat_shamir.Transcript(fid))
+    oracle.set_threads(max(1, len(os.sched_getaffinity(0))))
+    ref = oracle.gkr_sumcheck_prove(oracle.Transcript(fid), 1, P, D, [oracle.synth_table(fid, 0xB2000010 + P, t, n) for t in range(P * D)])
+    assert [q.coefficients for q in pr.proof_polynomials] == ref["coeffs"]
+    assert pr.random_challenges == ref["challenges"] and pr.final_values == ref["final_vals"]
+    sp.free()
+    for t in tabs:
+        t.free()
+
+
+def test_multi_gpu_parity_two_ranks():
+    """tests/multi_gpu_check.py under torchrun with 2 ranks (real NCCL, one process per GPU): sharded == single-GPU ==
+    oracle for plain and composed sumchecks, both exchange paths.  Needs two visible GPUs."""
+    import subprocess
+    import sys
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run on a multi-GPU box: gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ZKB_REPEAT="5")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")], cwd=root, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_GPU_PARITY OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_stress_short(zkb):
+    """tools/stress.py for a few seconds: thousands of small proofs through every regime of the round driver (the
+    persistent kernels publish round messages without a system fence and rely on checksums), each compared with the oracle."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "stress.py"), "5"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_fullsize_evaluate_linearity(zkb, ctxs):

@@ -1641,7 +1641,10 @@ const char* zkb_strerror(int32_t s) {
     }
     return "unknown status";
 }
-const char* zkb_version(void) { return "zkb200 0.1 (sm_100a)"; }
+#ifndef ZKB_SRC_HASH
+#define ZKB_SRC_HASH "unknown"
+#endif
+const char* zkb_version(void) { return "zkb200 0.2 (sm_100a) src:" ZKB_SRC_HASH; }
 
 int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx** out) {
     if (!out) return ZKB_ERR_BAD_ARG;

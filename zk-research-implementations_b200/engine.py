@@ -141,6 +141,25 @@ def lib() -> C.CDLL:
 EXPORTS = None  # filled by tests from include/zkb200.h
 
 
+def tree_src_hash() -> str:
+    """Hash of the library sources as they are in the tree (csrc/src_hash.py; the Makefile bakes the same
+    hash into the library at build time)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_zkb_src_hash", os.path.join(_HERE, "csrc", "src_hash.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.src_hash()
+
+
+def build_info() -> dict:
+    """zkb_version() of the loaded library against the tree: `stale` means the .so was built from other sources."""
+    v = lib().zkb_version().decode()
+    lib_hash = v.rsplit("src:", 1)[1] if "src:" in v else "unknown"
+    tree = tree_src_hash()
+    return {"version": v, "lib_src_hash": lib_hash, "tree_src_hash": tree, "stale": lib_hash != tree}
+
+
 # ------------------------------------------------------------- limb helpers
 def ints_to_limbs(vals: Iterable[int]) -> np.ndarray:
     vals = [int(v) for v in vals]
