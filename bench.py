@@ -57,9 +57,12 @@ def macs_per_quad(P: int, D: int) -> int:
 
 
 def macs_per_pair_round0(P: int, D: int) -> int:
-    """k_sc_eval: D+1 points of a product of D factors per pair position."""
+    """k_sc_eval: D+1 points of a product of D factors per pair position.  For D = 3 the product of the first two
+    factors is a quadratic in t, interpolated from three full products (kernels.cuh RoundAcc::add_product)."""
     if D == 1:
         return 0
+    if D == 3:
+        return P * (3 * MACS_FULL + 4 * MACS_LAZY)
     return P * (D + 1) * ((D - 2) * MACS_FULL + MACS_LAZY)
 
 

@@ -60,6 +60,20 @@ pub mod gkr_circuit {
         pub fn get_layer_poly(&self) -> Vec<F> {
             self.gates.iter().map(|g| g.output).collect()
         }
+        /// gkr_circuit.rs:39-52: the dense 0/1 indicator over a||b||c (2^(3g+2) entries; small layers only), made on
+        /// the device by `zkb_layer_add_mul_i`.
+        pub fn get_add_mul_i(&self, op: Operation) -> crate::multilinear_polynomial::MultilinearPoly<F> {
+            let c = ctx(F::FIELD_ID, sys::ZKB_MODE_COMPAT);
+            let ops: Vec<u8> = self.gates.iter().map(|g| g.op.code()).collect();
+            let mut h: sys::zkb_mle = 0;
+            check(c.0, unsafe { sys::zkb_layer_add_mul_i(c.0, ops.as_ptr(), ops.len() as u32, op.code() as i32, &mut h) });
+            let mut nv = 0u32;
+            check(c.0, unsafe { sys::zkb_mle_num_vars(c.0, h, &mut nv) });
+            let mut out = zeroed::<F>(1usize << nv);
+            check(c.0, unsafe { sys::zkb_mle_download(c.0, h, limbs_mut(&mut out)) });
+            unsafe { sys::zkb_mle_free(c.0, h) };
+            crate::multilinear_polynomial::MultilinearPoly::new(out)
+        }
     }
 
     #[derive(Debug, Clone)]

@@ -7,9 +7,11 @@
 //! `F` must be one of the three 4-limb Montgomery fields the library instantiates.  The element <-> limb
 //! cast relies on ark-ff 0.5's layout `Fp<MontBackend<C, 4>, 4>(BigInt<4>([u64; 4]), PhantomData)`.
 pub mod field;
+pub mod fiat_shamir;
 pub mod gkr;
 pub mod multilinear_polynomial;
 pub mod sum_check_protocol;
+pub mod univariate_polynomial;
 
 use std::cell::RefCell;
 use zkb200_sys as sys;

@@ -115,7 +115,14 @@ int32_t zkb_ctx_set_device_transcript(zkb_ctx* ctx, int32_t enable);
 int32_t zkb_ctx_device_transcript_stats(const zkb_ctx* ctx, uint64_t* launches, uint64_t* rounds_checked);
 
 /* --------------------------------------------- MultilinearPoly (device table) */
-/* MultilinearPoly::new (multilinear_polynomial_evaluation.rs:26-37): `len` must be a power of two. */
+/* MultilinearPoly::new (multilinear_polynomial_evaluation.rs:26-37): `len` must be a power of two.
+ * Source-buffer lifetime: the host-to-device copy is queued, not awaited.  From PAGEABLE memory (a Rust Vec) the
+ * driver stages the data before the call returns, so the buffer may be reused at once; from PINNED memory the
+ * buffer must stay unchanged until the next call that returns a result from this table (any prove / evaluate /
+ * download) or zkb_ctx_sync.  The same holds for zkb_mle_upload_shard and the `inputs` of zkb_circuit_evaluate /
+ * zkb_gkr_prove*.
+ * Table lifetime: a SumPoly holds a reference to the tables it was created from (the reference's SumPoly owns clones):
+ * zkb_mle_free on such a table only marks it, the memory is released when the last SumPoly using it is freed. */
 int32_t zkb_mle_upload(zkb_ctx* ctx, const uint64_t* aos_mont, uint64_t len, zkb_mle* out);
 /* Rank-local shard of a host table that every rank holds in full (strided gather on upload). */
 int32_t zkb_mle_upload_shard(zkb_ctx* ctx, const uint64_t* aos_mont_full, uint64_t len_full, zkb_mle* out);

@@ -277,6 +277,24 @@ struct RoundAcc {
     }
     // one product of D factors at this pair position
     __device__ __forceinline__ void add_product(const Fe* lo, const Fe* hi) {
+        if (!SKIP1 && D == 3 && NPTS == 4) {
+            // Round 0 of a 3-factor product needs all four points.  q(t) = (lo0 + t d0)(lo1 + t d1) is a quadratic in t:
+            // three full products (t = 0, 1, infinity) give it at every point by second differences, instead of four.
+            const Fe q0 = Fd::mul(lo[0], lo[1]), q1 = Fd::mul(hi[0], hi[1]);
+            const Fe d2 = Fd::sub(hi[2], lo[2]);
+            Fe e = Fd::mul(Fd::sub(hi[0], lo[0]), Fd::sub(hi[1], lo[1]));  // q(inf)
+            mac(0, q0, lo[2]);
+            mac(1, q1, hi[2]);
+            e = Fd::dbl(e);                       // the constant second difference 2 q(inf)
+            Fe dd = Fd::add(Fd::sub(q1, q0), e);  // q(2) - q(1)
+            Fe q = Fd::add(q1, dd), c = Fd::add(hi[2], d2);
+            mac(2, q, c);
+            dd = Fd::add(dd, e);
+            q = Fd::add(q, dd);
+            c = Fd::add(c, d2);
+            mac(3, q, c);
+            return;
+        }
         {
             Fe m = lo[0];
 #pragma unroll
@@ -309,6 +327,21 @@ struct RoundAcc {
                 for (int f = 1; f < D - 1; ++f) m = Fd::mul(m, cur[f]);
                 mac(S::of(t), m, cur[D - 1]);
             }
+        }
+    }
+    // The same product taken one factor at a time (SKIP1 rounds): m[k] carries the partial product at point
+    // k of {0, 2, 3, ..} over the factors seen so far, so only S::N values stay live between two folds instead of
+    // every folded factor (what keeps the >= 3-factor kernels inside 128 registers).
+    __device__ __forceinline__ void factor(int f, const Fe& lo, const Fe& hi, Fe* m) {
+        Fe cur = lo;
+        const Fe d = Fd::sub(hi, lo);
+#pragma unroll
+        for (int k = 0; k < S::N; ++k) {
+            if (k == 1) cur = Fd::add(hi, d);                 // t = 2 (t = 1 is skipped)
+            else if (k > 1) cur = Fd::add(cur, d);
+            if (f == 0) m[k] = cur;
+            else if (f < D - 1) m[k] = Fd::mul(m[k], cur);
+            else mac(k, m[k], cur);
         }
     }
     __device__ __forceinline__ void finish(Fe* out) {
@@ -410,6 +443,32 @@ __device__ __forceinline__ Fe fe_from_smem(const uint4* slot_lo, const uint4* sl
     r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
+// ---- TMA 1-D bulk copies (cp.async.bulk -> UBLKCP in SASS) completing on an mbarrier.  One lane issues a copy for
+// the whole warp: no thread holds an address or a register for data in flight, which is what lets the >= 3-factor
+// round kernel (at the 128-register limit) prefetch at all.
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return static_cast<unsigned int>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "ZKB_MBAR_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra ZKB_MBAR_WAIT_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned int bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int EVAL_BUFS = 4;   // k_sc_eval: 4 buffers x 4 vectors (lo, hi of one table)
 constexpr int FOLD_BUFS = 2;   // k_sc_fold_eval: 2 buffers x 8 vectors (the quad of one table)
 constexpr int STAGE_BYTES = 2 * 8 * BLOCK * 16;  // 64 KiB per CTA of staging for both kernels
@@ -503,14 +562,205 @@ template <int KIND, int D>
 struct Staged {
     static constexpr bool value = KIND == KIND_XYZ || D <= 2;
 };
+// BULK: products of >= 3 factors stage through per-WARP buffers filled by TMA bulk copies.  A unit is one fold of one
+// table for the warp's 32 positions: 4 segments (2 elements x 2 limb planes) of 512 bytes; BULK_BUFS units in flight.
+template <int KIND, int D>
+struct Bulk {
+#ifdef ZKB_BULK_OFF  // (kbench only: the unstaged path of round 1, for comparison)
+    static constexpr bool value = false;
+#else
+    static constexpr bool value = KIND == KIND_PROD && D >= 3;
+#endif
+};
+template <int NPTS>
+struct BulkBufs {
+    static constexpr int value = NPTS <= 4 ? 3 : 2;  // bounded by 2 CTAs/SM next to the parked accumulators
+};
+constexpr int BULK_UNIT_VECS = 4 * 32;  // uint4 per unit and warp (2 KiB)
+#ifndef ZKB_BULK_TMA
+#define ZKB_BULK_TMA 0
+#endif
+constexpr bool BULK_USE_TMA = ZKB_BULK_TMA != 0;  // 1: per-warp TMA bulk copies; 0: per-thread cp.async slots (measured faster)
+template <int NPTS>
+struct BulkWarpBytes {  // per warp: the unit buffers (+ with TMA one mbarrier per buffer, padded to 32 bytes)
+    static constexpr int value = BulkBufs<NPTS>::value * BULK_UNIT_VECS * 16 + (BULK_USE_TMA ? 32 : 0);
+};
 template <int KIND, int D, int NPTS>
 struct FoldSmem {
-    static constexpr int bytes = (Staged<KIND, D>::value ? STAGE_BYTES : 0) + (NPTS - 1) * ACC_VECS * BLOCK * 16;
+    static constexpr int stage_bytes =
+        Staged<KIND, D>::value ? STAGE_BYTES : (Bulk<KIND, D>::value ? (BLOCK / 32) * BulkWarpBytes<NPTS>::value : 0);
+    static constexpr int bytes = stage_bytes + (NPTS - 1) * ACC_VECS * BLOCK * 16;
 };
 template <int KIND, int D, int NPTS>
 struct TailSmem {  // the persistent kernel may start with the evaluation pass, which stages through 64 KiB
     static constexpr int bytes = FoldSmem<KIND, D, NPTS>::bytes > STAGE_BYTES ? FoldSmem<KIND, D, NPTS>::bytes : STAGE_BYTES;
 };
+// The >= 3-factor round pass: same arithmetic as round_pass, table reads through per-warp TMA bulk copies.
+// Warp w owns positions [jw, jw + 32) of each grid-stride iteration; unit sequence per iteration: for every table, the
+// "lo" fold (entries j, j + n_out) then the "hi" fold (entries j + half, j + half + n_out).  Production runs exactly
+// BULK_BUFS units ahead of consumption: right after the warp has moved unit u from shared memory into registers,
+// lane 0 refills the same buffer with unit u + BULK_BUFS, whose coordinates follow from the consumer's loop counters
+// (no separate producer state in registers).  The warp's buffers and mbarriers are addressed from one 32-bit base.
+__device__ __forceinline__ Fe lds_fe(unsigned int a_lo, unsigned int a_hi) {
+    Fe r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]) : "r"(a_lo));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]) : "r"(a_hi));
+    return r;
+}
+template <class F, int D, int NPTS>
+__device__ __forceinline__ void round_pass_bulk(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
+                                                uint64_t n_out, const FixedMul& rt, uint4* stage, uint4* accs, Fe* out) {
+    typedef Field<F> Fd;
+    constexpr int NB = BulkBufs<NPTS>::value;
+    constexpr unsigned int UNIT = BULK_UNIT_VECS * 16;  // bytes per unit
+    const unsigned int lane = threadIdx.x & 31;
+    const uint64_t half = n_out >> 1;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t jw0 = (uint64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31u);  // the warp's first position
+    const int units = 2 * n_products * D;                                      // units per iteration
+    const unsigned int wb = smem_u32(stage) + (threadIdx.x >> 5) * BulkWarpBytes<NPTS>::value;
+    const unsigned int bars = wb + NB * UNIT;
+    auto issue = [&](uint64_t pj, int pu, unsigned int buf) {  // one lane: unit pu of the iteration at pj -> buffer buf
+        const uint64_t left = half - pj;
+        const unsigned int bytes = (unsigned int)(left < 32 ? left : 32) * 16u;
+        const TabRef& t = in[pu >> 1];
+        const uint4* g0 = t.base + pj + ((pu & 1) ? half : 0);
+        const uint4* g1 = g0 + t.stride;
+        const unsigned int dst = wb + buf * UNIT, bar = bars + buf * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g0), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 512u), "l"(g1), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 1024u), "l"(g0 + n_out), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 1536u), "l"(g1 + n_out), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + b * 8) : "memory");
+        fence_barrier_init();
+        fence_proxy_async();
+        if (jw0 < half) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) issue(jw0, b, b);  // units 0 .. NB-1 (units >= 6 > NB)
+        }
+    }
+    __syncwarp();
+    unsigned int cb = 0, phases = 0;  // buffer to consume next; bit b = parity to wait for on buffer b
+    RoundAcc<F, D, NPTS, true, true> acc;
+    acc.init(accs);
+    for (uint64_t jw = jw0; jw < half; jw += step) {
+        const uint64_t j = jw + lane;
+        const bool active = j < half;  // only the last warp of a tiny table is ragged
+        for (int p = 0; p < n_products; ++p) {
+            Fe m[NPTS - 1];
+#pragma unroll
+            for (int f = 0; f < D; ++f) {
+                Fe lo, hi;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    {
+                        const unsigned int bar = bars + cb * 8, par = (phases >> cb) & 1u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "ZKB_W_%=:\n\t"
+                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                            "@!p bra ZKB_W_%=;\n\t}" ::"r"(bar), "r"(par) : "memory");
+                    }
+                    const unsigned int src = wb + cb * UNIT + lane * 16u;
+                    const Fe x0 = lds_fe(src, src + 512u), x1 = lds_fe(src + 1024u, src + 1536u);
+                    __syncwarp();  // every lane has its operands in registers: the buffer may be refilled
+                    phases ^= 1u << cb;
+                    {
+                        int pu = 2 * (p * D + f) + h + NB;
+                        uint64_t pj = jw;
+                        if (pu >= units) {
+                            pu -= units;
+                            pj += step;
+                        }
+                        if (lane == 0 && pj < half) issue(pj, pu, cb);
+                    }
+                    cb = cb + 1 == NB ? 0u : cb + 1;
+                    Fe& dst = h ? hi : lo;
+                    dst = Fd::fold_fixed(x0, x1, rt);
+                    if (active) st_fe(outp[p * D + f], h ? j + half : j, dst);
+                }
+                if (active) acc.factor(f, lo, hi, m);
+            }
+        }
+    }
+    acc.finish(out);
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + b * 8) : "memory");
+    }
+    __syncwarp();
+}
+
+// Same unit pipeline with per-THREAD cp.async (LDGSTS) slots instead of per-warp bulk copies: slot layout
+// stage[buf][vec][thread]; a slot is private to its thread, so cp.async.wait_group is the only synchronisation.
+// Measured on B200 (2^28, 1 x 3): the bulk version 30.4 ms per proof in this kernel, this one see DESIGN.md section 6.
+template <class F, int D, int NPTS>
+__device__ __forceinline__ void round_pass_async3(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
+                                                  uint64_t n_out, const FixedMul& rt, uint4* stage, uint4* accs, Fe* out) {
+    typedef Field<F> Fd;
+    constexpr int NB = BulkBufs<NPTS>::value;
+    constexpr unsigned int UNIT = 4 * BLOCK * 16;  // bytes per unit (CTA-wide): 4 vectors per thread
+    const uint64_t half = n_out >> 1;
+    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t j0 = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const int units = 2 * n_products * D;
+    const unsigned int sb = smem_u32(stage) + threadIdx.x * 16u;
+    auto issue = [&](uint64_t pj, int pu, unsigned int buf) {
+        if (pj < half) {
+            const TabRef& t = in[pu >> 1];
+            const uint4* g0 = t.base + pj + ((pu & 1) ? half : 0);
+            const uint4* g1 = g0 + t.stride;
+            const unsigned int dst = sb + buf * UNIT;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g0) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + BLOCK * 16u), "l"(g1) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2u * BLOCK * 16u), "l"(g0 + n_out) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 3u * BLOCK * 16u), "l"(g1 + n_out) : "memory");
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int b = 0; b < NB; ++b) issue(j0, b, b);
+    unsigned int cb = 0;
+    RoundAcc<F, D, NPTS, true, true> acc;
+    acc.init(accs);
+    for (uint64_t j = j0; j < half; j += step) {
+        for (int p = 0; p < n_products; ++p) {
+            Fe m[NPTS - 1];
+#pragma unroll
+            for (int f = 0; f < D; ++f) {
+                Fe lo, hi;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    cp_async_wait<NB - 1>();
+                    const unsigned int src = sb + cb * UNIT;
+                    const Fe x0 = lds_fe(src, src + BLOCK * 16u), x1 = lds_fe(src + 2u * BLOCK * 16u, src + 3u * BLOCK * 16u);
+                    {
+                        int pu = 2 * (p * D + f) + h + NB;
+                        uint64_t pj = j;
+                        if (pu >= units) {
+                            pu -= units;
+                            pj += step;
+                        }
+                        issue(pj, pu, cb);
+                    }
+                    cb = cb + 1 == NB ? 0u : cb + 1;
+                    Fe& dst = h ? hi : lo;
+                    dst = Fd::fold_fixed(x0, x1, rt);
+                    st_fe(outp[p * D + f], h ? j + half : j, dst);
+                }
+                acc.factor(f, lo, hi, m);
+            }
+        }
+    }
+    acc.finish(out);
+    cp_async_wait<0>();
+}
+
 template <class F, int KIND, int D, int NPTS>
 __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
                                            uint64_t n_out, const FixedMul& rt, uint4* stage, Fe* out) {
@@ -521,7 +771,12 @@ __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const 
     const uint64_t j0 = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     const int T = KIND == KIND_XYZ ? 3 : n_products * D;
     uint4* my = stage + threadIdx.x;
-    uint4* accs = stage + (STAGED ? FOLD_BUFS * 8 * BLOCK : 0) + threadIdx.x;  // accumulators after the staging buffers
+    uint4* accs = stage + FoldSmem<KIND, D, NPTS>::stage_bytes / 16 + threadIdx.x;  // accumulators after the staging buffers
+    if constexpr (Bulk<KIND, D>::value) {
+        if constexpr (BULK_USE_TMA) round_pass_bulk<F, D, NPTS>(in, outp, n_products, n_out, rt, stage, accs, out);
+        else round_pass_async3<F, D, NPTS>(in, outp, n_products, n_out, rt, stage, accs, out);
+        return;
+    }
     uint64_t pj = j0;
     int pt = 0, pbuf = 0;
     auto issue = [&]() {

@@ -28,6 +28,36 @@
 
 using namespace zkb;
 
+// ------------------------------------------------------------------ host portability (x86-64 and aarch64 hosts)
+namespace {
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
+// A monotonic tick counter for the trace (ZKB200_TRACE); ticks_per_us() calibrates it against CLOCK_MONOTONIC.
+inline unsigned long long host_ticks() {
+#if defined(__x86_64__) || defined(__i386__)
+    return __builtin_ia32_rdtsc();
+#elif defined(__aarch64__)
+    unsigned long long v;
+    asm volatile("mrs %0, cntvct_el0" : "=r"(v));
+    return v;
+#else
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (unsigned long long)t.tv_sec * 1000000000ull + (unsigned long long)t.tv_nsec;
+#endif
+}
+// Flags and sequence numbers written by the device into mapped host memory (or by the host for the device) are read
+// with acquire / written with release semantics: on a weakly ordered host (Grace) a plain load of the payload could
+// otherwise be satisfied before the load of the flag that guards it.
+inline unsigned int load_acquire(const volatile unsigned int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void store_release(volatile unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+}  // namespace
+
 // ------------------------------------------------------------------ NCCL (lazy)
 // Resolved with dlopen at zkb_ctx_comm_init so that (a) the library loads on a
 // machine without NCCL/GPU and (b) a process that already carries NCCL (torch)
@@ -87,6 +117,8 @@ struct Table {
     uint4* base = nullptr;
     uint64_t n = 0;       // live entries
     uint64_t stride = 0;  // distance between the two limb planes (uint4 units) = allocated entries
+    int refs = 0;         // SumPolys that read this table (zkb_sumpoly_create .. zkb_sumpoly_free)
+    bool dead = false;    // zkb_mle_free was called while refs > 0: the memory goes when the last SumPoly does
     TabRef ref() const { return TabRef{base, stride}; }
 };
 
@@ -97,6 +129,7 @@ struct SumPolyState {
     std::vector<int> sel;         // tables the round kernel reads (kernel order)
     std::vector<int> rest;        // tables that are only folded (compat mode)
     std::vector<Table> src;       // caller's tables, never written
+    std::vector<uint64_t> src_handles;  // their handles (reference counts, see Table::refs)
     std::vector<Table> work;      // private folded copies
     std::vector<Table> gath;      // after the multi-GPU gather
     uint64_t n0 = 0;              // local entries per table before any bind
@@ -217,9 +250,7 @@ struct ShmComm {
             uint64_t spins = 0;
             while (__atomic_load_n(&s.seq, __ATOMIC_ACQUIRE) < k) {
                 if (++spins > (1ull << 33)) return false;  // a peer died
-#if defined(__x86_64__)
-                __builtin_ia32_pause();
-#endif
+                cpu_relax();
             }
             for (int i = 0; i < n; ++i) {
                 Fe v;
@@ -419,7 +450,7 @@ int32_t ensure_partials(zkb_ctx* c, size_t n_fe) {
 
 Table* find_mle(zkb_ctx* c, zkb_mle h) {
     auto it = c->mles.find(h);
-    return it == c->mles.end() ? nullptr : &it->second;
+    return it == c->mles.end() || it->second.dead ? nullptr : &it->second;
 }
 zkb_mle put_mle(zkb_ctx* c, const Table& t) {
     zkb_mle h = c->next_handle++;
@@ -432,11 +463,11 @@ zkb_mle put_mle(zkb_ctx* c, const Table& t) {
 // a hang).
 int32_t wait_mailbox(zkb_ctx* c, unsigned int seq) {
     uint32_t spins = 0;
-    while (*c->h_flag != seq) {
+    while (load_acquire(c->h_flag) != seq) {
         if ((++spins & 0x3fff) == 0) {
             cudaError_t e = cudaStreamQuery(c->stream);
             if (e == cudaSuccess) {
-                if (*c->h_flag == seq) break;
+                if (load_acquire(c->h_flag) == seq) break;
                 ZK_FAIL(c, ZKB_ERR_CUDA, "mailbox: stream drained without a result");
             }
             if (e != cudaErrorNotReady) {
@@ -444,12 +475,9 @@ int32_t wait_mailbox(zkb_ctx* c, unsigned int seq) {
                 return ZKB_ERR_CUDA;
             }
         }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
+        cpu_relax();
     }
-    asm volatile("" ::: "memory");  // results are read only after the flag
-    return ZKB_OK;
+    return ZKB_OK;  // the acquire load above orders the reads of the results after the flag
 }
 
 // Fill the FinishArgs of a reducing launch of `grid` CTAs returning `npts` sums.
@@ -755,10 +783,10 @@ struct RoundDriver {
         if (v == 0) {
             timespec a, b;
             clock_gettime(CLOCK_MONOTONIC, &a);
-            unsigned long long t0 = __builtin_ia32_rdtsc();
+            unsigned long long t0 = host_ticks();
             do clock_gettime(CLOCK_MONOTONIC, &b);
             while ((b.tv_sec - a.tv_sec) * 1e9 + (b.tv_nsec - a.tv_nsec) < 2e6);
-            v = (double)(__builtin_ia32_rdtsc() - t0) / (((b.tv_sec - a.tv_sec) * 1e9 + (b.tv_nsec - a.tv_nsec)) * 1e-3);
+            v = (double)(host_ticks() - t0) / (((b.tv_sec - a.tv_sec) * 1e9 + (b.tv_nsec - a.tv_nsec)) * 1e-3);
         }
         return v;
     }
@@ -799,7 +827,7 @@ struct RoundDriver {
         uint32_t spins = 0;
         // "not yet reached": with the device transcript the kernel does not wait for the host and may already be
         // several messages ahead, so the sequence number is compared as a counter, not for equality
-        auto behind = [&]() { return (int32_t)(c->mb->dev_seq - want) < 0; };
+        auto behind = [&]() { return (int32_t)(load_acquire(&c->mb->dev_seq) - want) < 0; };
         while (behind()) {
             if ((++spins & 0x3fff) == 0) {
                 cudaError_t e = cudaStreamQuery(c->stream);
@@ -813,12 +841,9 @@ struct RoundDriver {
                     return ZKB_ERR_CUDA;
                 }
             }
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
+            cpu_relax();
         }
-        asm volatile("" ::: "memory");
-        return ZKB_OK;
+        return ZKB_OK;  // (acquire load in behind(): mb->finals / evals are read after dev_seq)
     }
     // The persistent kernels publish a round's sums without a system fence (kernels.cuh FinishArgs::chk): the sequence
     // number may become visible before the sums, so they are taken only once their checksum matches.
@@ -833,9 +858,7 @@ struct RoundDriver {
                 abort();
                 ZK_FAIL(c, ZKB_ERR_CUDA, "round message from the device never became consistent");
             }
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
+            cpu_relax();
         }
     }
     void begin_mailbox() {
@@ -853,8 +876,7 @@ struct RoundDriver {
             x ^= r.l[k];
         }
         c->mb->chk = x ^ (want * 0x9E3779B9u);
-        asm volatile("" ::: "memory");
-        c->mb->host_seq = want;  // x86 keeps store order: the payload is visible before the sequence number
+        store_release(&c->mb->host_seq, want);  // the payload is visible before the sequence number (and the device checks chk)
     }
     int32_t launch_small(bool first_eval, const Fe& r, const Fe* claim = nullptr) {
         if (sp->state == 0) ZK_TRY(sp_ensure_work(c, sp));
@@ -988,7 +1010,7 @@ struct RoundDriver {
         const bool tracing = c->trace && was_live && !small;
         unsigned long long t_send = 0;
         if (tracing) {
-            t_send = __builtin_ia32_rdtsc();
+            t_send = host_ticks();
             if (t_recv) c->tr_host += (double)(t_send - t_recv) / tsc_per_us();
         }
         if (was_live && small && dt) {
@@ -1012,7 +1034,7 @@ struct RoundDriver {
             else ZK_TRY(launch_tail(r));
         }
         ZK_TRY(wait_dev(base + (++pubs)));
-        t_recv = c->trace ? __builtin_ia32_rdtsc() : 0;
+        t_recv = c->trace ? host_ticks() : 0;
         if (tracing) {
             const unsigned long long* ts = c->mb->ts;
             // CTA 0's stamps are not ordered with the publishing CTA's flag: they may belong to the previous round,
@@ -1599,6 +1621,31 @@ int32_t gkr_prove_wired_impl(zkb_ctx* c, CircuitState* cs, const uint64_t* input
     return ZKB_OK;
 }
 
+// Untrusted proof elements must be canonical Montgomery residues (limbs < p): the host arithmetic and H.eq assume it,
+// and a proof carrying c + p in place of c would otherwise hash as c and could be accepted (malleability).  ark-ff
+// cannot produce such a value; a C caller can.
+bool all_canonical(const HostField& H, const uint64_t* v, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t* x = v + 4 * i;
+        bool lt = false;
+        for (int k = 3; k >= 0; --k) {
+            if (x[k] != H.p[k]) {
+                lt = x[k] < H.p[k];
+                break;
+            }
+        }
+        if (!lt) return false;
+    }
+    return true;
+}
+bool coeffs_canonical(const HostField& H, const uint64_t* coeffs, const int32_t* lens, uint32_t n_rounds, uint32_t slots) {
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        if (lens[k] < 0 || (uint32_t)lens[k] > slots) return false;
+        if (!all_canonical(H, coeffs + (size_t)k * slots * 4, (size_t)lens[k])) return false;
+    }
+    return true;
+}
+
 // gkr_verify (sum_check_protocol.rs:117-150) on the host.
 bool sc_verify_rounds(const HostField& H, TranscriptImpl* tr, uint32_t n_rounds, uint32_t slots, const uint64_t* coeffs,
                       const int32_t* lens, Fe claim, Fe* final_claim, Fe* chals) {
@@ -1921,6 +1968,10 @@ int32_t zkb_mle_clone(zkb_ctx* c, zkb_mle m, zkb_mle* out) {
 int32_t zkb_mle_free(zkb_ctx* c, zkb_mle m) {
     Table* t = c ? find_mle(c, m) : nullptr;
     if (!t) return ZKB_ERR_BAD_ARG;
+    if (t->refs > 0) {  // a SumPoly still reads it (the reference's SumPoly owns clones): free when the last one goes
+        t->dead = true;
+        return ZKB_OK;
+    }
     free_table(c, t);
     c->mles.erase(m);
     return ZKB_OK;
@@ -2030,6 +2081,10 @@ int32_t zkb_sumpoly_create(zkb_ctx* c, const zkb_mle* tables, uint32_t n_product
         if (i && t->n != sp->src[0].n) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "all evaluations must have same length");
         sp->src.push_back(*t);
     }
+    for (uint32_t i = 0; i < n_products * degree; ++i) {
+        sp->src_handles.push_back(tables[i]);
+        ++c->mles[tables[i]].refs;
+    }
     sp->n0 = sp->src[0].n;
     sp_reset(c, sp.get());
     zkb_sp h = c->next_handle++;
@@ -2042,6 +2097,14 @@ int32_t zkb_sumpoly_free(zkb_ctx* c, zkb_sp h) {
     auto it = c->sps.find(h);
     if (it == c->sps.end()) return ZKB_ERR_BAD_ARG;
     sp_release(c, it->second.get());
+    for (uint64_t mh : it->second->src_handles) {  // drop the references; tables freed meanwhile go now
+        auto mt = c->mles.find(mh);
+        if (mt == c->mles.end()) continue;
+        if (--mt->second.refs <= 0 && mt->second.dead) {
+            free_table(c, &mt->second);
+            c->mles.erase(mt);
+        }
+    }
     c->sps.erase(it);
     return ZKB_OK;
 }
@@ -2246,6 +2309,7 @@ int32_t zkb_sumcheck_verify(zkb_ctx* c, zkb_mle poly, uint32_t flags, const uint
     Table* t = c ? find_mle(c, poly) : nullptr;
     if (!t || !claimed_sum || !accepted || (!msgs && n_msgs)) return ZKB_ERR_BAD_ARG;
     *accepted = 0;
+    if (!all_canonical(c->H, claimed_sum, 1) || !all_canonical(c->H, msgs, 2 * (size_t)n_msgs)) return ZKB_OK;  // rejected
     TranscriptImpl tr;
     tr.H = c->H;
     if (flags & 1u) ZK_TRY(absorb_table(c, *t, &tr));
@@ -2289,7 +2353,8 @@ int32_t zkb_gkr_sumcheck_verify(zkb_transcript* t, uint32_t n_rounds, uint32_t s
     const HostField& H = t->impl.H;
     std::vector<Fe> ch(n_rounds ? n_rounds : 1);
     Fe fin;
-    if (!sc_verify_rounds(H, &t->impl, n_rounds, slots, coeffs, lens, fe_from_u64x4(claimed_sum), &fin, ch.data())) {
+    if (!all_canonical(H, claimed_sum, 1) || !coeffs_canonical(H, coeffs, lens, n_rounds, slots) ||
+        !sc_verify_rounds(H, &t->impl, n_rounds, slots, coeffs, lens, fe_from_u64x4(claimed_sum), &fin, ch.data())) {
         *accepted = 0;  // :129-133
         std::memset(final_claim, 0, 32);
         std::memset(challenges, 0, 32);
@@ -2418,6 +2483,13 @@ int32_t zkb_gkr_verify(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uint64_t 
     const int L = cs->L;
     if (n_inputs != 2ull * cs->gates[0]) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "circuit: inputs must be 2 x gates of the first layer");
     const HostField& H = c->H;
+    {   // untrusted proof elements must be canonical residues (see all_canonical)
+        uint32_t tot = 0;
+        for (int l = 0; l < L; ++l) tot += layer_rounds(cs->gates[l]);
+        if (!all_canonical(H, w0_in, 2) || !all_canonical(H, final_openings, 2) || !coeffs_canonical(H, coeffs, lens, tot, 3) ||
+            (L > 1 && (!claimed || !all_canonical(H, claimed, 2 * (size_t)(L - 1)))))
+            return ZKB_OK;  // *accepted == 0
+    }
     TranscriptImpl tr;
     tr.H = H;
     Fe w0[2] = {fe_from_u64x4(w0_in), fe_from_u64x4(w0_in + 4)};
@@ -2626,6 +2698,13 @@ int32_t zkb_gkr_verify_wired(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uin
     if (n_w0 != n0) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "gkr: w0 must hold max(outputs, 2) elements");
     if (L > 1 && !claimed) return ZKB_ERR_BAD_ARG;
     const HostField& H = c->H;
+    {   // untrusted proof elements must be canonical residues (see all_canonical)
+        uint32_t tot = 0;
+        for (int l = 0; l < L; ++l) tot += 2u * (uint32_t)ilog2_u64(cs->width[l]);
+        if (!all_canonical(H, w0_in, (size_t)n0) || !all_canonical(H, final_openings, 2) || !coeffs_canonical(H, coeffs, lens, tot, 3) ||
+            (L > 1 && !all_canonical(H, claimed, 2 * (size_t)(L - 1))))
+            return ZKB_OK;  // *accepted == 0
+    }
     TranscriptImpl tr;
     tr.H = H;
     const int k0 = ilog2_u64(n0);
