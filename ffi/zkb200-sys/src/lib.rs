@@ -14,6 +14,7 @@ pub struct zkb_transcript {
 pub type zkb_mle = u64;
 pub type zkb_sp = u64;
 pub type zkb_circ = u64;
+pub type zkb_kzg = u64;
 
 pub const ZKB_OK: i32 = 0;
 pub const ZKB_ERR_BAD_ARG: i32 = -1;
@@ -111,6 +112,12 @@ extern "C" {
     pub fn zkb_gkr_prove_wired(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *mut u64, n_w0: u64, coeffs: *mut u64, lens: *mut i32, challenges: *mut u64, claimed: *mut u64, final_openings: *mut u64, n_rounds: *mut u32) -> i32;
     pub fn zkb_gkr_verify_wired(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *const u64, n_w0: u64, coeffs: *const u64, lens: *const i32, claimed: *const u64, final_openings: *const u64, accepted: *mut i32) -> i32;
 
+    pub fn zkb_kzg_setup(ctx: *mut zkb_ctx, n_vars: u32, taus_mont: *const u64, out: *mut zkb_kzg) -> i32;
+    pub fn zkb_kzg_free(ctx: *mut zkb_ctx, k: zkb_kzg) -> i32;
+    pub fn zkb_kzg_basis(ctx: *mut zkb_ctx, k: zkb_kzg, level: u32, first: u64, count: u64, out: *mut u8) -> i32;
+    pub fn zkb_kzg_commit(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, out: *mut u8) -> i32;
+    pub fn zkb_kzg_open(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, opening_values: *const u64, n: u32, out: *mut u64) -> i32;
+    pub fn zkb_kzg_get_proof(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, opened_value: *const u64, opening_values: *const u64, n: u32, out: *mut u8) -> i32;
     pub fn zkb_bench_modmul(ctx: *mut zkb_ctx, variant: i32, iters: u32, modmuls_per_s: *mut f64) -> i32;
     pub fn zkb_bench_imad(ctx: *mut zkb_ctx, mode: i32, iters: u32, ops_per_s: *mut f64) -> i32;
 }

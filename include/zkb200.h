@@ -39,6 +39,7 @@ typedef struct zkb_transcript zkb_transcript;
 typedef uint64_t zkb_mle;  /* opaque handle of a device-resident MultilinearPoly */
 typedef uint64_t zkb_sp;   /* opaque handle of a device-resident SumPoly        */
 typedef uint64_t zkb_circ; /* opaque handle of a device-resident Circuit        */
+typedef uint64_t zkb_kzg;  /* opaque handle of a multilinear-KZG setup (G1 side)   */
 
 typedef enum {
     ZKB_OK = 0,
@@ -265,6 +266,29 @@ int32_t zkb_gkr_verify_wired(zkb_ctx* ctx, zkb_circ c, const uint64_t* inputs_mo
                              const uint64_t final_openings[8], int32_t* accepted);
 
 /* ------------------------------------------------------------ microbenchmarks */
+/* ------------------------------------------------ input-layer commitment: multilinear KZG over BLS12-381 G1
+ * Prover side of pcs/src/kzg_pcs/kzg.rs, as gkr/src/gkr_protocol.rs:92-118 runs it on the input MLE.  The ctx must be
+ * created with ZKB_FIELD_BLS12_381_FR (ZKB_ERR_UNSUPPORTED otherwise).  G1 points cross the ABI as 96 bytes: the affine
+ * coordinates x, y as 48-byte little-endian canonical integers; 96 zero bytes = the point at infinity (the reference
+ * compares projective points for equality, which is equality of these bytes).
+ *
+ * zkb_kzg_setup    KZG::new / run_trusted_setup / get_lagrange_basis (kzg.rs:17-49,183-212), G1 side: basis[i] =
+ *                  g1 * eq(taus, i).  `taus`: n_vars Montgomery Fr elements -- an INPUT here (the reference draws them
+ *                  from OS entropy inside gkr_protocol::prove, :95-101, which no implementation can reproduce).
+ * zkb_kzg_basis    canonical bytes of `count` basis points from `first` (level 0 = the Lagrange basis; level k = the
+ *                  basis folded over its k leading variables, see csrc/kzg_impl.cuh)
+ * zkb_kzg_commit   KZG::commit (:51-53) = evaluate_poly_with_l_basis_in_g1 (:131-144), as a bucket MSM
+ * zkb_kzg_open     KZG::open (:55-57) = poly.evaluate(opening_values)
+ * zkb_kzg_get_proof  KZG::get_proof (:59-95): `n` quotient commitments (n x 96 bytes), one per opening value
+ * The G2 powers and KZG::verify (:97-129, pairings) are verifier-side and not provided. */
+int32_t zkb_kzg_setup(zkb_ctx* ctx, uint32_t n_vars, const uint64_t* taus_mont, zkb_kzg* out);
+int32_t zkb_kzg_free(zkb_ctx* ctx, zkb_kzg k);
+int32_t zkb_kzg_basis(zkb_ctx* ctx, zkb_kzg k, uint32_t level, uint64_t first, uint64_t count, uint8_t* out);
+int32_t zkb_kzg_commit(zkb_ctx* ctx, zkb_kzg k, zkb_mle poly, uint8_t out[96]);
+int32_t zkb_kzg_open(zkb_ctx* ctx, zkb_kzg k, zkb_mle poly, const uint64_t* opening_values, uint32_t n, uint64_t out[4]);
+int32_t zkb_kzg_get_proof(zkb_ctx* ctx, zkb_kzg k, zkb_mle poly, const uint64_t opened_value[4], const uint64_t* opening_values, uint32_t n,
+                          uint8_t* out);
+
 /* Device-timed multiplier throughput (fills the IMAD-roofline denominator).
  * variant: 0/1 = IMAD.WIDE multiplier with 1/2 independent chains per thread, 2/3 = 32-bit lo/hi
  * multiplier.  Returns modmuls per second. */

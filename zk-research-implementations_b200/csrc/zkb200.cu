@@ -25,6 +25,7 @@
 
 #include "../../include/zkb200.h"
 #include "host_math.hpp"
+#include "kzg_impl.cuh"
 
 using namespace zkb;
 
@@ -263,6 +264,12 @@ struct ShmComm {
     }
 };
 
+// Multilinear KZG setup (G1 side): the Lagrange basis and its folds, affine, on the device.
+struct KzgState {
+    uint32_t n_vars = 0;
+    std::vector<G1Affine*> basis;  // level k: 2^(n_vars - k) points; level 0 = g1 * eq(taus, .)
+};
+
 struct zkb_transcript {
     TranscriptImpl impl;
 };
@@ -300,6 +307,8 @@ struct zkb_ctx {
     std::unordered_map<uint64_t, Table> mles;
     std::unordered_map<uint64_t, std::unique_ptr<SumPolyState>> sps;
     std::unordered_map<uint64_t, std::unique_ptr<CircuitState>> circs;
+    std::unordered_map<uint64_t, std::unique_ptr<KzgState>> kzgs;
+    G1Affine* g1_table = nullptr;  // 32 x 256 multiples of the generator (fixed-base windows), made on first use
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, log2world = 0;
@@ -1666,6 +1675,89 @@ bool sc_verify_rounds(const HostField& H, TranscriptImpl* tr, uint32_t n_rounds,
     return true;
 }
 
+
+// ------------------------------------------------------------------- KZG core (kzg_impl.cuh)
+void kzg_release(zkb_ctx* c, KzgState* k) {
+    for (auto* p : k->basis)
+        if (p) cudaFreeAsync(p, c->stream);
+    k->basis.clear();
+}
+MsmPlan msm_plan(uint64_t n) {
+    int lg = ilog2_u64(n);
+    int cbits = lg - 4;
+    if (cbits < 4) cbits = 4;
+    if (cbits > 16) cbits = 16;
+    MsmPlan pl;
+    pl.c = (uint32_t)cbits;
+    pl.windows = (255 + pl.c - 1) / pl.c;
+    const uint32_t digits = 1u << pl.c;
+    pl.chunks = digits / 64 ? digits / 64 : 1;
+    return pl;
+}
+// sum_i bases[i] * scalars[i] -> 96 canonical affine bytes in d_out (device).  scalars: a Montgomery Fr table.
+int32_t msm_run(zkb_ctx* c, const Table& scalars, const G1Affine* bases, uint64_t n, uint8_t* d_out) {
+    if (n <= 256) {
+        G1Jac* scratch = nullptr;
+        ZK_CUDA(c, cudaMallocAsync((void**)&scratch, sizeof(G1Jac) * 256, c->stream));
+        k_msm_small<<<1, 256, 0, c->stream>>>(scalars.ref(), bases, (uint32_t)n, scratch, d_out);
+        ZK_TRY(check_launch(c, "k_msm_small"));
+        cudaFreeAsync(scratch, c->stream);
+        return ZKB_OK;
+    }
+    const MsmPlan pl = msm_plan(n);
+    const uint64_t m = (uint64_t)pl.windows * n;
+    if (m >= (1ull << 32)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "msm: more than 2^32 (window, point) pairs");
+    const uint32_t nb = pl.windows << pl.c;
+    uint32_t *keys = nullptr, *vals = nullptr, *keys2 = nullptr, *vals2 = nullptr, *start = nullptr, *heavy = nullptr;
+    G1Jac *buckets = nullptr, *parts = nullptr, *wsum = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int key_bits = (int)pl.c;
+    while ((1u << (key_bits - (int)pl.c)) < pl.windows) ++key_bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)m, 0, key_bits, c->stream);
+    ZK_CUDA(c, cudaMallocAsync((void**)&keys, m * 4, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&vals, m * 4, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&keys2, m * 4, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&vals2, m * 4, c->stream));
+    ZK_CUDA(c, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&start, (size_t)nb * 8, c->stream));  // start[nb], end[nb]
+    ZK_CUDA(c, cudaMallocAsync((void**)&heavy, ((size_t)nb + 1) * 4, c->stream));  // count, then the list
+    ZK_CUDA(c, cudaMallocAsync((void**)&buckets, sizeof(G1Jac) * nb, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&parts, sizeof(G1Jac) * pl.windows * pl.chunks, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&wsum, sizeof(G1Jac) * pl.windows, c->stream));
+    ZK_CUDA(c, cudaMemsetAsync(start, 0, (size_t)nb * 8, c->stream));
+    ZK_CUDA(c, cudaMemsetAsync(heavy, 0, 4, c->stream));
+    uint32_t* end = start + nb;
+    k_msm_digits<<<grid_for(c, n, 8), BLOCK, 0, c->stream>>>(scalars.ref(), n, pl, keys, vals);
+    ZK_TRY(check_launch(c, "k_msm_digits"));
+    if (cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)m, 0, key_bits, c->stream) != cudaSuccess)
+        ZK_FAIL(c, ZKB_ERR_CUDA, "msm: radix sort failed");
+    k_msm_bounds<<<grid_for(c, m, 8), BLOCK, 0, c->stream>>>(keys2, m, start, end);
+    ZK_TRY(check_launch(c, "k_msm_bounds"));
+    k_msm_buckets<<<(nb + 127) / 128, 128, 0, c->stream>>>(vals2, start, end, bases, pl, buckets, heavy + 1, heavy);
+    ZK_TRY(check_launch(c, "k_msm_buckets"));
+    k_msm_heavy<<<c->sm_count, 256, sizeof(G1Jac) * 256, c->stream>>>(vals2, start, end, bases, buckets, heavy + 1, heavy);
+    ZK_TRY(check_launch(c, "k_msm_heavy"));
+    k_msm_window_chunks<<<(pl.windows * pl.chunks + 127) / 128, 128, 0, c->stream>>>(buckets, pl, parts);
+    ZK_TRY(check_launch(c, "k_msm_window_chunks"));
+    k_msm_window_sum<<<pl.windows, 128, 0, c->stream>>>(parts, pl, wsum);
+    ZK_TRY(check_launch(c, "k_msm_window_sum"));
+    k_msm_horner<<<1, 32, 0, c->stream>>>(wsum, pl, d_out);
+    ZK_TRY(check_launch(c, "k_msm_horner"));
+    for (void* q : {(void*)keys, (void*)vals, (void*)keys2, (void*)vals2, tmp, (void*)start, (void*)heavy, (void*)buckets, (void*)parts, (void*)wsum})
+        cudaFreeAsync(q, c->stream);
+    return ZKB_OK;
+}
+int32_t kzg_require_field(zkb_ctx* c) {
+    if (c->field != ZKB_FIELD_BLS12_381_FR) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "kzg: the commitment lives on BLS12-381; create the ctx with ZKB_FIELD_BLS12_381_FR");
+    if (c->comm && c->world > 1) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "kzg: sharded tables are not supported (GKR input layers are replicas only)");
+    return ZKB_OK;
+}
+int32_t jac_to_affine(zkb_ctx* c, const G1Jac* jac, G1Affine* aff, uint64_t n) {
+    const uint64_t threads = (n + KZG_BATCH - 1) / KZG_BATCH;
+    k_g1_batch_affine<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(jac, aff, n);
+    return check_launch(c, "k_g1_batch_affine");
+}
 }  // namespace
 
 // =================================================================== C ABI
@@ -1782,6 +1874,8 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->sps) sp_release(c, kv.second.get());
+    for (auto& kv : c->kzgs) kzg_release(c, kv.second.get());
+    if (c->g1_table) cudaFree(c->g1_table);
     for (auto& kv : c->circs) {
         CircuitState* cs = kv.second.get();
         sp_release(c, &cs->sp);
@@ -2813,6 +2907,135 @@ int32_t zkb_gkr_verify_wired(zkb_ctx* c, zkb_circ h, const uint64_t* inputs, uin
 }
 
 // ------------------------------------------------------------- microbenchmarks
+// ------------------------------------------------------------ multilinear KZG (input-layer commitment)
+int32_t zkb_kzg_setup(zkb_ctx* c, uint32_t n_vars, const uint64_t* taus, zkb_kzg* out) {
+    if (!c || !taus || !out) return ZKB_ERR_BAD_ARG;
+    ZK_TRY(kzg_require_field(c));
+    if (n_vars < 1 || n_vars > 26) ZK_FAIL(c, ZKB_ERR_ARITY, "Invalid num of vars for lagrange basis");  // kzg.rs:184-186
+    const uint64_t N = 1ull << n_vars;
+    if (!c->g1_table) {
+        ZK_CUDA(c, cudaMalloc((void**)&c->g1_table, sizeof(G1Affine) * 32 * 256));
+        k_g1_window_table<<<64, 128, 0, c->stream>>>(c->g1_table);
+        ZK_TRY(check_launch(c, "k_g1_window_table"));
+    }
+    // Lagrange scalars eq(taus, .) (kzg.rs:183-207)
+    std::vector<Fe> tv(n_vars);
+    for (uint32_t i = 0; i < n_vars; ++i) tv[i] = fe_from_u64x4(taus + 4 * i);
+    const int n_hi = (int)n_vars / 2, n_lo = (int)n_vars - n_hi;
+    Table hi, lo, L;
+    ZK_TRY(alloc_table(c, 1ull << n_hi, &hi));
+    ZK_TRY(alloc_table(c, 1ull << n_lo, &lo));
+    ZK_TRY(alloc_table(c, N, &L));
+    int nlo_out = 0;
+    ZK_TRY(eq_tables(c, tv.data(), (int)n_vars, &hi, &lo, &nlo_out));
+    k_kzg_eq_full<<<grid_for(c, N, 8), BLOCK, 0, c->stream>>>(hi.ref(), lo.ref(), nlo_out, L.ref(), N);
+    ZK_TRY(check_launch(c, "k_kzg_eq_full"));
+    std::unique_ptr<KzgState> ks(new KzgState);
+    ks->n_vars = n_vars;
+    ks->basis.assign(n_vars + 1, nullptr);
+    G1Jac* jac = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&jac, sizeof(G1Jac) * N, c->stream));
+    ZK_CUDA(c, cudaMallocAsync((void**)&ks->basis[0], sizeof(G1Affine) * N, c->stream));
+    k_g1_fixed_base<<<grid_for(c, N, 8) * 2, 128, 0, c->stream>>>(L.ref(), c->g1_table, jac, N);  // g1 * scalar, kzg.rs:209-212
+    ZK_TRY(check_launch(c, "k_g1_fixed_base"));
+    ZK_TRY(jac_to_affine(c, jac, ks->basis[0], N));
+    for (uint32_t k = 1; k <= n_vars; ++k) {  // folded bases: level k[j] = level k-1[j] + level k-1[j + half]
+        const uint64_t half = N >> k;
+        ZK_CUDA(c, cudaMallocAsync((void**)&ks->basis[k], sizeof(G1Affine) * half, c->stream));
+        k_g1_fold_basis<<<grid_for(c, half, 8) * 2, 128, 0, c->stream>>>(ks->basis[k - 1], jac, half);
+        ZK_TRY(check_launch(c, "k_g1_fold_basis"));
+        ZK_TRY(jac_to_affine(c, jac, ks->basis[k], half));
+    }
+    cudaFreeAsync(jac, c->stream);
+    free_table(c, &hi);
+    free_table(c, &lo);
+    free_table(c, &L);
+    zkb_kzg h = c->next_handle++;
+    c->kzgs[h] = std::move(ks);
+    *out = h;
+    return ZKB_OK;
+}
+int32_t zkb_kzg_free(zkb_ctx* c, zkb_kzg h) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    auto it = c->kzgs.find(h);
+    if (it == c->kzgs.end()) return ZKB_ERR_BAD_ARG;
+    kzg_release(c, it->second.get());
+    c->kzgs.erase(it);
+    return ZKB_OK;
+}
+int32_t zkb_kzg_basis(zkb_ctx* c, zkb_kzg h, uint32_t level, uint64_t first, uint64_t count, uint8_t* out) {
+    if (!c || !out) return ZKB_ERR_BAD_ARG;
+    auto it = c->kzgs.find(h);
+    if (it == c->kzgs.end() || level > it->second->n_vars) return ZKB_ERR_BAD_ARG;
+    const uint64_t n = 1ull << (it->second->n_vars - level);
+    if (first + count > n) return ZKB_ERR_BAD_ARG;
+    if (!count) return ZKB_OK;
+    uint8_t* d = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&d, count * 96, c->stream));
+    k_g1_export<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(it->second->basis[level] + first, count, d);
+    ZK_TRY(check_launch(c, "k_g1_export"));
+    ZK_CUDA(c, cudaMemcpyAsync(out, d, count * 96, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(d, c->stream);
+    return ZKB_OK;
+}
+int32_t zkb_kzg_commit(zkb_ctx* c, zkb_kzg h, zkb_mle poly, uint8_t out[96]) {
+    if (!c || !out) return ZKB_ERR_BAD_ARG;
+    ZK_TRY(kzg_require_field(c));
+    auto it = c->kzgs.find(h);
+    Table* t = find_mle(c, poly);
+    if (it == c->kzgs.end() || !t) return ZKB_ERR_BAD_ARG;
+    if (t->n != (1ull << it->second->n_vars)) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "invalid polynomial or lagrange basis");  // kzg.rs:135-137
+    uint8_t* d = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&d, 96, c->stream));
+    ZK_TRY(msm_run(c, *t, it->second->basis[0], t->n, d));
+    ZK_CUDA(c, cudaMemcpyAsync(out, d, 96, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(d, c->stream);
+    return ZKB_OK;
+}
+int32_t zkb_kzg_open(zkb_ctx* c, zkb_kzg h, zkb_mle poly, const uint64_t* opening_values, uint32_t n, uint64_t out[4]) {
+    if (!c) return ZKB_ERR_BAD_ARG;
+    if (c->kzgs.find(h) == c->kzgs.end()) return ZKB_ERR_BAD_ARG;
+    return zkb_mle_evaluate(c, poly, opening_values, n, out);  // kzg.rs:55-57
+}
+int32_t zkb_kzg_get_proof(zkb_ctx* c, zkb_kzg h, zkb_mle poly, const uint64_t opened_value[4], const uint64_t* opening_values, uint32_t n,
+                          uint8_t* out) {
+    (void)opened_value;  // the quotients do not depend on the constant shift poly - v (see kzg_impl.cuh)
+    if (!c || !opening_values || !out) return ZKB_ERR_BAD_ARG;
+    ZK_TRY(kzg_require_field(c));
+    auto it = c->kzgs.find(h);
+    Table* t = find_mle(c, poly);
+    if (it == c->kzgs.end() || !t) return ZKB_ERR_BAD_ARG;
+    KzgState* ks = it->second.get();
+    if (t->n != (1ull << ks->n_vars)) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "invalid polynomial or lagrange basis");
+    if (n > ks->n_vars) ZK_FAIL(c, ZKB_ERR_ARITY, "Invalid number of values");
+    uint8_t* d = nullptr;
+    ZK_CUDA(c, cudaMallocAsync((void**)&d, 96 * (size_t)(n ? n : 1), c->stream));
+    Table cur = *t, work, q;
+    ZK_TRY(alloc_table(c, t->n / 2, &work));
+    ZK_TRY(alloc_table(c, t->n / 2, &q));
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint64_t half = cur.n / 2;
+        q.n = half;
+        k_kzg_quotient<<<grid_for(c, half, 8), BLOCK, 0, c->stream>>>(cur.ref(), q.ref(), half);  // kzg.rs:152-163
+        ZK_TRY(check_launch(c, "k_kzg_quotient"));
+        ZK_TRY(msm_run(c, q, ks->basis[k + 1], half, d + 96 * (size_t)k));                          // :80-83 on the folded basis
+        FixedMul rt;                                                                               // remainder: partial_evaluate(0, z_k), :146-150
+        c->fmb.make(c->H, fe_from_u64x4(opening_values + 4 * k), &rt);
+        c->K->fold(cur.ref(), work.ref(), half, (uint32_t)ilog2_u64(half), rt, grid_for(c, half, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_fold"));
+        cur = work;
+        cur.n = half;
+    }
+    ZK_CUDA(c, cudaMemcpyAsync(out, d, 96 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFreeAsync(d, c->stream);
+    free_table(c, &work);
+    free_table(c, &q);
+    return ZKB_OK;
+}
+
 int32_t zkb_bench_modmul(zkb_ctx* c, int32_t variant, uint32_t iters, double* out) {
     if (!c || !out || variant < 0 || variant > 3) return ZKB_ERR_BAD_ARG;
     const int grid = c->sm_count * 8;

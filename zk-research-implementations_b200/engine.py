@@ -127,6 +127,12 @@ def lib() -> C.CDLL:
         "zkb_circuit_total_rounds": (i32, [vp, u64, u32p]),
         "zkb_gkr_prove_wired": (i32, [vp, u64, vp, u64, u64p, u64, u64p, i32p, u64p, u64p, u64p, u32p]),
         "zkb_gkr_verify_wired": (i32, [vp, u64, vp, u64, u64p, u64, u64p, i32p, u64p, u64p, i32p]),
+        "zkb_kzg_setup": (i32, [vp, u32, u64p, u64p]),
+        "zkb_kzg_free": (i32, [vp, u64]),
+        "zkb_kzg_basis": (i32, [vp, u64, u32, u64, u64, vp]),
+        "zkb_kzg_commit": (i32, [vp, u64, u64, vp]),
+        "zkb_kzg_open": (i32, [vp, u64, u64, u64p, u32, u64p]),
+        "zkb_kzg_get_proof": (i32, [vp, u64, u64, u64p, u64p, u32, vp]),
         "zkb_bench_modmul": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
         "zkb_bench_imad": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
     }
