@@ -112,6 +112,8 @@ extern "C" {
     pub fn zkb_gkr_prove_wired(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *mut u64, n_w0: u64, coeffs: *mut u64, lens: *mut i32, challenges: *mut u64, claimed: *mut u64, final_openings: *mut u64, n_rounds: *mut u32) -> i32;
     pub fn zkb_gkr_verify_wired(ctx: *mut zkb_ctx, c: zkb_circ, inputs_mont: *const u64, n_inputs: u64, w0: *const u64, n_w0: u64, coeffs: *const u64, lens: *const i32, claimed: *const u64, final_openings: *const u64, accepted: *mut i32) -> i32;
 
+    pub fn zkb_proof_encode(field_id: i32, kind: i32, n_rounds: u32, slots: u32, msgs_mont: *const u64, lens: *const i32, claimed_sum: *const u64, out: *mut u8, cap: usize, len: *mut usize) -> i32;
+    pub fn zkb_proof_decode(bytes: *const u8, len: usize, field_id: *mut i32, kind: *mut i32, n_rounds: *mut u32, slots: u32, msgs_mont: *mut u64, lens: *mut i32, claimed_sum: *mut u64) -> i32;
     pub fn zkb_kzg_setup(ctx: *mut zkb_ctx, n_vars: u32, taus_mont: *const u64, out: *mut zkb_kzg) -> i32;
     pub fn zkb_kzg_free(ctx: *mut zkb_ctx, k: zkb_kzg) -> i32;
     pub fn zkb_kzg_basis(ctx: *mut zkb_ctx, k: zkb_kzg, level: u32, first: u64, count: u64, out: *mut u8) -> i32;

@@ -192,6 +192,22 @@ int32_t zkb_uni_interpolate(int32_t field_id, const uint64_t* xs, const uint64_t
 /* evaluate :20-26 */
 int32_t zkb_uni_evaluate(int32_t field_id, const uint64_t* coeffs, uint32_t len, const uint64_t x[4], uint64_t out[4]);
 
+/* ------------------------------------------------ proof wire format (host only)
+ * A stable byte encoding of sum_check's two proof structs (sum_check_protocol.rs:8-17); every field element is written
+ * exactly as `fq_vec_to_bytes` writes it into the transcript (32-byte little-endian canonical integer,
+ * fiat_shamir_transcript.rs:32-37):
+ *   "ZKBP" | u8 version = 1 | u8 field_id | u8 kind | u8 0 | u32 n_rounds (LE) | claimed_sum (32 B) |
+ *   per round: u8 len, len x 32 B
+ * kind 1 = `Proof` (sum_check::prove): len = 2, the evaluations [s(0), s(1)]; `slots` must be 2, `lens` is ignored.
+ * kind 2 = `GkrProof` (gkr_prove): the trimmed ascending coefficients (len <= slots; `msgs` is n_rounds x slots).
+ * encode: out == NULL only returns the size in *len.  decode: msgs == NULL only checks the bytes and returns
+ * field / kind / n_rounds; it rejects (ZKB_ERR_BAD_ARG) bad magic, truncation, trailing bytes, len > slots and any
+ * element that is not a canonical residue, before writing anything. */
+int32_t zkb_proof_encode(int32_t field_id, int32_t kind, uint32_t n_rounds, uint32_t slots, const uint64_t* msgs_mont,
+                         const int32_t* lens, const uint64_t claimed_sum[4], uint8_t* out, size_t cap, size_t* len);
+int32_t zkb_proof_decode(const uint8_t* bytes, size_t len, int32_t* field_id, int32_t* kind, uint32_t* n_rounds, uint32_t slots,
+                         uint64_t* msgs_mont, int32_t* lens, uint64_t claimed_sum[4]);
+
 /* -------------------------------------------------------- sum_check_protocol */
 /* prove (sum_check_protocol.rs:25-52).  msgs: n_vars x 2 elements; challenges: n_vars elements (not part
  * of the reference's Proof, returned for callers that want them; may be NULL).

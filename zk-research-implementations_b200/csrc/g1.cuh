@@ -10,6 +10,14 @@
 #pragma once
 #include "fr.cuh"
 
+// The 12-limb product is ~600 instructions: as a real function (not inlined at its ~16 call sites per point addition)
+// it costs a few per cent at run time and cuts the compile time of the MSM kernels by an order of magnitude.
+#if defined(__CUDACC__)
+#define ZK_HD_CALL __host__ __device__ __noinline__
+#else
+#define ZK_HD_CALL inline
+#endif
+
 namespace zkb {
 
 struct Fq {
@@ -135,7 +143,7 @@ struct BigField {
         for (int k = 1; k < H; ++k) ev[k] = madwc_cc(P_::P(2 * k), m, ev[k]);
         od[H - 1] = pack64(lo32(od[H - 1]), addc(hi32(od[H - 1]), 0u));
     }
-    ZK_HD static E mul(const E& a, const E& b) {
+    ZK_HD_CALL static E mul(const E& a, const E& b) {
         uint64_t ev[H], od[H];
 #pragma unroll
         for (int i = 0; i < N; i += 2) {

@@ -332,6 +332,8 @@ struct zkb_ctx {
     unsigned long long* d_dbg = nullptr;
     int dbg_grid = 0;
     double tr_n = 0, tr_host = 0, tr_rtt = 0, tr_relay = 0, tr_spread = 0, tr_pass = 0, tr_reduce = 0;
+    // per table size (log2 of the entries bound in the round): rounds seen, device round trip, wait for the peer ranks
+    double trs_n[48] = {0}, trs_rtt[48] = {0}, trs_wait[48] = {0}, trs_host[48] = {0};
     std::unordered_map<std::string, int> occ_cache;
     // per-launch event timing (zkb_ctx_profile)
     bool prof = false;
@@ -1018,6 +1020,7 @@ struct RoundDriver {
         const bool was_live = live;
         const bool tracing = c->trace && was_live && !small;
         unsigned long long t_send = 0;
+        const unsigned long long t_recv_prev = t_recv;
         if (tracing) {
             t_send = host_ticks();
             if (t_recv) c->tr_host += (double)(t_send - t_recv) / tsc_per_us();
@@ -1080,9 +1083,19 @@ struct RoundDriver {
         Fe got[MAXPTS];
         if (small && dt) for (int t = 0; t < sp->npts - 1; ++t) got[t] = c->dt_rounds[pubs - 1].evals[t];
         else ZK_TRY(read_msg(got, sp->npts - 1, base + pubs));
+        const unsigned long long t_x0 = tracing ? host_ticks() : 0;
         if (sp->sharded && !c->shm.allreduce(c->H, got, sp->npts - 1)) {
             abort();
             ZK_FAIL(c, ZKB_ERR_NCCL, "shared-memory exchange: a peer rank stopped answering");
+        }
+        if (tracing) {
+            const int lg = ilog2_u64(sp->cur_n) + 1;  // the round that has just been answered bound tables of 2^lg entries
+            if (lg < 48) {
+                c->trs_n[lg] += 1;
+                c->trs_rtt[lg] += (double)(t_recv - t_send) / tsc_per_us();
+                c->trs_wait[lg] += (double)(host_ticks() - t_x0) / tsc_per_us();
+                if (t_recv_prev) c->trs_host[lg] += (double)(t_send - t_recv_prev) / tsc_per_us();
+            }
         }
         evals[0] = got[0];
         evals[1] = c->H.sub(claim, evals[0]);
@@ -1871,6 +1884,12 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
         fprintf(stderr, "[zkb200 trace] k_sc_tail rounds=%.0f  per round (us): host %.2f | send->result %.2f = relay %.2f + fan-out %.2f + pass(CTA0) %.2f + reduce/publish %.2f + pcie/poll %.2f\n",
                 c->tr_n, c->tr_host / c->tr_n, c->tr_rtt / c->tr_n, c->tr_relay / c->tr_n, c->tr_spread / c->tr_n, c->tr_pass / c->tr_n,
                 c->tr_reduce / c->tr_n, (c->tr_rtt - c->tr_relay - c->tr_spread - c->tr_pass - c->tr_reduce) / c->tr_n);
+    if (c->trace) {
+        for (int lg = 47; lg >= 0; --lg)
+            if (c->trs_n[lg] > 0)
+                fprintf(stderr, "[zkb200 trace] rank %d round 2^%-2d -> 2^%-2d  x%-4.0f device round trip %8.2f us | wait for the other ranks %7.2f us | host (transcript, claim) %5.2f us\n",
+                        c->rank, lg, lg - 1, c->trs_n[lg], c->trs_rtt[lg] / c->trs_n[lg], c->trs_wait[lg] / c->trs_n[lg], c->trs_host[lg] / c->trs_n[lg]);
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->sps) sp_release(c, kv.second.get());
@@ -2346,6 +2365,103 @@ int32_t zkb_uni_evaluate(int32_t field_id, const uint64_t* coeffs, uint32_t len,
     std::vector<Fe> co(len);
     for (uint32_t i = 0; i < len; ++i) co[i] = fe_from_u64x4(coeffs + 4 * i);
     fe_to_u64x4(uni_evaluate(H, co.data(), (int)len, fe_from_u64x4(x)), out);
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------ proof wire format (host only)
+// A stable byte encoding of the sumcheck proofs: every field element as fq_vec_to_bytes writes it into the transcript
+// (32-byte little-endian canonical integer, fiat_shamir_transcript.rs:32-37), behind a 12-byte header.
+//   "ZKBP" | u8 version = 1 | u8 field_id | u8 kind (1 = Proof of sum_check::prove, 2 = GkrProof of gkr_prove) | u8 0 |
+//   u32 n_rounds (LE) | claimed_sum (32 B) | per round: u8 len, then len x 32 B  (kind 1: len = 2, the evaluations
+//   [s(0), s(1)]; kind 2: the trimmed ascending coefficients, len <= slots)
+int32_t zkb_proof_encode(int32_t field_id, int32_t kind, uint32_t n_rounds, uint32_t slots, const uint64_t* msgs, const int32_t* lens,
+                         const uint64_t claimed_sum[4], uint8_t* out, size_t cap, size_t* len) {
+    const FieldKernels* K = kernels_for(field_id);
+    if (!K || (kind != 1 && kind != 2) || (!msgs && n_rounds) || !claimed_sum || !len || slots > 255 || (kind == 2 && !lens && n_rounds)) return ZKB_ERR_BAD_ARG;
+    if (kind == 1 && slots != 2) return ZKB_ERR_BAD_ARG;
+    HostField H = HostField::make(K);
+    size_t need = 12 + 32;
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        const int32_t l = kind == 1 ? 2 : lens[k];
+        if (l < 0 || (uint32_t)l > slots) return ZKB_ERR_BAD_ARG;
+        need += 1 + 32 * (size_t)l;
+    }
+    *len = need;
+    if (!out) return ZKB_OK;  // size query
+    if (cap < need) return ZKB_ERR_BAD_ARG;
+    if (!all_canonical(H, claimed_sum, 1)) return ZKB_ERR_BAD_ARG;
+    uint8_t* w = out;
+    std::memcpy(w, "ZKBP", 4);
+    w[4] = 1;
+    w[5] = (uint8_t)field_id;
+    w[6] = (uint8_t)kind;
+    w[7] = 0;
+    for (int i = 0; i < 4; ++i) w[8 + i] = (uint8_t)(n_rounds >> (8 * i));
+    w += 12;
+    auto put = [&](const uint64_t* mont) {
+        const Fe v = H.from_mont(fe_from_u64x4(mont));
+        std::memcpy(w, v.l, 32);
+        w += 32;
+    };
+    put(claimed_sum);
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        const int32_t l = kind == 1 ? 2 : lens[k];
+        if (!all_canonical(H, msgs + (size_t)k * slots * 4, (size_t)l)) return ZKB_ERR_BAD_ARG;
+        *w++ = (uint8_t)l;
+        for (int32_t i = 0; i < l; ++i) put(msgs + ((size_t)k * slots + i) * 4);
+    }
+    return ZKB_OK;
+}
+int32_t zkb_proof_decode(const uint8_t* bytes, size_t len, int32_t* field_id, int32_t* kind, uint32_t* n_rounds, uint32_t slots,
+                         uint64_t* msgs, int32_t* lens, uint64_t claimed_sum[4]) {
+    if (!bytes || len < 44 || !field_id || !kind || !n_rounds) return ZKB_ERR_BAD_ARG;
+    if (std::memcmp(bytes, "ZKBP", 4) != 0 || bytes[4] != 1 || bytes[7] != 0) return ZKB_ERR_BAD_ARG;
+    const FieldKernels* K = kernels_for(bytes[5]);
+    if (!K || (bytes[6] != 1 && bytes[6] != 2)) return ZKB_ERR_BAD_ARG;
+    HostField H = HostField::make(K);
+    *field_id = bytes[5];
+    *kind = bytes[6];
+    uint32_t n = 0;
+    for (int i = 0; i < 4; ++i) n |= (uint32_t)bytes[8 + i] << (8 * i);
+    // first pass: structure and canonical values (every element < p), nothing is written on a malformed proof
+    size_t off = 44;
+    auto canon_ok = [&](const uint8_t* p) {
+        uint64_t v[4];
+        std::memcpy(v, p, 32);
+        for (int k = 3; k >= 0; --k)
+            if (v[k] != H.p[k]) return v[k] < H.p[k];
+        return false;
+    };
+    if (!canon_ok(bytes + 12)) return ZKB_ERR_BAD_ARG;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (off >= len) return ZKB_ERR_BAD_ARG;
+        const uint32_t l = bytes[off++];
+        if ((bytes[6] == 1 && l != 2) || off + 32 * (size_t)l > len) return ZKB_ERR_BAD_ARG;
+        for (uint32_t i = 0; i < l; ++i)
+            if (!canon_ok(bytes + off + 32 * (size_t)i)) return ZKB_ERR_BAD_ARG;
+        if (msgs && l > slots) return ZKB_ERR_BAD_ARG;
+        off += 32 * (size_t)l;
+    }
+    if (off != len) return ZKB_ERR_BAD_ARG;
+    *n_rounds = n;
+    if (!msgs) return ZKB_OK;  // header query (the caller sizes its buffers from n_rounds and its slot count)
+    if (!claimed_sum || !lens) return ZKB_ERR_BAD_ARG;
+    auto get = [&](const uint8_t* p, uint64_t* mont) {
+        Fe v;
+        std::memcpy(v.l, p, 32);
+        fe_to_u64x4(H.to_mont(v), mont);
+    };
+    get(bytes + 12, claimed_sum);
+    off = 44;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t l = bytes[off++];
+        lens[k] = (int32_t)l;
+        for (uint32_t i = 0; i < slots; ++i) {
+            if (i < l) get(bytes + off + 32 * (size_t)i, msgs + ((size_t)k * slots + i) * 4);
+            else std::memset(msgs + ((size_t)k * slots + i) * 4, 0, 32);
+        }
+        off += 32 * (size_t)l;
+    }
     return ZKB_OK;
 }
 

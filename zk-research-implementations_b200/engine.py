@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         "zkb_circuit_total_rounds": (i32, [vp, u64, u32p]),
         "zkb_gkr_prove_wired": (i32, [vp, u64, vp, u64, u64p, u64, u64p, i32p, u64p, u64p, u64p, u32p]),
         "zkb_gkr_verify_wired": (i32, [vp, u64, vp, u64, u64p, u64, u64p, i32p, u64p, u64p, i32p]),
+        "zkb_proof_encode": (i32, [i32, i32, u32, u32, u64p, i32p, u64p, vp, sz, C.POINTER(sz)]),
+        "zkb_proof_decode": (i32, [vp, sz, i32p, i32p, u32p, u32, u64p, i32p, u64p]),
         "zkb_kzg_setup": (i32, [vp, u32, u64p, u64p]),
         "zkb_kzg_free": (i32, [vp, u64]),
         "zkb_kzg_basis": (i32, [vp, u64, u32, u64, u64, vp]),

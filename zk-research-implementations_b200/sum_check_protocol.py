@@ -131,3 +131,52 @@ def gkr_verify(round_polys: Sequence[UnivariatePoly], claimed_sum: int, transcri
     if not ok.value:
         return GkrVerify(False, 0, [0])  # :129-133
     return GkrVerify(True, E.limbs_to_ints(E.from_mont(fld, fin))[0], E.limbs_to_ints(E.from_mont(fld, ch[:n])) if n else [])
+
+
+# ------------------------------------------------------------------ proof wire format (zkb_proof_*)
+def _encode(field: int, kind: int, msgs: Sequence[Sequence[int]], claimed_sum: int, slots: int) -> bytes:
+    n = len(msgs)
+    arr = np.zeros((max(n, 1), slots, 4), dtype=np.uint64)
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    for k, m in enumerate(msgs):
+        if len(m) > slots:
+            raise ValueError("round message longer than the slot count")
+        lens[k] = len(m)
+        if len(m):
+            arr[k, : len(m)] = E.to_mont(field, E.ints_to_limbs([int(x) % E.MODULI[field] for x in m]))
+    cs = E.to_mont(field, E.ints_to_limbs([int(claimed_sum) % E.MODULI[field]]))
+    size = C.c_size_t()
+    _ck(None, lib().zkb_proof_encode(field, kind, n, slots, _p(arr), lens.ctypes.data_as(i32p), _p(cs), None, 0, C.byref(size)))
+    out = np.zeros(size.value, dtype=np.uint8)
+    _ck(None, lib().zkb_proof_encode(field, kind, n, slots, _p(arr), lens.ctypes.data_as(i32p), _p(cs), out.ctypes.data, size.value, C.byref(size)))
+    return out.tobytes()
+
+
+def _decode(data: bytes, slots: int):
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    fld, kind, n = C.c_int32(), C.c_int32(), C.c_uint32()
+    _ck(None, lib().zkb_proof_decode(buf.ctypes.data, len(data), C.byref(fld), C.byref(kind), C.byref(n), slots, None, None, None))
+    arr = np.zeros((max(n.value, 1), slots, 4), dtype=np.uint64)
+    lens = np.zeros(max(n.value, 1), dtype=np.int32)
+    cs = np.zeros((1, 4), dtype=np.uint64)
+    _ck(None, lib().zkb_proof_decode(buf.ctypes.data, len(data), C.byref(fld), C.byref(kind), C.byref(n), slots, _p(arr), lens.ctypes.data_as(i32p), _p(cs)))
+    msgs = [E.limbs_to_ints(E.from_mont(fld.value, arr[k, : lens[k]])) if lens[k] else [] for k in range(n.value)]
+    return fld.value, kind.value, msgs, E.limbs_to_ints(E.from_mont(fld.value, cs))[0]
+
+
+def proof_to_bytes(proof, field: int) -> bytes:
+    """Stable byte encoding of a `Proof` (kind 1) or `GkrProof` (kind 2): elements as fq_vec_to_bytes writes them
+    (fiat_shamir_transcript.rs:32-37) behind a 12-byte header; see include/zkb200.h."""
+    if isinstance(proof, GkrProof):
+        msgs = [q.coefficients for q in proof.proof_polynomials]
+        return _encode(field, 2, msgs, proof.claimed_sum, max([len(m) for m in msgs] + [1]))
+    return _encode(field, 1, proof.proof_polynomials, proof.claimed_sum, 2)
+
+
+def proof_from_bytes(data: bytes):
+    """Inverse of proof_to_bytes; raises ZkbError on malformed bytes or non-canonical elements."""
+    kind = data[6] if len(data) > 6 else 0
+    fld, kind, msgs, cs = _decode(data, 2 if kind == 1 else 8)
+    if kind == 1:
+        return Proof(msgs, cs), fld
+    return GkrProof([UnivariatePoly(m, fld) for m in msgs], cs, []), fld
