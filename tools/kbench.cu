@@ -77,14 +77,15 @@ int main(int argc, char** argv) {
         a.fin.ticket = ticket;
         a.fin.result = result;
         auto kern = k_sc_eval<FT, KIND_PROD, D, NPTS>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        constexpr int ESM = STAGE_BYTES;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ESM));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, STAGE_BYTES));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, ESM));
         const int grid = sms * occ;
         float best = 1e30f;
         for (int r = 0; r < reps + 1; ++r) {
             CK(cudaEventRecord(e0));
-            kern<<<grid, BLOCK, STAGE_BYTES>>>(a);
+            kern<<<grid, BLOCK, ESM>>>(a);
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             float ms;

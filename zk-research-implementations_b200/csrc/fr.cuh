@@ -372,47 +372,45 @@ struct Field {
             od[3] = madwc_cc(T.t[i][7], x.l[i], od[3]);
             co = addc(co, 0u);
         }
-        // merge to 10 x 32-bit limbs: s = ev + (od << 32)
-        uint32_t s[10];
-        s[0] = lo32(ev[0]);
-        s[1] = add_cc(hi32(ev[0]), lo32(od[0]));
-        s[2] = addc_cc(lo32(ev[1]), hi32(od[0]));
-        s[3] = addc_cc(hi32(ev[1]), lo32(od[1]));
-        s[4] = addc_cc(lo32(ev[2]), hi32(od[1]));
-        s[5] = addc_cc(hi32(ev[2]), lo32(od[2]));
-        s[6] = addc_cc(lo32(ev[3]), hi32(od[2]));
-        s[7] = addc_cc(hi32(ev[3]), lo32(od[3]));
-        s[8] = addc_cc(ce, hi32(od[3]));
-        s[9] = addc(co, 0u);
-        // two reduction rows: s = (s + m*p) / 2^32
-#pragma unroll
-        for (int row = 0; row < 2; ++row) {
-            const uint32_t m = mul_lo(s[0], F::INV);
-            s[0] = mad_lo_cc(F::P(0), m, s[0]);
-            s[1] = madc_hi_cc(F::P(0), m, s[1]);
-#pragma unroll
-            for (int j = 2; j < 8; j += 2) {
-                s[j] = madc_lo_cc(F::P(j), m, s[j]);
-                s[j + 1] = madc_hi_cc(F::P(j), m, s[j + 1]);
-            }
-            s[8] = addc_cc(s[8], 0u);
-            s[9] = addc(s[9], 0u);
-            s[1] = mad_lo_cc(F::P(1), m, s[1]);
-            s[2] = madc_hi_cc(F::P(1), m, s[2]);
-#pragma unroll
-            for (int j = 3; j < 8; j += 2) {
-                s[j] = madc_lo_cc(F::P(j), m, s[j]);
-                s[j + 1] = madc_hi_cc(F::P(j), m, s[j + 1]);
-            }
-            s[9] = addc(s[9], 0u);
-#pragma unroll
-            for (int j = 0; j < 9; ++j) s[j] = s[j + 1];
-            s[9] = 0;
-        }
+        // Two Montgomery rows (divide by 2^64) on the split accumulators, so every product stays on a 64-bit aligned
+        // limb pair (no re-pairing moves).  Row 1 clears limb 0 = lo32(ev[0]); row 2 clears limb 1 =
+        // hi32(ev[0]) + lo32(od[0]) (mod 2^32): m1 * p sits one limb higher, so its even-limb products go to the
+        // odd accumulator and its odd-limb products to the even one, one word up.
+        const uint32_t m0 = mul_lo(lo32(ev[0]), F::INV);
+        ev[0] = madw_cc(F::P(0), m0, ev[0]);
+        ev[1] = madwc_cc(F::P(2), m0, ev[1]);
+        ev[2] = madwc_cc(F::P(4), m0, ev[2]);
+        ev[3] = madwc_cc(F::P(6), m0, ev[3]);
+        ce = addc(ce, 0u);
+        od[0] = madw_cc(F::P(1), m0, od[0]);
+        od[1] = madwc_cc(F::P(3), m0, od[1]);
+        od[2] = madwc_cc(F::P(5), m0, od[2]);
+        od[3] = madwc_cc(F::P(7), m0, od[3]);
+        co = addc(co, 0u);
+        const uint32_t m1 = mul_lo(hi32(ev[0]) + lo32(od[0]), F::INV);
+        od[0] = madw_cc(F::P(0), m1, od[0]);
+        od[1] = madwc_cc(F::P(2), m1, od[1]);
+        od[2] = madwc_cc(F::P(4), m1, od[2]);
+        od[3] = madwc_cc(F::P(6), m1, od[3]);
+        co = addc(co, 0u);
+        uint64_t e4 = ce;  // limbs (8, 9) of the even accumulator
+        ev[1] = madw_cc(F::P(1), m1, ev[1]);
+        ev[2] = madwc_cc(F::P(3), m1, ev[2]);
+        ev[3] = madwc_cc(F::P(5), m1, ev[3]);
+        e4 = madwc(F::P(7), m1, e4);
+        // result = (ev + (od << 32)) >> 64 < p (1 + 2^-29): S < 2^35 p and m0 + m1 2^32 < 2^64.  Limb 1 is zero mod 2^32;
+        // its carry (1 unless both halves are zero) enters limb 2.
         Fe r;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r.l[j] = s[j];
-        return reduce_once(r);  // s < 2p, s[8] == 0
+        (void)add_cc(hi32(ev[0]), lo32(od[0]));
+        r.l[0] = addc_cc(lo32(ev[1]), hi32(od[0]));
+        r.l[1] = addc_cc(hi32(ev[1]), lo32(od[1]));
+        r.l[2] = addc_cc(lo32(ev[2]), hi32(od[1]));
+        r.l[3] = addc_cc(hi32(ev[2]), lo32(od[2]));
+        r.l[4] = addc_cc(lo32(ev[3]), hi32(od[2]));
+        r.l[5] = addc_cc(hi32(ev[3]), lo32(od[3]));
+        r.l[6] = addc_cc(lo32(e4), hi32(od[3]));
+        r.l[7] = addc(hi32(e4), co);
+        return reduce_once(r);
     }
     // b - a + p in (0, 2p): an UNREDUCED difference (no compare / select), fine as the x of mul_fixed and as an
     // operand of mac_wide, which only need x < 2^256
