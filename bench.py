@@ -47,13 +47,20 @@ DTYPE = "u32x8 Montgomery (BN254 Fr)"
 
 # Wide (32x32->64) multiply-accumulates of the round kernels per unit of work:
 #   fold with a fixed multiplicand 80, lazy 512-bit product 64, full Montgomery product 136.
-MACS_FOLD, MACS_LAZY, MACS_FULL = 80, 64, 136
+#   A fold on the tensor cores (tcfold.cuh: u8 x u8 -> s32 tcgen05.mma, throughput-bound rounds of products of >= 2
+#   factors and <= 4 points) leaves the CUDA cores ONE Montgomery row = 8 wide multiplies.
+MACS_FOLD, MACS_FOLD_TC, MACS_LAZY, MACS_FULL = 80, 8, 64, 136
+
+
+def tc_folds(D: int) -> bool:
+    return 2 <= D <= 3 and os.environ.get("ZKB200_NO_TC") is None
 
 
 def macs_per_quad(P: int, D: int) -> int:
-    """k_sc_fold_eval: per quad and product, 2*D folds and D sums (s(1) comes from the claim), each sum one product of
-    D factors = (D-2) full products + one lazy product."""
-    return P * (2 * D * MACS_FOLD + D * ((D - 2) * MACS_FULL + MACS_LAZY))
+    """k_sc_fold_eval / k_sc_tail, large rounds: per quad and product, 2*D folds and D sums (s(1) comes from the claim),
+    each sum one product of D factors = (D-2) full products + one lazy product."""
+    fold = MACS_FOLD_TC if tc_folds(D) else MACS_FOLD
+    return P * (2 * D * fold + D * ((D - 2) * MACS_FULL + MACS_LAZY))
 
 
 def macs_per_pair_round0(P: int, D: int) -> int:
@@ -495,6 +502,8 @@ class Bench:
             "note": "the persistent kernel's duration includes its per-round waits for the host transcript (mailbox); "
                     "largest_round isolates one round of the same code",
             "largest_round": big,
+            "fold_engine": ("tcgen05.mma kind::i8 (u8 x u8 -> s32 in TMEM, operands by TMA bulk copy; csrc/tcfold.cuh): bit-identical to the "
+                            "CUDA-core fold" if tc_folds(D_) else "CUDA cores (fixed-multiplicand Montgomery product)"),
             "imad": {"wide_macs_per_quad": macs_per_quad(P_, D_), "bytes_per_quad": 96 * P_ * D_ * 2,
                      "measured_imad_wide_x_per_s": imad, "measured": "zkb_bench_imad in this run"},
             "kernels": {k: {"launches": v[0], "ms_per_step": v[1] / args.steps, "GBps": v[2] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0}

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "tcfold.cuh"
 
 #ifndef KB_D
 #define KB_D 3
@@ -124,11 +125,21 @@ int main(int argc, char** argv) {
             memcpy(a.rt.t[i], t.l, 32);
             for (int k = 0; k < 32; ++k) v = Field<FT>::add(v, v);
         }
+#ifdef KB_TC
+        ScArgsTc atc;
+        atc.s = a;
+        tc_fold_mats<FT>(r, &atc.mats);
+        auto kern = k_sc_fold_eval_tc<FT, KIND_PROD, D, NPTS>;
+        constexpr int SM = TcRoundSmem<NPTS>::bytes;
+#define a atc
+#else
         auto kern = k_sc_fold_eval<FT, KIND_PROD, D, NPTS>;
         constexpr int SM = FoldSmem<KIND_PROD, D, NPTS>::bytes;
+#endif
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, SM));
+        if (getenv("KB_OCC")) occ = atoi(getenv("KB_OCC"));
         const int grid = sms * occ;
         float best = 1e30f;
         for (int r2 = 0; r2 < reps + 1; ++r2) {
@@ -146,9 +157,9 @@ int main(int argc, char** argv) {
         // hash a slice of every folded table
         std::vector<unsigned char> buf(1 << 20);
         for (int t = 0; t < T; ++t) {
-            CK(cudaMemcpy(buf.data(), work[t].base + (N / 4) - 1000, buf.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(buf.data(), work[t].base + (N / 4 > 1000 ? (N / 4) - 1000 : 0), buf.size() < N * 8 ? buf.size() : N * 8, cudaMemcpyDeviceToHost));
             h = fnv(h, buf.data(), buf.size());
-            CK(cudaMemcpy(buf.data(), work[t].base + work[t].stride, buf.size(), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(buf.data(), work[t].base + work[t].stride, buf.size() < N * 8 ? buf.size() : N * 8, cudaMemcpyDeviceToHost));
             h = fnv(h, buf.data(), buf.size());
         }
         const double bytes = 96.0 * T * (double)(N / 2);

@@ -38,8 +38,35 @@ bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaSt
 #undef X
     return false;
 }
-int l_sc_tail(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream_t s) {
+#define ZKB_TC_CASES(X) X(KIND_PROD, 2, 3) X(KIND_PROD, 2, 4) X(KIND_PROD, 3, 4)
+bool l_sc_fold_eval_tc(int kind, int D, int npts, const ScArgsTc& a, int grid, cudaStream_t s) {
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { \
+        constexpr int SM = TcRoundSmem<NP>::bytes; \
+        static bool once = (cudaFuncSetAttribute(k_sc_fold_eval_tc<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
+        (void)once; \
+        k_sc_fold_eval_tc<FT, K, DD, NP><<<grid, BLOCK, SM, s>>>(a); \
+        return true; \
+    }
+    ZKB_TC_CASES(X)
+#undef X
+    return false;
+}
+int l_sc_tail(int kind, int D, int npts, bool tc, const TailArgs& a, int grid, cudaStream_t s) {
     void* params[1] = {const_cast<TailArgs*>(&a)};
+    if (tc) {
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { \
+        constexpr int SM = TailSmemTc<NP>::bytes; \
+        static bool once = (cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
+        (void)once; \
+        k_sc_tail<FT, K, DD, NP, true><<<grid, BLOCK, SM, s>>>(a); \
+        return (int)cudaGetLastError(); \
+    }
+        ZKB_TC_CASES(X)
+#undef X
+        return -1;
+    }
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         constexpr int SM = TailSmem<K, DD, NP>::bytes; \
@@ -67,6 +94,19 @@ int l_sc_small(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s) {
 }
 int l_sc_occupancy(int fused, int kind, int D, int npts) {
     int nb = 0;
+    if (fused >= 3) {
+        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that allocates tensor memory; two CTAs
+        // of 128 columns each are co-resident (measured: 2 x 148 CTAs run in the time of one wave), so the count
+        // follows from shared memory and registers (<= 128 by __launch_bounds__(BLOCK, 2)) alone
+#define X(K, DD, NP) \
+    if (kind == K && D == DD && npts == NP) { \
+        const int sm = fused == 3 ? TcRoundSmem<NP>::bytes : TailSmemTc<NP>::bytes; \
+        return 2 * (sm + 1024) + 2048 <= 227 * 1024 ? 2 : 1; \
+    }
+        ZKB_TC_CASES(X)
+#undef X
+        return 0;
+    }
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         if (fused == 2) { \
@@ -162,7 +202,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

@@ -150,6 +150,13 @@ struct FixedMul {
     uint32_t t[8][8];
 };
 
+// The same challenge for the tensor-core fold (tcfold.cuh): the two u8 B operands of tcgen05.mma kind::i8, [0] for the
+// "a" rows (1 - r), [1] for the "b" rows (r).  B[n][k] = byte n of T_k with T_k = (1 - r) 2^(8 k + 32) mod p resp.
+// r 2^(8 k + 32) mod p, stored K-major without swizzle: byte offset (k / 16) * 512 + n * 16 + k % 16.
+struct alignas(16) TcFoldMats {
+    uint8_t b[2][1024];
+};
+
 // 512-bit (+32 guard bits) integer accumulator for sums of raw products
 // a*b of Montgomery residues; one Montgomery reduction at the very end.
 struct Wide {

@@ -402,6 +402,32 @@ struct FixedMulBuilder {
     }
 };
 
+// The same challenge for the tensor-core fold (fr.cuh TcFoldMats, tcfold.cuh): column k of the two byte matrices is
+// T1_k = (1 - r) 2^(8 k + 32) mod p resp. T2_k = r 2^(8 k + 32) mod p; c[32] = ONE (Montgomery form).
+struct TcMatsBuilder {
+    Fe c[33];  // 2^(8 k + 32) mod p as plain integers, then ONE
+    void init(const HostField& H) {
+        Fe v = H.zero();
+        v.l[1] = 1;
+        for (int k = 0; k < 32; ++k) {
+            c[k] = v;
+            for (int d = 0; d < 8; ++d) v = H.add(v, v);
+        }
+        c[32] = H.one();
+    }
+    void make(const HostField& H, const Fe& r, TcFoldMats* out) const {
+        const Fe omr = H.sub(c[32], r);
+        for (int k = 0; k < 32; ++k) {
+            const Fe t1 = H.mul(omr, c[k]), t2 = H.mul(r, c[k]);
+            uint8_t* m = out->b[0] + (k / 16) * 512 + k % 16;
+            for (int n = 0; n < 32; ++n) {
+                m[n * 16] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
+                m[1024 + n * 16] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
+            }
+        }
+    }
+};
+
 // -------------------------------------------------------------- Transcript
 // fiat_shamir_transcript.rs:5-30
 struct TranscriptImpl {

@@ -879,6 +879,10 @@ __global__ void __launch_bounds__(BLOCK, ZKB_MINB) k_sc_fold_eval(const __grid_c
     finish_round<F, NPTS - 1>(out, a.fin);
 }
 
+}  // namespace zkb
+#include "tcfold.cuh"
+namespace zkb {
+
 // ------------------------------------------------- persistent round kernel
 // All remaining rounds of a sumcheck in ONE cooperative launch.  The transcript
 // stays on the host: per round the kernel publishes its NPTS-1 sums to a mailbox
@@ -910,6 +914,8 @@ struct TailRelay {  // device memory: CTA 0 re-publishes the host's message for 
     FixedMul rt;
     unsigned int seq;
     unsigned int abort;
+    unsigned int pad[2];
+    TcFoldMats mats;  // tensor-core variant: the byte matrices of the same challenge
 };
 struct TailArgs {
     TabRef in[MAXT];
@@ -919,6 +925,8 @@ struct TailArgs {
     uint64_t n_in;             // entries per table at entry
     FixedMul rt0;              // table of the first challenge to bind
     Fe cpow[8];                // 2^(32 i + 64) mod p: FixedMul rows are mul(r, cpow[i])
+    const Fe* cpow8;           // tensor-core variant (device memory): 2^(8 i + 32) mod p, i < 32, and ONE (Montgomery) at [32]
+    TcFoldMats mats0;          // tensor-core variant: the matrices of the first challenge to bind
     TailMailbox* mb;
     TailRelay* relay;
     Fe* partials;
@@ -930,12 +938,35 @@ struct TailArgs {
     unsigned long long* dbg;   // optional [2 * gridDim]: per-CTA start/end %globaltimer of the pass of round `it == 1`
 };
 
-template <class F, int KIND, int D, int NPTS>
+// TC: the folds of every round pass run on the tensor cores (round_pass_tc); the host only launches this variant when
+// every round of the launch has at least 256 output entries per table (n_out / 2 a multiple of 128).
+template <class F, int KIND, int D, int NPTS, bool TC>
+__device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, FixedMul& s_rt, unsigned int& s_abort, uint32_t tmem);
+
+template <class F, int KIND, int D, int NPTS, bool TC = false>
 __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ TailArgs a) {
-    typedef Field<F> Fd;
-    extern __shared__ uint4 stage[];
+    extern __shared__ __align__(128) uint4 stage[];
     __shared__ FixedMul s_rt;
     __shared__ unsigned int s_abort;
+    __shared__ uint32_t s_tmem;
+    uint32_t tmem = 0;
+    if (TC) {
+        if (threadIdx.x < 32) tmem_alloc(&s_tmem, TcCfg<NPTS>::tmem_cols);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem = s_tmem;
+    }
+    tail_body<F, KIND, D, NPTS, TC>(a, stage, s_rt, s_abort, tmem);
+    if (TC) {  // every exit of the body is CTA-uniform
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x < 32) tmem_dealloc(tmem, TcCfg<NPTS>::tmem_cols);
+    }
+}
+template <class F, int KIND, int D, int NPTS, bool TC>
+__device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, FixedMul& s_rt, unsigned int& s_abort, uint32_t tmem) {
+    typedef Field<F> Fd;
     uint64_t n_in = a.n_in;
     if (threadIdx.x == 0) s_abort = 0;
     if (a.first_eval) {  // round 0 inside the launch: message 1 = s(0..d) of the unbound tables
@@ -961,6 +992,10 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
         // ---- the challenge table of this round -> shared memory
         if (it == 0) {
             for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = (&a.rt0.t[0][0])[w];
+            if (TC) {
+                for (int w = threadIdx.x; w < 128; w += BLOCK)
+                    reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stage) + TcRoundSmem<NPTS>::mats_off)[w] = reinterpret_cast<const uint4*>(&a.mats0)[w];
+            }
             if (threadIdx.x == 0) s_abort = 0;
         } else {
             const unsigned int want = a.base_seq + it;
@@ -990,6 +1025,16 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
 #pragma unroll
                         for (int k = 0; k < 8; ++k) a.relay->rt.t[lane][k] = t.l[k];
                     }
+                    if (TC) {  // lane i: column i of both byte matrices, T1_i = (1 - r) 2^(8 i + 32), T2_i = r 2^(8 i + 32) mod p
+                        const Fe cp = a.cpow8[lane];
+                        const Fe t1 = Fd::mul(Fd::sub(a.cpow8[32], r), cp), t2 = Fd::mul(r, cp);
+                        uint8_t* m0 = a.relay->mats.b[0] + (lane / 16) * 512 + lane % 16;
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) {
+                            m0[n * 16] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
+                            m0[1024 + n * 16] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
+                        }
+                    }
                     __threadfence();
                     __syncwarp();
                     if (lane == 0) {
@@ -1015,7 +1060,12 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             __syncthreads();
             if (s_abort) return;
             for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = __ldcg(&a.relay->rt.t[0][0] + w);
+            if (TC) {
+                for (int w = threadIdx.x; w < 128; w += BLOCK)
+                    reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stage) + TcRoundSmem<NPTS>::mats_off)[w] = __ldcg(reinterpret_cast<const uint4*>(&a.relay->mats) + w);
+            }
         }
+        if (TC) fence_proxy_async();  // the matrices: generic-proxy writes, read by the tensor core through the async proxy
         __syncthreads();
         const uint64_t n_out = n_in >> 1;
         const TabRef* src = it == it0 ? a.in : a.out;
@@ -1040,7 +1090,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_tail(const __grid_constant__ Ta
             Fe out[NPTS - 1];
             if (blockIdx.x == 0 && threadIdx.x == 0) a.mb->ts[2] = gtime();
             if (a.dbg && it == 1 && threadIdx.x == 0) a.dbg[2 * blockIdx.x] = gtime();
-            round_pass<F, KIND, D, NPTS>(src, a.out, a.n_products, n_out, s_rt, stage, out);
+            if constexpr (TC) round_pass_tc<F, D, NPTS>(src, a.out, a.n_products, n_out, reinterpret_cast<uint8_t*>(stage), tmem, out);
+            else round_pass<F, KIND, D, NPTS>(src, a.out, a.n_products, n_out, s_rt, stage, out);
             if (blockIdx.x == 0 && threadIdx.x == 0) a.mb->ts[3] = gtime();
             if (a.dbg && it == 1) {
                 __syncthreads();

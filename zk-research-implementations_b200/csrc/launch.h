@@ -13,11 +13,15 @@ struct FieldKernels {
     // composed-sumcheck kernels; kind/D/npts select the instantiation. Return false if unsupported.
     bool (*sc_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
     bool (*sc_fold_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
-    // persistent round kernel (cooperative launch); returns a cudaError_t, or -1 if the shape is not instantiated
-    int (*sc_tail)(int kind, int D, int npts, const TailArgs& a, int grid, cudaStream_t s);
+    // the same round with the folds on the tensor cores (tcfold.cuh); false if the shape is not instantiated
+    bool (*sc_fold_eval_tc)(int kind, int D, int npts, const ScArgsTc& a, int grid, cudaStream_t s);
+    // persistent round kernel (cooperative launch; tc: tensor-core variant, plain launch of a grid the caller sized to be
+    // co-resident); returns a cudaError_t, or -1 if the shape is not instantiated
+    int (*sc_tail)(int kind, int D, int npts, bool tc, const TailArgs& a, int grid, cudaStream_t s);
     // single-CTA shared-memory kernel for small tables; returns a cudaError_t, or -1 if not instantiated
     int (*sc_small)(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s);
-    // resident CTAs per SM for that instantiation (0 = unsupported); fused: 0 = k_sc_eval, 1 = k_sc_fold_eval, 2 = k_sc_tail
+    // resident CTAs per SM for that instantiation (0 = unsupported); fused: 0 = k_sc_eval, 1 = k_sc_fold_eval, 2 = k_sc_tail,
+    // 3 = k_sc_fold_eval_tc, 4 = k_sc_tail<TC>
     int (*sc_occupancy)(int fused, int kind, int D, int npts);
     void (*fold_tables)(const FoldTablesArgs& a, int grid, cudaStream_t s);
     void (*final_bind)(const FoldTablesArgs& a, Fe* out, volatile unsigned int* flag, unsigned int seq, cudaStream_t s);

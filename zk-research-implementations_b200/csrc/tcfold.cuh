@@ -1,0 +1,387 @@
+// tcfold.cuh -- binding a challenge on the 5th-generation tensor cores (tcgen05.mma kind::i8, sm_100a).
+//
+// A fold with a challenge r that is fixed for a whole launch,
+//     new = a + r (b - a) = a (1 - r) + b r            (multilinear_polynomial_evaluation.rs:52-63),
+// is linear in the BYTES of a and b: with T1_i = (1 - r) 2^(8 i + 32) mod p and T2_i = r 2^(8 i + 32) mod p,
+//     S = sum_i a_i T1_i + b_i T2_i  ==  (a (1 - r) + b r) 2^32   (mod p),      S < 64 * 255 * p < 2^14 p,
+// and S is two u8 x u8 -> s32 matrix products [128 entries x 32 bytes] . [32 x 32] accumulated in TMEM.  The rows of
+// the A operand are table entries exactly as they lie in the planar layout (plane 0 = bytes 0..15, plane 1 = bytes
+// 16..31 of every entry), which IS the K-major no-swizzle operand layout of the instruction (8-row x 16-byte core
+// matrices: SBO = 128 bytes, LBO = the distance of the two planes), so a tile goes from HBM to shared memory by TMA bulk
+// copies and from there into the tensor core without passing through a register.  The CUDA cores only carry the 32
+// column sums (< 2^22 each) into 9 limbs, run ONE 32-bit Montgomery row (division by 2^32: 8 wide multiplies instead
+// of the 82 of Field::fold_fixed) and subtract p once: the result is the canonical residue, bit-identical to the
+// CUDA-core fold.
+#pragma once
+// (included by kernels.cuh after the round-pass building blocks and before the persistent kernel)
+
+namespace zkb {
+
+template <class F>
+ZK_HD void tc_fold_mats(const Fe& r_mont, TcFoldMats* out) {
+    typedef Field<F> Fd;
+    const Fe one_minus_r = Fd::sub(Fd::one(), r_mont);
+    Fe v = Fd::zero();
+    v.l[1] = 1;  // 2^32 as a plain integer: mul(x R, v) = x v mod p
+    for (int i = 0; i < 32; ++i) {
+        const Fe t1 = Fd::mul(one_minus_r, v), t2 = Fd::mul(r_mont, v);
+        for (int n = 0; n < 32; ++n) {
+            const int off = (i / 16) * 512 + n * 16 + i % 16;
+            out->b[0][off] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
+            out->b[1][off] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
+        }
+        for (int k = 0; k < 8; ++k) v = Fd::add(v, v);
+    }
+}
+
+#if defined(__CUDACC__)
+// ---- tcgen05 / TMEM primitives (PTX; the encodings follow cute/arch/mma_sm100_desc.hpp) ----
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// shared-memory matrix descriptor, K-major, no swizzle: start address, LBO (distance of the two 16-byte K chunks),
+// SBO (distance of 8-row groups), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC_U8_M128_N32 = (2u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// this thread's row (TMEM lane) of 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* c) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]), "=r"(c[10]),
+          "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15]), "=r"(c[16]), "=r"(c[17]), "=r"(c[18]), "=r"(c[19]), "=r"(c[20]),
+          "=r"(c[21]), "=r"(c[22]), "=r"(c[23]), "=r"(c[24]), "=r"(c[25]), "=r"(c[26]), "=r"(c[27]), "=r"(c[28]), "=r"(c[29]), "=r"(c[30]),
+          "=r"(c[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 column sums (byte weights 2^(8 n), each < 2^22) -> the canonical residue S 2^-32 mod p
+template <class F>
+__device__ __forceinline__ Fe tc_fold_finish(const uint32_t* c) {
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t t01 = c[4 * k] + (c[4 * k + 1] << 8), t23 = c[4 * k + 2] + (c[4 * k + 3] << 8);  // < 2^31
+        const uint64_t w = (uint64_t)t01 + ((uint64_t)t23 << 16);                                       // limb k + its overflow (< 2^15)
+        lo[k] = lo32(w);
+        hi[k] = hi32(w);
+    }
+    uint32_t s[9];
+    s[0] = lo[0];
+    s[1] = add_cc(lo[1], hi[0]);
+#pragma unroll
+    for (int k = 2; k < 8; ++k) s[k] = addc_cc(lo[k], hi[k - 1]);
+    s[8] = addc(hi[7], 0u);
+    // one Montgomery row: (S + m p) >> 32 < p (1 + 2^-18).  m p is taken as even-limb products chained onto S and
+    // odd-limb products computed stand-alone (no carry, full-rate), merged by the final addition.
+    const uint32_t m = mul_lo(s[0], F::INV);
+    uint64_t e0 = madw_cc(F::P(0), m, pack64(s[0], s[1]));
+    uint64_t e1 = madwc_cc(F::P(2), m, pack64(s[2], s[3]));
+    uint64_t e2 = madwc_cc(F::P(4), m, pack64(s[4], s[5]));
+    uint64_t e3 = madwc_cc(F::P(6), m, pack64(s[6], s[7]));
+    s[8] = addc(s[8], 0u);
+    const uint64_t o0 = mul_wide(F::P(1), m), o1 = mul_wide(F::P(3), m), o2 = mul_wide(F::P(5), m), o3 = mul_wide(F::P(7), m);
+    Fe r;
+    r.l[0] = add_cc(hi32(e0), lo32(o0));
+    r.l[1] = addc_cc(lo32(e1), hi32(o0));
+    r.l[2] = addc_cc(hi32(e1), lo32(o1));
+    r.l[3] = addc_cc(lo32(e2), hi32(o1));
+    r.l[4] = addc_cc(hi32(e2), lo32(o2));
+    r.l[5] = addc_cc(lo32(e3), hi32(o2));
+    r.l[6] = addc_cc(hi32(e3), lo32(o3));
+    r.l[7] = addc(s[8], hi32(o3));
+    return Field<F>::reduce_once(r);
+}
+
+// ---- stand-alone fold kernel (partial_evaluate of variable 0): one tile of 128 output entries per step ----
+constexpr int TC_FOLD_THREADS = 128;
+constexpr int TC_TILE_BYTES = 2 * 128 * 16;                        // one operand tile: two planes of 128 x 16 bytes
+constexpr int TC_FOLD_SMEM = 2 * TC_TILE_BYTES + 2048 + 64;       // a, b, the two B matrices, barriers + TMEM address
+template <class F>
+__global__ void __launch_bounds__(TC_FOLD_THREADS) k_tc_fold(TabRef in, TabRef out, uint64_t n_out, const TcFoldMats* __restrict__ mats) {
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    uint8_t* sm_a = tc_sm;
+    uint8_t* sm_b = tc_sm + TC_TILE_BYTES;
+    uint8_t* sm_m = tc_sm + 2 * TC_TILE_BYTES;
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(tc_sm + 2 * TC_TILE_BYTES + 2048);
+    uint64_t* bar_mma = bar_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 2);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid; i < 2048 / 16; i += TC_FOLD_THREADS) reinterpret_cast<uint4*>(sm_m)[i] = reinterpret_cast<const uint4*>(mats)[i];
+    if (tid == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();  // the matrices were written through the generic proxy, the tensor core reads through the async one
+    if (warp == 0) tmem_alloc(tmem_slot, 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint64_t tiles = (n_out + 127) / 128;
+    uint32_t phase = 0;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t j0 = tile * 128;
+        const uint32_t rows = (uint32_t)(n_out - j0 < 128 ? n_out - j0 : 128);
+        if (tid == 0) {
+            mbar_expect_tx(bar_full, rows * 64u);
+            bulk_g2s(sm_a, in.base + j0, rows * 16u, bar_full);
+            bulk_g2s(sm_a + 2048, in.base + in.stride + j0, rows * 16u, bar_full);
+            bulk_g2s(sm_b, in.base + j0 + n_out, rows * 16u, bar_full);
+            bulk_g2s(sm_b + 2048, in.base + in.stride + j0 + n_out, rows * 16u, bar_full);
+        }
+#ifdef TC_TIMING
+        const long long t0 = clock64();
+#endif
+        mbar_wait(bar_full, phase);
+        tc_fence_after();
+#ifdef TC_TIMING
+        const long long t1 = clock64();
+#endif
+        if (tid == 0) {
+            umma_i8(tmem, umma_desc(smem_u32(sm_a), 2048, 128), umma_desc(smem_u32(sm_m), 512, 128), TC_IDESC_U8_M128_N32, 0u);
+            umma_i8(tmem, umma_desc(smem_u32(sm_b), 2048, 128), umma_desc(smem_u32(sm_m + 1024), 512, 128), TC_IDESC_U8_M128_N32, 1u);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, phase);
+        tc_fence_after();
+#ifdef TC_TIMING
+        const long long t2 = clock64();
+#endif
+        uint32_t c[32];
+        tmem_ld32(tmem + ((warp * 32u) << 16), c);
+        tmem_wait_ld();
+#ifdef TC_TIMING
+        const long long t3 = clock64();
+        if (tid == 0 && blockIdx.x == 0 && tile < 8 * (uint64_t)gridDim.x)
+            printf("tile %llu: TMA issue->landed %lld, MMA issue->barrier %lld, LDTM %lld cycles\n", (unsigned long long)tile, t1 - t0, t2 - t1, t3 - t2);
+#endif
+        const Fe v = tc_fold_finish<F>(c);
+        if (tid < rows) st_fe(out, j0 + tid, v);
+        tc_fence_before();
+        __syncthreads();  // every row has been read: the accumulator and the operand tiles may be overwritten
+        phase ^= 1u;
+    }
+    if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+// ---- the fused round pass (fold all tables with the challenge, write them once, accumulate the next round's sums
+// from the folded values) with the folds on the tensor cores.  Same ownership as round_pass (kernels.cuh): row r of
+// a tile is the quad position j = tile * 128 + r, its "lo" fold is entries (j, j + n_out) -> new[j], its "hi" fold
+// (j + half, j + half + n_out) -> new[j + half]; in-place operation stays safe.
+// A CTA is two independent warpgroups of 128 threads; a warpgroup walks its tiles unit by unit (unit = one fold of one
+// table for the 128 positions of the tile = 8 KiB of operands + one 32-column accumulator):
+//   TMA (leader thread):   unit q + NS  -> operand stage q % NS          (after the MMAs of unit q have completed)
+//   MMA (leader thread):   unit q + 1   -> TMEM stage (q + 1) % 2         (after every warp has read unit q - 1)
+//   all 128 threads:       unit q: TMEM -> registers, carry + Montgomery row, store, product accumulation
+// Needs n_out / 2 to be a multiple of 128 and BLOCK == 256.
+constexpr int TC_UNIT_BYTES = 2 * TC_TILE_BYTES;  // a tile + b tile
+#ifndef ZKB_TC_NT
+#define ZKB_TC_NT 2
+#endif
+// Pipeline depth: NS operand stages (shared memory, 8 KiB each) and NT accumulator stages (TMEM, 32 columns each) per
+// warpgroup, chosen so that two CTAs fit one SM next to the parked accumulators of the round sums.
+template <int NPTS>
+struct TcCfg {
+#ifdef ZKB_TC_NS
+    static constexpr int NS = ZKB_TC_NS;
+#else
+    static constexpr int NS = NPTS <= 3 ? 4 : 3;
+#endif
+    static constexpr int NT = ZKB_TC_NT;      // power of two, <= NS
+    static constexpr int tmem_cols = 2 * NT * 32;  // per CTA (a power of two >= 32)
+    static_assert(NT <= NS && (NT & (NT - 1)) == 0, "accumulator stages");
+};
+template <int NPTS>
+struct TcRoundSmem {
+    typedef TcCfg<NPTS> C;
+    static constexpr int stage_bytes = 2 * C::NS * TC_UNIT_BYTES;
+    static constexpr int mats_off = stage_bytes;
+    static constexpr int bars_off = mats_off + 2048;
+    static constexpr int bars_per_wg = (C::NS + 2 * C::NT) * 8;  // full[NS], mma[NT], empty[NT]
+    static constexpr int tmem_off = bars_off + 2 * bars_per_wg;
+    static constexpr int accs_off = bars_off + 256;
+    static constexpr int bytes = accs_off + (NPTS - 1) * ACC_VECS * BLOCK * 16;
+    static_assert(2 * bars_per_wg + 4 <= 256, "barrier block");
+};
+__device__ __forceinline__ void mbar_init_u32(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "ZKB_TCW_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra ZKB_TCW_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void wg_sync(uint32_t wg) {  // named barrier 1 / 2 (immediate ids: a register id makes ptxas reserve all 16)
+    if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+template <class F, int D, int NPTS>
+__device__ __forceinline__ void round_pass_tc(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products, uint64_t n_out,
+                                              uint8_t* smb, uint32_t tmem_cta, Fe* out) {
+    static_assert(BLOCK == 256, "two warpgroups per CTA");
+    typedef TcRoundSmem<NPTS> L;
+    constexpr int NS = TcCfg<NPTS>::NS, NT = TcCfg<NPTS>::NT, LOG_NT = NT == 1 ? 0 : (NT == 2 ? 1 : 2);
+    const uint32_t wg = threadIdx.x >> 7, r = threadIdx.x & 127u, wq = (threadIdx.x >> 5) & 3u, lane = threadIdx.x & 31u;
+    const uint64_t half = n_out >> 1;
+    const uint64_t tiles = half >> 7;
+    const uint64_t first = (uint64_t)blockIdx.x * 2 + wg, tstride = (uint64_t)gridDim.x * 2;
+    const uint32_t upt = 2u * (uint32_t)n_products * D;  // units per tile
+    const uint32_t my_tiles = first < tiles ? (uint32_t)((tiles - first + tstride - 1) / tstride) : 0u;
+    const uint32_t U = my_tiles * upt;
+    const uint32_t st0 = smem_u32(smb) + wg * (NS * TC_UNIT_BYTES);
+    const uint32_t mats = smem_u32(smb + L::mats_off);
+    const uint32_t b_full = smem_u32(smb + L::bars_off) + wg * L::bars_per_wg, b_mma = b_full + NS * 8, b_empty = b_mma + NT * 8;
+    const uint32_t tmem = tmem_cta + wg * (NT * 32u);
+    if (r == 0) {  // the barriers live for one pass (phase counting restarts with every pass)
+#pragma unroll
+        for (int b = 0; b < NS + 2 * NT; ++b) mbar_init_u32(b_full + b * 8, b < NS + NT ? 1u : 4u);
+        fence_barrier_init();
+    }
+    wg_sync(wg);
+    // leader state: next unit to load (tile, unit in tile, stage) and next unit to multiply (index, stage, parity)
+    uint64_t t_tile = first;
+    uint32_t t_u = 0, t_stage = 0, m_q = 0, m_stage = 0, m_par = 0;
+    auto issue_tma = [&]() {
+        const TabRef& tb = in[t_u >> 1];
+        const uint4* g0 = tb.base + t_tile * 128 + ((t_u & 1u) ? half : 0);
+        const uint4* g1 = g0 + tb.stride;
+        const uint32_t dst = st0 + t_stage * TC_UNIT_BYTES, bar = b_full + t_stage * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TC_UNIT_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g0), "r"(2048u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2048u), "l"(g1), "r"(2048u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 4096u), "l"(g0 + n_out), "r"(2048u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 6144u), "l"(g1 + n_out), "r"(2048u), "r"(bar) : "memory");
+        if (++t_u == upt) {
+            t_u = 0;
+            t_tile += tstride;
+        }
+        t_stage = t_stage + 1 == NS ? 0u : t_stage + 1;
+    };
+    auto issue_mma = [&]() {
+        const uint32_t ts = m_q & (NT - 1);
+        mbar_wait_u32(b_full + m_stage * 8, m_par);
+        if (m_q >= NT) mbar_wait_u32(b_empty + ts * 8, ((m_q >> LOG_NT) & 1u) ^ 1u);  // every warp has read unit m_q - NT
+        tc_fence_after();
+        const uint32_t d = tmem + ts * 32u, a0 = st0 + m_stage * TC_UNIT_BYTES;
+        umma_i8(d, umma_desc(a0, 2048, 128), umma_desc(mats, 512, 128), TC_IDESC_U8_M128_N32, 0u);
+        umma_i8(d, umma_desc(a0 + TC_TILE_BYTES, 2048, 128), umma_desc(mats + 1024, 512, 128), TC_IDESC_U8_M128_N32, 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_mma + ts * 8) : "memory");
+        ++m_q;
+        if (++m_stage == NS) {
+            m_stage = 0;
+            m_par ^= 1u;
+        }
+    };
+    // The two producer roles sit on different warps, and on different ones in the two warpgroups of a CTA: warp w of
+    // every CTA issues from scheduler w % 4, so with two CTAs per SM each scheduler carries two roles (one thread
+    // doing both for all four warpgroups of an SM loaded one scheduler 20-40 % above the other three).
+    const bool tma_role = lane == 0 && wq == ((2u * wg) & 3u), mma_role = lane == 0 && wq == ((2u * wg + 1u) & 3u);
+    if (tma_role && U) {
+        for (uint32_t k = 0; k < NS && k < U; ++k) issue_tma();
+    }
+    if (mma_role && U) {
+        for (uint32_t k = 0; k + 1 < NT && k < U; ++k) issue_mma();
+    }
+    uint4* accs = reinterpret_cast<uint4*>(smb + L::accs_off) + threadIdx.x;
+    RoundAcc<F, D, NPTS, true, true> acc;
+    acc.init(accs);
+    uint32_t q = 0;
+    for (uint32_t tk = 0; tk < my_tiles; ++tk) {
+        const uint64_t j = (first + (uint64_t)tk * tstride) * 128 + r;
+        for (int p = 0; p < n_products; ++p) {
+            Fe m[NPTS - 1];
+#pragma unroll 1
+            for (int f = 0; f < D; ++f) {
+                Fe lo, hi;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ts = q & (NT - 1);
+                    if (mma_role && q + NT - 1 < U) issue_mma();
+                    mbar_wait_u32(b_mma + ts * 8, (q >> LOG_NT) & 1u);
+                    tc_fence_after();
+                    uint32_t c[32];
+                    tmem_ld32(tmem + ts * 32u + ((wq * 32u) << 16), c);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_u32(b_empty + ts * 8);
+                    if (tma_role && q + NS < U) issue_tma();  // stage q % NS: its MMAs have completed
+                    ++q;
+                    Fe& dst = h ? hi : lo;
+                    dst = tc_fold_finish<F>(c);
+                    st_fe(outp[p * D + f], h ? j + half : j, dst);
+                }
+                acc.factor(f, lo, hi, m);
+            }
+        }
+    }
+    acc.finish(out);
+    wg_sync(wg);  // nobody of this warpgroup still waits on a barrier
+    if (r == 0) {
+#pragma unroll
+        for (int b = 0; b < NS + 2 * NT; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_full + b * 8) : "memory");
+    }
+}
+
+template <int NPTS>
+struct TailSmemTc {  // the persistent kernel may start with the evaluation pass, which stages through STAGE_BYTES
+    static constexpr int bytes = TcRoundSmem<NPTS>::bytes > STAGE_BYTES ? TcRoundSmem<NPTS>::bytes : STAGE_BYTES;
+};
+// Shapes the tensor-core round pass is instantiated for (products of >= 2 factors, at most 4 points: the parked
+// accumulators of more points leave no room for the operand stages of two CTAs per SM).
+constexpr bool tc_shape(int kind, int D, int npts) { return kind == KIND_PROD && D >= 2 && npts <= 4; }
+struct ScArgsTc {
+    ScArgs s;
+    TcFoldMats mats;
+};
+template <class F, int KIND, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK, 2) k_sc_fold_eval_tc(const __grid_constant__ ScArgsTc a) {
+    typedef TcRoundSmem<NPTS> L;
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_sm + L::tmem_off);
+    for (uint32_t i = threadIdx.x; i < 2048 / 16; i += BLOCK)
+        reinterpret_cast<uint4*>(tc_sm + L::mats_off)[i] = reinterpret_cast<const uint4*>(&a.mats)[i];
+    fence_proxy_async();
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, TcCfg<NPTS>::tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    Fe out[NPTS - 1];
+    round_pass_tc<F, D, NPTS>(a.s.in, a.s.out, a.s.n_products, a.s.n_out, tc_sm, tmem, out);
+    finish_round<F, NPTS - 1>(out, a.s.fin);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, TcCfg<NPTS>::tmem_cols);
+}
+#endif  // __CUDACC__
+
+}  // namespace zkb

@@ -317,6 +317,11 @@ struct zkb_ctx {
     bool use_shm = false;
     RoundInterpolator interp[MAXPTS + 1];
     FixedMulBuilder fmb;
+    // tensor-core folds (tcfold.cuh): on for the throughput-bound rounds of products of >= 2 factors; ZKB200_NO_TC=1 keeps
+    // every fold on the CUDA cores
+    TcMatsBuilder tcm;
+    Fe* d_cpow8 = nullptr;
+    bool tc_enabled = true;
     // persistent round kernel
     TailMailbox* mb = nullptr;   // mapped pinned host memory
     TailRelay* d_relay = nullptr;
@@ -528,6 +533,13 @@ int32_t collect(zkb_ctx* c, int npts, bool sharded, const FinishArgs& f, Fe* out
     return ZKB_OK;
 }
 
+int sc_occ(zkb_ctx* c, int fused, int kind, int D, int npts);
+// Tensor-core folds for a round pass whose smallest output tables have n_out_min entries: throughput-bound sizes only
+// (a tile is 128 quad positions; below 2^16 entries the TMA -> MMA -> TMEM pipeline is latency, not bandwidth).
+constexpr uint64_t TC_MIN_N_OUT = 1ull << 16;
+bool tc_round_ok(zkb_ctx* c, int kind, int D, int npts, uint64_t n_out_min, int fused) {
+    return c->tc_enabled && tc_shape(kind, D, npts) && n_out_min >= TC_MIN_N_OUT && ((n_out_min >> 1) & 127u) == 0 && sc_occ(c, fused, kind, D, npts) > 0;
+}
 int sc_occ(zkb_ctx* c, int fused, int kind, int D, int npts) {
     char key[64];
     snprintf(key, sizeof key, "%d/%d/%d/%d", fused, kind, D, npts);
@@ -737,10 +749,16 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
     Fe co[MAXPTS];
     const int colen = ip.interpolate(sp->last_evals, co);
     const Fe claim = uni_evaluate(c->H, co, colen, r);
-    const int grid = grid_for(c, n_out / 2, sc_occ(c, 1, sp->kind, sp->kD, sp->npts));
+    const bool tc = tc_round_ok(c, sp->kind, sp->kD, sp->npts, n_out, 3);
+    const int grid = grid_for(c, n_out / 2, sc_occ(c, tc ? 3 : 1, sp->kind, sp->kD, sp->npts));
     ZK_TRY(prep_finish(c, grid, sp->npts - 1, sp->sharded, &a.fin));
     prof_begin(c, ZKB_K_SC_FOLD_EVAL, 96.0 * (double)sp->sel.size() * (double)n_out);
-    if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
+    if (tc) {
+        ScArgsTc at;
+        at.s = a;
+        c->tcm.make(c->H, r, &at.mats);
+        if (!c->K->sc_fold_eval_tc(sp->kind, sp->kD, sp->npts, at, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval_tc: shape not instantiated");
+    } else if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
     ZK_TRY(check_launch(c, "k_sc_fold_eval"));
     if (sp->state == 0) sp->state = 1;
     sp->cur_n = n_out;
@@ -955,8 +973,14 @@ struct RoundDriver {
         const bool big = sp->cur_n > MID_N;
         if (big && stop_n < MID_N) stop_n = MID_N;
         a.stop_n = stop_n;
+        // tensor-core folds when every round of this launch is throughput-bound (its last round writes stop_n entries)
+        const bool tc = big && !first_eval && stop_n >= MID_N && tc_round_ok(c, sp->kind, sp->kD, sp->npts, stop_n, 4);
+        if (tc) {
+            a.cpow8 = c->d_cpow8;
+            c->tcm.make(c->H, r, &a.mats0);
+        }
         const uint64_t quads = first_eval ? sp->cur_n / 2 : (sp->cur_n / 4 ? sp->cur_n / 4 : 1);
-        const int grid = grid_for(c, quads, sc_occ(c, 2, sp->kind, sp->kD, sp->npts));
+        const int grid = grid_for(c, quads, sc_occ(c, tc ? 4 : 2, sp->kind, sp->kD, sp->npts));
         ZK_TRY(ensure_partials(c, (size_t)grid * MAXPTS));
         a.partials = c->d_partials;
         ZK_CUDA(c, cudaMemsetAsync(&c->d_relay->seq, 0, 2 * sizeof(unsigned int), c->stream));
@@ -969,7 +993,7 @@ struct RoundDriver {
         }
         prof_begin(c, big ? ZKB_K_SC_TAIL : ZKB_K_SC_TAIL_MID, 96.0 * (double)sp->sel.size() * (double)(sp->cur_n - (stop_n ? stop_n : 1)) +
                                          (first_eval ? 32.0 * (double)sp->sel.size() * (double)sp->cur_n : 0.0));
-        int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, a, grid, c->stream);
+        int e = c->K->sc_tail(sp->kind, sp->kD, sp->npts, tc, a, grid, c->stream);
         if (e < 0) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_tail: shape not instantiated");
         if (e != 0) {
             c->last_error = std::string("k_sc_tail launch: ") + cudaGetErrorString((cudaError_t)e);
@@ -1837,6 +1861,10 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
     cudaMemset(c->d_relay, 0, sizeof(TailRelay));
     for (int n = 2; n <= MAXPTS; ++n) c->interp[n].init(c->H, n);
     c->fmb.init(c->H);
+    c->tcm.init(c->H);
+    if (cudaMalloc((void**)&c->d_cpow8, sizeof(Fe) * 33) != cudaSuccess) return ZKB_ERR_CUDA;
+    if (cudaMemcpy(c->d_cpow8, c->tcm.c, sizeof(Fe) * 33, cudaMemcpyHostToDevice) != cudaSuccess) return ZKB_ERR_CUDA;
+    c->tc_enabled = getenv("ZKB200_NO_TC") == nullptr;
     // Under Nsight Compute every launch is made synchronous, so a kernel that waits for the host's next
     // challenge can never be answered: profile with one launch per round (the same round_pass code).
     extern char** environ;
@@ -1941,6 +1969,7 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     cudaFreeHost((void*)c->mb);
     if (c->dt_rounds) cudaFreeHost(c->dt_rounds);
     cudaFree(c->d_relay);
+    cudaFree(c->d_cpow8);
     cudaStreamDestroy(c->stream);
     delete c;
     return ZKB_OK;
