@@ -77,11 +77,17 @@ int main(int argc, char** argv) {
         a.fin.partials = partials;
         a.fin.ticket = ticket;
         a.fin.result = result;
+#if defined(KB_TC) && KB_D == 2
+        auto kern = k_sc_eval_tc<FT, NPTS>;
+        constexpr int ESM = TCG_SMEM;
+#else
         auto kern = k_sc_eval<FT, KIND_PROD, D, NPTS>;
         constexpr int ESM = STAGE_BYTES;
+#endif
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ESM));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, ESM));
+        if (getenv("KB_OCC_EVAL")) occ = atoi(getenv("KB_OCC_EVAL"));
         const int grid = sms * occ;
         float best = 1e30f;
         for (int r = 0; r < reps + 1; ++r) {

@@ -39,6 +39,18 @@ bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaSt
     return false;
 }
 #define ZKB_TC_CASES(X) X(KIND_PROD, 2, 3) X(KIND_PROD, 2, 4) X(KIND_PROD, 3, 4)
+bool l_sc_eval_tc(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
+#define X(NP) \
+    if (kind == KIND_PROD && D == 2 && npts == NP) { \
+        static bool once = (cudaFuncSetAttribute(k_sc_eval_tc<FT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCG_SMEM), true); \
+        (void)once; \
+        k_sc_eval_tc<FT, NP><<<grid, BLOCK, TCG_SMEM, s>>>(a); \
+        return true; \
+    }
+    X(3) X(4) X(5)
+#undef X
+    return false;
+}
 bool l_sc_fold_eval_tc(int kind, int D, int npts, const ScArgsTc& a, int grid, cudaStream_t s) {
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
@@ -202,7 +214,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_eval_tc, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

@@ -13,6 +13,8 @@ struct FieldKernels {
     // composed-sumcheck kernels; kind/D/npts select the instantiation. Return false if unsupported.
     bool (*sc_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
     bool (*sc_fold_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
+    // round 0 of a product of two factors as a Gram matrix on the tensor cores (tcfold.cuh); one CTA per SM
+    bool (*sc_eval_tc)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
     // the same round with the folds on the tensor cores (tcfold.cuh); false if the shape is not instantiated
     bool (*sc_fold_eval_tc)(int kind, int D, int npts, const ScArgsTc& a, int grid, cudaStream_t s);
     // persistent round kernel (cooperative launch; tc: tensor-core variant, plain launch of a grid the caller sized to be

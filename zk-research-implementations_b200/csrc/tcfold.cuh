@@ -382,6 +382,192 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_fold_eval_tc(const __grid_const
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(tmem, TcCfg<NPTS>::tmem_cols);
 }
+
+// ================================================================================================================
+// Sums of products on the tensor cores (round 0 of a product of two factors).
+//   s(0) = sum_j lo0_j lo1_j,   s(1) = sum_j hi0_j hi1_j,   s(2) = sum_j (2 hi0_j - lo0_j)(2 hi1_j - lo1_j) = 4 s(1) + s(0) - 2 X,
+//   X = sum_j lo0_j hi1_j + hi0_j lo1_j
+// are inner products over the table index j -- a contraction: with the elements written in bytes,
+//   sum_j a_j b_j = sum_{i,k} 2^(8 (i + k)) sum_j a_{j,i} b_{j,k} = sum_{i,k} 2^(8 (i + k)) G[i][k],   G = A^T B  (u8 x u8 -> s32),
+// so one tcgen05.mma stream over the rows j produces the 128 x 128 Gram matrix of the byte columns
+// [lo0 | hi0 | lo1 | hi1] (A and B are the SAME shared-memory tile, both MN-major: 8 rows x 16 bytes of one plane are a
+// core matrix exactly as they lie in HBM), and the CUDA cores do not multiply at all: every 2^15 rows (a column sum of
+// 255^2 per row stays below 2^31) the four needed 32 x 32 blocks are read from TMEM and assembled into the 544-bit
+// integers the lazy accumulators (fr.cuh Wide) already stand for.  Bit-identical to k_sc_eval.
+constexpr int TCG_TILE_BYTES = 8 * 2048;  // 128 rows x 8 pieces (factor, half, plane) of 16 bytes
+constexpr int TCG_NS = 4;                 // operand stages per warpgroup
+constexpr uint32_t TC_IDESC_GRAM = (2u << 4) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int TCG_SMEM = 2 * TCG_NS * TCG_TILE_BYTES + 3 * 32 * 12 * 4 * 2 + 256;  // stages, drain scratch, barriers
+constexpr uint32_t TCG_DRAIN_ROWS = 1u << 15;
+
+// V = sum_k c[k] 2^(8 k) for 32 column sums c[k] < 2^31: 10 limbs
+__device__ __forceinline__ void tcg_assemble(const uint32_t* c, uint32_t* v) {
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint64_t w = (uint64_t)c[4 * k] + ((uint64_t)c[4 * k + 1] << 8) + ((uint64_t)c[4 * k + 2] << 16) + ((uint64_t)c[4 * k + 3] << 24) + carry;
+        v[k] = lo32(w);
+        carry = w >> 32;
+    }
+    v[8] = lo32(carry);
+    v[9] = hi32(carry);
+}
+
+template <class F, int NPTS>
+__global__ void __launch_bounds__(BLOCK, 1) k_sc_eval_tc(const __grid_constant__ ScArgs a) {
+    typedef Field<F> Fd;
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    __shared__ uint32_t s_tmem;
+    __shared__ Fe s_out[2][2];
+    const uint32_t wg = threadIdx.x >> 7, r = threadIdx.x & 127u, wq = (threadIdx.x >> 5) & 3u, lane = threadIdx.x & 31u;
+    if (threadIdx.x < 32) tmem_alloc(&s_tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem + wg * 128u;
+    const uint64_t half = a.n_out >> 1;   // n_out = table size here (k_sc_eval convention)
+    const uint64_t tiles = half >> 7;
+    const uint64_t first = (uint64_t)blockIdx.x * 2 + wg, tstride = (uint64_t)gridDim.x * 2;
+    const uint32_t P = (uint32_t)a.n_products;
+    const uint32_t my_tiles = first < tiles ? (uint32_t)((tiles - first + tstride - 1) / tstride) : 0u;
+    const uint32_t U = my_tiles * P;  // units: one product of one tile
+    const uint32_t st0 = smem_u32(tc_sm) + wg * (TCG_NS * TCG_TILE_BYTES);
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(tc_sm + 2 * TCG_NS * TCG_TILE_BYTES) + wg * (3 * 32 * 12);
+    const uint32_t b_full = smem_u32(tc_sm + 2 * TCG_NS * TCG_TILE_BYTES + 3 * 32 * 12 * 4 * 2) + wg * 128, b_free = b_full + TCG_NS * 8, b_acc = b_free + TCG_NS * 8;
+    if (r == 0) {
+        for (int b = 0; b < 2 * TCG_NS + 1; ++b) mbar_init_u32(b_full + b * 8, 1u);
+        fence_barrier_init();
+    }
+    wg_sync(wg);
+    // lazy sums: s(0) rows in warp 0, s(1) in warp 1, X shared; kept as Wide integers by lane 0 of warps 0 and 1
+    Wide acc_d = Fd::wide_zero(), acc_x = Fd::wide_zero();  // "diagonal" (lo*lo resp. hi*hi) and cross sums of this warp
+    const uint32_t units_per_drain = TCG_DRAIN_ROWS / 128u;
+    uint32_t done = 0;
+    while (done < U) {
+        const uint32_t batch = U - done < units_per_drain ? U - done : units_per_drain;
+        if (r == 0) {  // TMA producer
+            for (uint32_t u = 0; u < batch; ++u) {
+                const uint32_t q = done + u, stage = q % TCG_NS;
+                if (q >= TCG_NS) mbar_wait_u32(b_free + stage * 8, ((q / TCG_NS) & 1u) ^ 1u);  // the MMAs of unit q - NS have read it
+                const uint64_t tile = first + (uint64_t)(q / P) * tstride;
+                const uint32_t p = q % P;
+                const uint32_t dst = st0 + stage * TCG_TILE_BYTES, bar = b_full + stage * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TCG_TILE_BYTES) : "memory");
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const TabRef& tb = a.in[p * 2 + f];
+                    const uint4* g = tb.base + tile * 128;
+#pragma unroll
+                    for (int hp = 0; hp < 4; ++hp) {  // lo plane 0, lo plane 1, hi plane 0, hi plane 1
+                        const uint4* src = g + ((hp & 2) ? half : 0) + ((hp & 1) ? tb.stride : 0);
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (f * 4 + hp) * 2048u), "l"(src), "r"(2048u), "r"(bar) : "memory");
+                    }
+                }
+            }
+        } else if (r == 32) {  // MMA issuer
+            for (uint32_t u = 0; u < batch; ++u) {
+                const uint32_t q = done + u, stage = q % TCG_NS;
+                mbar_wait_u32(b_full + stage * 8, (q / TCG_NS) & 1u);
+                tc_fence_after();
+                const uint32_t t0 = st0 + stage * TCG_TILE_BYTES;
+#pragma unroll
+                for (uint32_t k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t d = umma_desc(t0 + k4 * 512u, 128, 2048);
+                    umma_i8(tmem, d, d, TC_IDESC_GRAM, (u | k4) ? 1u : 0u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_free + stage * 8) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_acc) : "memory");
+        }
+        __syncwarp();
+        // drain: every thread waits for the batch, rows 0..63 (warps 0, 1 of the warpgroup) hold the needed blocks
+        mbar_wait_u32(b_acc, (done / units_per_drain) & 1u);
+        tc_fence_after();
+        if (wq < 2) {
+            uint32_t c[32], v[10];
+            // columns 64..95 = bytes of lo1, 96..127 = bytes of hi1.  Warp 0 (rows = bytes of lo0): lo1 -> s(0), hi1 -> X;
+            // warp 1 (rows = bytes of hi0): hi1 -> s(1), lo1 -> X.
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const uint32_t col = 64u + 32u * ((wq == 0) ? part : 1 - part);  // part 0 = diagonal, part 1 = cross
+                tmem_ld32(tmem + col + ((wq * 32u) << 16), c);
+                tmem_wait_ld();
+                tcg_assemble(c, v);
+                // this lane's term is V 2^(8 lane): shift by 8 (lane % 4) bits inside the limbs, by lane / 4 limbs through the scratch
+                const uint32_t sh = 8u * (lane & 3u);
+                uint32_t w[11];
+                w[0] = v[0] << sh;
+#pragma unroll
+                for (int k = 1; k < 10; ++k) w[k] = sh ? (v[k] << sh) | (v[k - 1] >> (32u - sh)) : v[k];
+                w[10] = sh ? v[9] >> (32u - sh) : 0u;
+                uint32_t* row = scratch + (wq * 32u + lane) * 12u;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) row[k] = w[k];
+                __syncwarp();
+                // column sums: limb L of the total = sum_i w_i[L - i / 4]; lane L < 18 takes limb L, then a serial carry
+                uint64_t colsum = 0;
+                if (lane < 18) {
+                    for (uint32_t i = 0; i < 32; ++i) {
+                        const int k = (int)lane - (int)(i >> 2);
+                        if (k >= 0 && k < 11) colsum += scratch[(wq * 32u + i) * 12u + k];
+                    }
+                }
+                __syncwarp();
+                // carry propagation by shuffles (18 steps), result limb in `lim`
+                uint64_t carry = 0;
+                uint32_t lim = 0;
+                for (uint32_t L = 0; L < 18; ++L) {
+                    const uint64_t cs = __shfl_sync(0xffffffffu, colsum, L) + carry;
+                    if (lane == L) lim = lo32(cs);
+                    carry = cs >> 32;
+                }
+                // lane 0 adds the 18-limb total (limb 17 is zero: < 2^544) into its Wide accumulator
+                Wide& dst = part == 0 ? acc_d : acc_x;
+                uint32_t cc = 0;
+                for (uint32_t L = 0; L < 17; ++L) {
+                    const uint32_t x = __shfl_sync(0xffffffffu, lim, L);
+                    if (lane == 0) {
+                        const uint64_t t = (uint64_t)dst.l[L] + x + cc;
+                        dst.l[L] = lo32(t);
+                        cc = hi32(t);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        tc_fence_before();
+        wg_sync(wg);  // the accumulator has been read: the next batch may overwrite it
+        done += batch;
+    }
+    // s(0), s(1), X of this warpgroup -> CTA totals -> the round's three evaluations
+    Fe out[NPTS];
+#pragma unroll
+    for (int p3 = 0; p3 < NPTS; ++p3) out[p3] = Fd::zero();
+    if (wq < 2 && lane == 0) {
+        s_out[wg][wq == 0 ? 0 : 1] = Fd::reduce_wide(acc_d);
+        // the two cross sums: warp 0's goes through shared memory to be added to warp 1's
+    }
+    __shared__ Fe s_cross[2][2];
+    if (wq < 2 && lane == 0) s_cross[wg][wq] = Fd::reduce_wide(acc_x);
+    __syncthreads();
+    if (r == 0) {
+        const Fe s0 = s_out[wg][0], s1 = s_out[wg][1], x = Fd::add(s_cross[wg][0], s_cross[wg][1]);
+        // s(t) = c0 + c1 t + c2 t^2 with c0 = s(0), c2 = sum d0 d1 = s(0) + s(1) - X: forward differences
+        // s(t + 1) - s(t) = (s(1) - s(0)) + 2 t c2
+        const Fe two_c2 = Fd::dbl(Fd::sub(Fd::add(s0, s1), x));
+        Fe delta = Fd::sub(s1, s0);
+        out[0] = s0;
+#pragma unroll
+        for (int t = 1; t < NPTS; ++t) {
+            out[t] = Fd::add(out[t - 1], delta);
+            delta = Fd::add(delta, two_c2);
+        }
+    }
+    finish_round<F, NPTS>(out, a.fin);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(s_tmem, 256);
+}
 #endif  // __CUDACC__
 
 }  // namespace zkb

@@ -610,10 +610,14 @@ int32_t sp_round_evals(zkb_ctx* c, SumPolyState* sp, Fe* evals) {
     a.n_tables = (int)sp->sel.size();
     a.n_products = sp->kP;
     a.n_out = sp->cur_n;
-    const int grid = grid_for(c, sp->cur_n / 2, sc_occ(c, 0, sp->kind, sp->kD, sp->npts));
+    // products of two factors, throughput-bound sizes: the sums of products are a Gram matrix on the tensor cores
+    const bool tc = c->tc_enabled && sp->kind == KIND_PROD && sp->kD == 2 && sp->cur_n >= (1ull << 17) && ((sp->cur_n >> 1) & 127u) == 0;
+    const int grid = tc ? grid_for(c, sp->cur_n / 2, 1) : grid_for(c, sp->cur_n / 2, sc_occ(c, 0, sp->kind, sp->kD, sp->npts));
     ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
     prof_begin(c, ZKB_K_SC_EVAL, 32.0 * (double)sp->sel.size() * (double)sp->cur_n);
-    if (!c->K->sc_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_eval: shape not instantiated");
+    if (tc) {
+        if (!c->K->sc_eval_tc(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_eval_tc: shape not instantiated");
+    } else if (!c->K->sc_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_eval: shape not instantiated");
     ZK_TRY(check_launch(c, "k_sc_eval"));
     ZK_TRY(collect(c, sp->npts, sp->sharded, a.fin, evals));
     for (int i = 0; i < sp->npts; ++i) sp->last_evals[i] = evals[i];
