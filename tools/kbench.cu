@@ -80,6 +80,9 @@ int main(int argc, char** argv) {
 #if defined(KB_TC) && KB_D == 2
         auto kern = k_sc_eval_tc<FT, NPTS>;
         constexpr int ESM = TCG_SMEM;
+#elif defined(KB_TC) && KB_D == 3
+        auto kern = k_sc_eval_gram<FT, D, NPTS>;
+        constexpr int ESM = TcGramEvalSmem<NPTS>::bytes;
 #else
         auto kern = k_sc_eval<FT, KIND_PROD, D, NPTS>;
         constexpr int ESM = STAGE_BYTES;
@@ -136,7 +139,7 @@ int main(int argc, char** argv) {
         atc.s = a;
         tc_fold_mats<FT>(r, &atc.mats);
         auto kern = k_sc_fold_eval_tc<FT, KIND_PROD, D, NPTS>;
-        constexpr int SM = TcRoundSmem<NPTS>::bytes;
+        constexpr int SM = TcFoldEvalCfg<D, NPTS>::smem;
 #define a atc
 #else
         auto kern = k_sc_fold_eval<FT, KIND_PROD, D, NPTS>;

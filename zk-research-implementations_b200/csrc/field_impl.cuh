@@ -49,12 +49,19 @@ bool l_sc_eval_tc(int kind, int D, int npts, const ScArgs& a, int grid, cudaStre
     }
     X(3) X(4) X(5)
 #undef X
+    if (kind == KIND_PROD && D == 3 && npts == 4) {
+        constexpr int SM = TcGramEvalSmem<4>::bytes;
+        static bool once = (cudaFuncSetAttribute(k_sc_eval_gram<FT, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true);
+        (void)once;
+        k_sc_eval_gram<FT, 3, 4><<<grid, BLOCK, SM, s>>>(a);
+        return true;
+    }
     return false;
 }
 bool l_sc_fold_eval_tc(int kind, int D, int npts, const ScArgsTc& a, int grid, cudaStream_t s) {
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        constexpr int SM = TcRoundSmem<NP>::bytes; \
+        constexpr int SM = TcFoldEvalCfg<DD, NP>::smem; \
         static bool once = (cudaFuncSetAttribute(k_sc_fold_eval_tc<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
         (void)once; \
         k_sc_fold_eval_tc<FT, K, DD, NP><<<grid, BLOCK, SM, s>>>(a); \
@@ -106,13 +113,14 @@ int l_sc_small(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s) {
 }
 int l_sc_occupancy(int fused, int kind, int D, int npts) {
     int nb = 0;
+    if (fused == 5) return kind == KIND_PROD && D == 2 && npts <= 5 ? 1 : (kind == KIND_PROD && D == 3 && npts == 4 ? 2 : 0);  // k_sc_eval_tc / _gram
     if (fused >= 3) {
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that allocates tensor memory; two CTAs
         // of 128 columns each are co-resident (measured: 2 x 148 CTAs run in the time of one wave), so the count
         // follows from shared memory and registers (<= 128 by __launch_bounds__(BLOCK, 2)) alone
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        const int sm = fused == 3 ? TcRoundSmem<NP>::bytes : TailSmemTc<NP>::bytes; \
+        const int sm = fused == 3 ? TcFoldEvalCfg<DD, NP>::smem : TailSmemTc<NP>::bytes; \
         return 2 * (sm + 1024) + 2048 <= 227 * 1024 ? 2 : 1; \
     }
         ZKB_TC_CASES(X)

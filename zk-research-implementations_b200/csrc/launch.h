@@ -13,7 +13,7 @@ struct FieldKernels {
     // composed-sumcheck kernels; kind/D/npts select the instantiation. Return false if unsupported.
     bool (*sc_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
     bool (*sc_fold_eval)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
-    // round 0 of a product of two factors as a Gram matrix on the tensor cores (tcfold.cuh); one CTA per SM
+    // round 0 of a product of two or three factors with the sums of products as a Gram matrix on the tensor cores (tcfold.cuh)
     bool (*sc_eval_tc)(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s);
     // the same round with the folds on the tensor cores (tcfold.cuh); false if the shape is not instantiated
     bool (*sc_fold_eval_tc)(int kind, int D, int npts, const ScArgsTc& a, int grid, cudaStream_t s);
@@ -23,7 +23,7 @@ struct FieldKernels {
     // single-CTA shared-memory kernel for small tables; returns a cudaError_t, or -1 if not instantiated
     int (*sc_small)(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s);
     // resident CTAs per SM for that instantiation (0 = unsupported); fused: 0 = k_sc_eval, 1 = k_sc_fold_eval, 2 = k_sc_tail,
-    // 3 = k_sc_fold_eval_tc, 4 = k_sc_tail<TC>
+    // 3 = k_sc_fold_eval_tc, 4 = k_sc_tail<TC>, 5 = k_sc_eval_tc / k_sc_eval_gram
     int (*sc_occupancy)(int fused, int kind, int D, int npts);
     void (*fold_tables)(const FoldTablesArgs& a, int grid, cudaStream_t s);
     void (*final_bind)(const FoldTablesArgs& a, Fe* out, volatile unsigned int* flag, unsigned int seq, cudaStream_t s);

@@ -362,26 +362,6 @@ struct ScArgsTc {
     ScArgs s;
     TcFoldMats mats;
 };
-template <class F, int KIND, int D, int NPTS>
-__global__ void __launch_bounds__(BLOCK, 2) k_sc_fold_eval_tc(const __grid_constant__ ScArgsTc a) {
-    typedef TcRoundSmem<NPTS> L;
-    extern __shared__ __align__(128) uint8_t tc_sm[];
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_sm + L::tmem_off);
-    for (uint32_t i = threadIdx.x; i < 2048 / 16; i += BLOCK)
-        reinterpret_cast<uint4*>(tc_sm + L::mats_off)[i] = reinterpret_cast<const uint4*>(&a.mats)[i];
-    fence_proxy_async();
-    if (threadIdx.x < 32) tmem_alloc(tmem_slot, TcCfg<NPTS>::tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    Fe out[NPTS - 1];
-    round_pass_tc<F, D, NPTS>(a.s.in, a.s.out, a.s.n_products, a.s.n_out, tc_sm, tmem, out);
-    finish_round<F, NPTS - 1>(out, a.s.fin);
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem, TcCfg<NPTS>::tmem_cols);
-}
 
 // ================================================================================================================
 // Sums of products on the tensor cores (round 0 of a product of two factors).
@@ -567,6 +547,407 @@ __global__ void __launch_bounds__(BLOCK, 1) k_sc_eval_tc(const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(s_tmem, 256);
+}
+
+// ================================================================================================================
+// Products of >= 3 factors: the sums of products of EVERY round go to the tensor cores the same way.  Per pair
+// position the CUDA cores still multiply the first D - 1 factors (full Montgomery products: the only multiplier work
+// left), m_k = prod_{f < D-1} (lo_f + t_k d_f) at the round's points t_k; the last factor enters linearly,
+//   s(t_k) = sum_j m_k,j ((1 - t_k) lo_j + t_k hi_j) = (1 - t_k) G(m_k, lo) + t_k G(m_k, hi),
+// and the inner products G are blocks of the Gram matrix [m_0 | .. | m_{K-1}]^T [lo | hi] of byte columns: the threads
+// of a warpgroup write their K + 2 values into a shared-memory tile (row = pair position, MN-major pieces of 128 rows x
+// 16 bytes), one thread issues four tcgen05.mma (128 rows) that accumulate into a 128 x 64 s32 tile in TMEM, and every
+// 2^15 rows warp k turns rows 32 k .. 32 k + 31 of the accumulator into two 544-bit integers (fr.cuh Wide).
+constexpr uint32_t TC_IDESC_GRAM64 = (2u << 4) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// rows 32 wq .. 32 wq + 31 (this warp) x 32 columns starting at `col` of a Gram accumulator -> sum_i,k C[i][k] 2^(8 (i + k)),
+// added by lane 0 into the 17-word integer at dst (shared memory).  scratch: 32 x 12 words of this warp.
+__device__ __forceinline__ void tcg_block_add(uint32_t taddr, uint32_t* scratch, uint32_t lane, uint32_t* dst) {
+    uint32_t c[32], v[10];
+    tmem_ld32(taddr, c);
+    tmem_wait_ld();
+    tcg_assemble(c, v);
+    // this lane's term is V 2^(8 lane): 8 (lane % 4) bits inside the limbs, lane / 4 limbs through the scratch rows
+    const uint32_t sh = 8u * (lane & 3u);
+    uint32_t* row = scratch + lane * 12u;
+    row[0] = v[0] << sh;
+#pragma unroll
+    for (int k = 1; k < 10; ++k) row[k] = sh ? (v[k] << sh) | (v[k - 1] >> (32u - sh)) : v[k];
+    row[10] = sh ? v[9] >> (32u - sh) : 0u;
+    __syncwarp();
+    uint64_t colsum = 0;  // limb L of the total = sum_i row_i[L - i / 4]
+    if (lane < 18) {
+        for (uint32_t i = 0; i < 32; ++i) {
+            const int k = (int)lane - (int)(i >> 2);
+            if (k >= 0 && k < 11) colsum += scratch[i * 12u + k];
+        }
+    }
+    __syncwarp();
+    uint64_t carry = 0;
+    uint32_t lim = 0;
+    for (uint32_t L = 0; L < 18; ++L) {
+        const uint64_t cs = __shfl_sync(0xffffffffu, colsum, L) + carry;
+        if (lane == L) lim = lo32(cs);
+        carry = cs >> 32;
+    }
+    uint32_t cc = 0;
+    for (uint32_t L = 0; L < 17; ++L) {
+        const uint32_t x = __shfl_sync(0xffffffffu, lim, L);
+        if (lane == 0) {
+            const uint64_t t = (uint64_t)dst[L] + x + cc;
+            dst[L] = lo32(t);
+            cc = hi32(t);
+        }
+    }
+    __syncwarp();
+}
+
+template <class F, int K>
+struct GramAcc {
+    typedef Field<F> Fd;
+    static constexpr int A_PIECES = 2 * K, PIECES = 2 * K + 4;
+    static constexpr int tile_bytes = PIECES * 2048;
+    static constexpr int sums_words = K * 2 * 17, scratch_words = K * 32 * 12;
+    static constexpr int bytes_per_wg = tile_bytes + (sums_words + scratch_words) * 4 + 64;
+    static_assert(K >= 2 && K <= 4, "the A operand spans 8 pieces from its base; 128 accumulator rows");
+    uint32_t tile, b_full, b_free, tmem, r, wq, lane, rows, pushes;
+    uint32_t *sums, *scratch;
+    bool mma_role;
+    __device__ __forceinline__ void init(uint8_t* base_wg, uint32_t tmem_cols, uint32_t wg_, uint32_t mma_warp) {
+        r = threadIdx.x & 127u;
+        wq = (threadIdx.x >> 5) & 3u;
+        lane = threadIdx.x & 31u;
+        tile = smem_u32(base_wg);
+        sums = reinterpret_cast<uint32_t*>(base_wg + tile_bytes);
+        scratch = sums + sums_words;
+        b_full = smem_u32(base_wg + tile_bytes + (sums_words + scratch_words) * 4);
+        b_free = b_full + 8;
+        tmem = tmem_cols;
+        mma_role = lane == 0 && wq == mma_warp;
+        rows = pushes = 0;
+        for (uint32_t i = r; i < (uint32_t)sums_words; i += 128) sums[i] = 0;
+        if (r == 0) {
+            mbar_init_u32(b_full, 128u);
+            mbar_init_u32(b_free, 1u);
+            fence_barrier_init();
+        }
+        wg_sync(wg_);
+    }
+    __device__ __forceinline__ void put(uint32_t piece, const Fe& v) {
+        const uint32_t a0 = tile + piece * 2048u + r * 16u;
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(v.l[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + 2048u), "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7]) : "memory");
+    }
+    // the 128 threads of the warpgroup together: one row each
+    __device__ __forceinline__ void push(const Fe* m, const Fe& lo, const Fe& hi, uint32_t wg_) {
+        if (pushes) mbar_wait_u32(b_free, (pushes - 1u) & 1u);  // the MMAs of the previous push have read the tile
+#pragma unroll
+        for (int k = 0; k < K; ++k) put(2 * k, m[k]);
+        put(A_PIECES, lo);
+        put(A_PIECES + 2, hi);
+        fence_proxy_async();
+        mbar_arrive_u32(b_full);
+        if (mma_role) {
+            mbar_wait_u32(b_full, pushes & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k4 = 0; k4 < 4; ++k4)
+                umma_i8(tmem, umma_desc(tile + k4 * 512u, 128, 2048), umma_desc(tile + A_PIECES * 2048u + k4 * 512u, 128, 2048), TC_IDESC_GRAM64,
+                        (rows | k4) ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_free) : "memory");
+        }
+        rows += 128u;
+        ++pushes;
+        if (rows == TCG_DRAIN_ROWS) drain(wg_);
+    }
+    __device__ __forceinline__ void drain(uint32_t wg_) {
+        if (!rows) return;
+        mbar_wait_u32(b_free, (pushes - 1u) & 1u);  // the commit of the last push covers every MMA before it
+        tc_fence_after();
+        if (wq < (uint32_t)K) {
+            tcg_block_add(tmem + ((wq * 32u) << 16), scratch + wq * (32 * 12), lane, sums + (wq * 2) * 17);
+            tcg_block_add(tmem + 32u + ((wq * 32u) << 16), scratch + wq * (32 * 12), lane, sums + (wq * 2 + 1) * 17);
+        }
+        tc_fence_before();
+        wg_sync(wg_);
+        rows = 0;
+    }
+    // out[k] = (1 - t_k) G(m_k, lo) + t_k G(m_k, hi) in lane 0 of warp k of this warpgroup, zero elsewhere; t_k = first_t
+    // for k = 0 and k + skip afterwards (skip = 1: the points 0, 2, 3, .. of a round whose s(1) comes from the claim)
+    __device__ __forceinline__ void finish(Fe* out, int skip, uint32_t wg_) {
+        drain(wg_);
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = Fd::zero();
+        if (wq < (uint32_t)K && lane == 0) {
+            Wide wl, wh;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                wl.l[i] = sums[(wq * 2) * 17 + i];
+                wh.l[i] = sums[(wq * 2 + 1) * 17 + i];
+            }
+            const Fe gl = Fd::reduce_wide(wl), gh = Fd::reduce_wide(wh), d = Fd::sub(gh, gl);
+            Fe v = gl;
+            const uint32_t t = wq == 0 ? 0u : wq + (uint32_t)skip;
+            for (uint32_t i = 0; i < t; ++i) v = Fd::add(v, d);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if ((uint32_t)k == wq) out[k] = v;
+        }
+        wg_sync(wg_);
+        if (r == 0) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_full) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_free) : "memory");
+        }
+    }
+};
+
+// ---- fold rounds of products of >= 3 factors: round_pass_tc with the sums through GramAcc ----
+template <int D, int NPTS>
+struct TcGramRoundSmem {
+    static constexpr int NS = 3, NT = 2;
+    static constexpr int stage_bytes = 2 * NS * TC_UNIT_BYTES;
+    static constexpr int mats_off = stage_bytes;
+    static constexpr int bars_off = mats_off + 2048;
+    static constexpr int bars_per_wg = (NS + 2 * NT) * 8;
+    static constexpr int tmem_off = bars_off + 2 * bars_per_wg;
+    static constexpr int gram_off = bars_off + 256;
+    static constexpr int gram_per_wg = (GramAcc<Bn254Fr, NPTS - 1>::bytes_per_wg + 127) / 128 * 128;
+    static constexpr int bytes = gram_off + 2 * gram_per_wg;
+    static constexpr int tmem_cols = 256;  // per CTA: per warpgroup 2 x 32 fold columns + 64 Gram columns
+};
+template <class F, int D, int NPTS>
+__device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products, uint64_t n_out,
+                                                   uint8_t* smb, uint32_t tmem_cta, Fe* out) {
+    static_assert(BLOCK == 256 && D >= 3, "two warpgroups per CTA");
+    typedef Field<F> Fd;
+    typedef TcGramRoundSmem<D, NPTS> L;
+    typedef Slots<NPTS, true> S;
+    constexpr int NS = L::NS, NT = L::NT, LOG_NT = 1, K = NPTS - 1;
+    const uint32_t wg = threadIdx.x >> 7, r = threadIdx.x & 127u, wq = (threadIdx.x >> 5) & 3u, lane = threadIdx.x & 31u;
+    const uint64_t half = n_out >> 1;
+    const uint64_t tiles = half >> 7;
+    const uint64_t first = (uint64_t)blockIdx.x * 2 + wg, tstride = (uint64_t)gridDim.x * 2;
+    const uint32_t upt = 2u * (uint32_t)n_products * D;
+    const uint32_t my_tiles = first < tiles ? (uint32_t)((tiles - first + tstride - 1) / tstride) : 0u;
+    const uint32_t U = my_tiles * upt;
+    const uint32_t st0 = smem_u32(smb) + wg * (NS * TC_UNIT_BYTES);
+    const uint32_t mats = smem_u32(smb + L::mats_off);
+    const uint32_t b_full = smem_u32(smb + L::bars_off) + wg * L::bars_per_wg, b_mma = b_full + NS * 8, b_empty = b_mma + NT * 8;
+    const uint32_t tmem = tmem_cta + wg * 128u;
+    if (r == 0) {
+#pragma unroll
+        for (int b = 0; b < NS + 2 * NT; ++b) mbar_init_u32(b_full + b * 8, b < NS + NT ? 1u : 4u);
+        fence_barrier_init();
+    }
+    const bool tma_role = lane == 0 && wq == ((2u * wg) & 3u), mma_role = lane == 0 && wq == ((2u * wg + 1u) & 3u);
+    GramAcc<F, K> gram;
+    gram.init(smb + L::gram_off + wg * L::gram_per_wg, tmem + 64u, wg, (2u * wg + 2u) & 3u);  // (its wg_sync publishes the barriers too)
+    uint64_t t_tile = first;
+    uint32_t t_u = 0, t_stage = 0, m_q = 0, m_stage = 0, m_par = 0;
+    auto issue_tma = [&]() {
+        const TabRef& tb = in[t_u >> 1];
+        const uint4* g0 = tb.base + t_tile * 128 + ((t_u & 1u) ? half : 0);
+        const uint4* g1 = g0 + tb.stride;
+        const uint32_t dst = st0 + t_stage * TC_UNIT_BYTES, bar = b_full + t_stage * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TC_UNIT_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g0), "r"(2048u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2048u), "l"(g1), "r"(2048u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 4096u), "l"(g0 + n_out), "r"(2048u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 6144u), "l"(g1 + n_out), "r"(2048u), "r"(bar) : "memory");
+        if (++t_u == upt) {
+            t_u = 0;
+            t_tile += tstride;
+        }
+        t_stage = t_stage + 1 == NS ? 0u : t_stage + 1;
+    };
+    auto issue_mma = [&]() {
+        const uint32_t ts = m_q & (NT - 1);
+        mbar_wait_u32(b_full + m_stage * 8, m_par);
+        if (m_q >= NT) mbar_wait_u32(b_empty + ts * 8, ((m_q >> LOG_NT) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem + ts * 32u, a0 = st0 + m_stage * TC_UNIT_BYTES;
+        umma_i8(d, umma_desc(a0, 2048, 128), umma_desc(mats, 512, 128), TC_IDESC_U8_M128_N32, 0u);
+        umma_i8(d, umma_desc(a0 + TC_TILE_BYTES, 2048, 128), umma_desc(mats + 1024, 512, 128), TC_IDESC_U8_M128_N32, 1u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_mma + ts * 8) : "memory");
+        ++m_q;
+        if (++m_stage == NS) {
+            m_stage = 0;
+            m_par ^= 1u;
+        }
+    };
+    if (tma_role && U) {
+        for (uint32_t k = 0; k < NS && k < U; ++k) issue_tma();
+    }
+    if (mma_role && U) {
+        for (uint32_t k = 0; k + 1 < NT && k < U; ++k) issue_mma();
+    }
+    uint32_t q = 0;
+    for (uint32_t tk = 0; tk < my_tiles; ++tk) {
+        const uint64_t j = (first + (uint64_t)tk * tstride) * 128 + r;
+        for (int p = 0; p < n_products; ++p) {
+            Fe m[K], lo, hi;
+#pragma unroll 1
+            for (int f = 0; f < D; ++f) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ts = q & (NT - 1);
+                    if (mma_role && q + NT - 1 < U) issue_mma();
+                    mbar_wait_u32(b_mma + ts * 8, (q >> LOG_NT) & 1u);
+                    tc_fence_after();
+                    uint32_t c[32];
+                    tmem_ld32(tmem + ts * 32u + ((wq * 32u) << 16), c);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_u32(b_empty + ts * 8);
+                    if (tma_role && q + NS < U) issue_tma();
+                    ++q;
+                    Fe& dst = h ? hi : lo;
+                    dst = tc_fold_finish<F>(c);
+                    st_fe(outp[p * D + f], h ? j + half : j, dst);
+                }
+                if (f < D - 1) {  // partial products of the first D - 1 factors at the points 0, 2, 3, ..
+                    Fe cur = lo;
+                    const Fe d = Fd::sub(hi, lo);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (k == 1) cur = Fd::add(hi, d);
+                        else if (k > 1) cur = Fd::add(cur, d);
+                        if (f == 0) m[k] = cur;
+                        else m[k] = Fd::mul(m[k], cur);
+                    }
+                }
+            }
+            gram.push(m, lo, hi, wg);
+        }
+    }
+    gram.finish(out, 1, wg);
+    if (r == 0) {
+#pragma unroll
+        for (int b = 0; b < NS + 2 * NT; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_full + b * 8) : "memory");
+    }
+}
+
+// ---- round 0 of a product of 3 factors: all four points.  q(t) = (lo0 + t d0)(lo1 + t d1) is a quadratic in t, so three
+// full products (t = 0, 1, infinity) give it at every point by second differences; the third factor enters through the
+// Gram accumulator.  Reads as in eval_pass (a private cp.async slot per thread), tiles of 128 pair positions per warpgroup.
+template <int NPTS>
+struct TcGramEvalSmem {
+    static constexpr int NBUF = 2;
+    static constexpr int stage_bytes = NBUF * 4 * BLOCK * 16;
+    static constexpr int gram_off = stage_bytes;
+    static constexpr int gram_per_wg = (GramAcc<Bn254Fr, NPTS>::bytes_per_wg + 127) / 128 * 128;
+    static constexpr int bytes = gram_off + 2 * gram_per_wg;
+    static constexpr int tmem_cols = 128;  // per CTA: 64 Gram columns per warpgroup
+};
+template <class F, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK, 2) k_sc_eval_gram(const __grid_constant__ ScArgs a) {
+    static_assert(D == 3 && NPTS == 4 && BLOCK == 256, "product of three factors");
+    typedef Field<F> Fd;
+    typedef TcGramEvalSmem<NPTS> L;
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t wg = threadIdx.x >> 7, r = threadIdx.x & 127u;
+    if (threadIdx.x < 32) tmem_alloc(&s_tmem, L::tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint64_t half = a.n_out >> 1;  // n_out = table size (k_sc_eval convention)
+    const uint64_t tiles = half >> 7;
+    const uint64_t first = (uint64_t)blockIdx.x * 2 + wg, tstride = (uint64_t)gridDim.x * 2;
+    const uint32_t my_tiles = first < tiles ? (uint32_t)((tiles - first + tstride - 1) / tstride) : 0u;
+    const int T = a.n_products * D;
+    GramAcc<F, NPTS> gram;
+    gram.init(tc_sm + L::gram_off + wg * L::gram_per_wg, s_tmem + wg * 64u, wg, wg);
+    uint4* my = reinterpret_cast<uint4*>(tc_sm) + threadIdx.x;
+    // flattened prefetch sequence: (tile, table)
+    uint32_t p_tile = 0;
+    int pt = 0, pbuf = 0, cbuf = 0;
+    auto issue = [&]() {
+        if (p_tile < my_tiles) {
+            const TabRef& t = a.in[pt];
+            const uint64_t pj = (first + (uint64_t)p_tile * tstride) * 128 + r;
+            uint4* dst = my + (size_t)pbuf * 4 * BLOCK;
+            cp_async16(dst, t.base + pj);
+            cp_async16(dst + BLOCK, t.base + t.stride + pj);
+            cp_async16(dst + 2 * BLOCK, t.base + pj + half);
+            cp_async16(dst + 3 * BLOCK, t.base + t.stride + pj + half);
+        }
+        cp_async_commit();
+        pbuf = (pbuf + 1) & (L::NBUF - 1);
+        if (++pt == T) {
+            pt = 0;
+            ++p_tile;
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < L::NBUF; ++k) issue();
+    auto take = [&](Fe& lo, Fe& hi) {
+        cp_async_wait<L::NBUF - 1>();
+        const uint4* src = my + (size_t)cbuf * 4 * BLOCK;
+        lo = fe_from_smem(src, src + BLOCK);
+        hi = fe_from_smem(src + 2 * BLOCK, src + 3 * BLOCK);
+        cbuf = (cbuf + 1) & (L::NBUF - 1);
+        issue();
+    };
+    for (uint32_t tk = 0; tk < my_tiles; ++tk) {
+        for (int p = 0; p < a.n_products; ++p) {
+            Fe m[NPTS];
+            {
+                Fe lo0, hi0, lo1, hi1;
+                take(lo0, hi0);
+                take(lo1, hi1);
+                m[0] = Fd::mul(lo0, lo1);
+                m[1] = Fd::mul(hi0, hi1);
+                Fe e = Fd::mul(Fd::sub(hi0, lo0), Fd::sub(hi1, lo1));  // q(infinity)
+                e = Fd::dbl(e);                                          // the constant second difference
+                Fe dd = Fd::add(Fd::sub(m[1], m[0]), e);                 // q(2) - q(1)
+                m[2] = Fd::add(m[1], dd);
+                dd = Fd::add(dd, e);
+                m[3] = Fd::add(m[2], dd);
+            }
+            Fe lo2, hi2;
+            take(lo2, hi2);
+            gram.push(m, lo2, hi2, wg);
+        }
+    }
+    Fe out[NPTS];
+    gram.finish(out, 0, wg);
+    cp_async_wait<0>();
+    finish_round<F, NPTS>(out, a.fin);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(s_tmem, L::tmem_cols);
+}
+
+// ---- one round as one launch: folds on the tensor cores; for >= 3 factors the sums of products too ----
+template <int D, int NPTS>
+struct TcFoldEvalCfg {
+    static constexpr bool gram = D >= 3;
+    static constexpr int smem = gram ? TcGramRoundSmem<D, NPTS>::bytes : TcRoundSmem<NPTS>::bytes;
+    static constexpr int tmem_cols = gram ? TcGramRoundSmem<D, NPTS>::tmem_cols : TcCfg<NPTS>::tmem_cols;
+    static constexpr int tmem_off = gram ? TcGramRoundSmem<D, NPTS>::tmem_off : TcRoundSmem<NPTS>::tmem_off;
+    static constexpr int mats_off = gram ? TcGramRoundSmem<D, NPTS>::mats_off : TcRoundSmem<NPTS>::mats_off;
+};
+template <class F, int KIND, int D, int NPTS>
+__global__ void __launch_bounds__(BLOCK, 2) k_sc_fold_eval_tc(const __grid_constant__ ScArgsTc a) {
+    typedef TcFoldEvalCfg<D, NPTS> L;
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_sm + L::tmem_off);
+    for (uint32_t i = threadIdx.x; i < 2048 / 16; i += BLOCK)
+        reinterpret_cast<uint4*>(tc_sm + L::mats_off)[i] = reinterpret_cast<const uint4*>(&a.mats)[i];
+    fence_proxy_async();
+    if (threadIdx.x < 32) tmem_alloc(tmem_slot, L::tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    Fe out[NPTS - 1];
+    if constexpr (L::gram) round_pass_tc_gram<F, D, NPTS>(a.s.in, a.s.out, a.s.n_products, a.s.n_out, tc_sm, tmem, out);
+    else round_pass_tc<F, D, NPTS>(a.s.in, a.s.out, a.s.n_products, a.s.n_out, tc_sm, tmem, out);
+    finish_round<F, NPTS - 1>(out, a.s.fin);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, L::tmem_cols);
 }
 #endif  // __CUDACC__
 

@@ -611,8 +611,9 @@ int32_t sp_round_evals(zkb_ctx* c, SumPolyState* sp, Fe* evals) {
     a.n_products = sp->kP;
     a.n_out = sp->cur_n;
     // products of two factors, throughput-bound sizes: the sums of products are a Gram matrix on the tensor cores
-    const bool tc = c->tc_enabled && sp->kind == KIND_PROD && sp->kD == 2 && sp->cur_n >= (1ull << 17) && ((sp->cur_n >> 1) & 127u) == 0;
-    const int grid = tc ? grid_for(c, sp->cur_n / 2, 1) : grid_for(c, sp->cur_n / 2, sc_occ(c, 0, sp->kind, sp->kD, sp->npts));
+    const int tc_occ = c->tc_enabled && sp->cur_n >= (1ull << 17) && ((sp->cur_n >> 1) & 127u) == 0 ? sc_occ(c, 5, sp->kind, sp->kD, sp->npts) : 0;
+    const bool tc = tc_occ > 0;
+    const int grid = grid_for(c, sp->cur_n / 2, tc ? tc_occ : sc_occ(c, 0, sp->kind, sp->kD, sp->npts));
     ZK_TRY(prep_finish(c, grid, sp->npts, sp->sharded, &a.fin));
     prof_begin(c, ZKB_K_SC_EVAL, 32.0 * (double)sp->sel.size() * (double)sp->cur_n);
     if (tc) {
