@@ -157,6 +157,11 @@ void l_multifold(int k, const MultiFoldArgs& a, int grid, cudaStream_t s) {
     else if (k == 2) k_multifold<FT, 2><<<grid, BLOCK, 0, s>>>(a);
     else k_multifold<FT, 1><<<grid, BLOCK, 0, s>>>(a);
 }
+void l_multifold_tc(const MultiFoldTcArgs& a, int grid, cudaStream_t s) {
+    static bool once = (cudaFuncSetAttribute(k_multifold_tc<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCM_SMEM), true);
+    (void)once;
+    k_multifold_tc<FT><<<grid, TCM_THREADS, TCM_SMEM, s>>>(a);
+}
 void l_fold(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const FixedMul& rt, int grid, cudaStream_t s) {
     k_fold<FT><<<grid, BLOCK, 0, s>>>(in, out, n_out, shift, rt);
 }
@@ -222,7 +227,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_eval_tc, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_eval_tc, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_multifold_tc, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

@@ -415,6 +415,14 @@ struct TcMatsBuilder {
         }
         c[32] = H.one();
     }
+    // one B operand for an arbitrary weight w (Montgomery form): byte n of w 2^(8 k + 32) mod p
+    void make_weight(const HostField& H, const Fe& w, uint8_t* out1024) const {
+        for (int k = 0; k < 32; ++k) {
+            const Fe t = H.mul(w, c[k]);
+            uint8_t* m = out1024 + (k / 16) * 512 + k % 16;
+            for (int n = 0; n < 32; ++n) m[n * 16] = (uint8_t)(t.l[n / 4] >> (8 * (n % 4)));
+        }
+    }
     void make(const HostField& H, const Fe& r, TcFoldMats* out) const {
         const Fe omr = H.sub(c[32], r);
         for (int k = 0; k < 32; ++k) {

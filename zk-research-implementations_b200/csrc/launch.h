@@ -28,6 +28,7 @@ struct FieldKernels {
     void (*fold_tables)(const FoldTablesArgs& a, int grid, cudaStream_t s);
     void (*final_bind)(const FoldTablesArgs& a, Fe* out, volatile unsigned int* flag, unsigned int seq, cudaStream_t s);
     void (*multifold)(int k, const MultiFoldArgs& a, int grid, cudaStream_t s);
+    void (*multifold_tc)(const MultiFoldTcArgs& a, int grid, cudaStream_t s);  // three variables per pass on the tensor cores
     void (*fold)(TabRef in, TabRef out, uint64_t n_out, uint32_t shift, const FixedMul& rt, int grid, cudaStream_t s);
     void (*aos_to_planar)(const void* aos, TabRef out, uint64_t n, uint64_t first, uint64_t stride, int conv, int grid, cudaStream_t s);
     void (*planar_to_aos)(TabRef in, void* aos, uint64_t n, int conv, int grid, cudaStream_t s);

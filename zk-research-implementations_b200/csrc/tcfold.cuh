@@ -77,6 +77,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* c) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+template <class F>
+__device__ __forceinline__ Fe tc_mont_row(uint32_t* s);
+__device__ __forceinline__ void tcg_assemble(const uint32_t* c, uint32_t* v);
 // 32 column sums (byte weights 2^(8 n), each < 2^22) -> the canonical residue S 2^-32 mod p
 template <class F>
 __device__ __forceinline__ Fe tc_fold_finish(const uint32_t* c) {
@@ -94,6 +97,11 @@ __device__ __forceinline__ Fe tc_fold_finish(const uint32_t* c) {
 #pragma unroll
     for (int k = 2; k < 8; ++k) s[k] = addc_cc(lo[k], hi[k - 1]);
     s[8] = addc(hi[7], 0u);
+    return tc_mont_row<F>(s);
+}
+// (S + m p) >> 32 for a 9-limb S < 2^31 p, then one conditional subtraction: the canonical residue S 2^-32 mod p
+template <class F>
+__device__ __forceinline__ Fe tc_mont_row(uint32_t* s) {
     // one Montgomery row: (S + m p) >> 32 < p (1 + 2^-18).  m p is taken as even-limb products chained onto S and
     // odd-limb products computed stand-alone (no carry, full-rate), merged by the final addition.
     const uint32_t m = mul_lo(s[0], F::INV);
@@ -917,6 +925,91 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval_gram(const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(s_tmem, L::tmem_cols);
+}
+
+// ---- evaluate / multi_partial_evaluate: three variables per pass on the tensor cores.  The bound entry is a LINEAR
+// combination of 8 input entries, out[v] = sum_i w_i in[v + i n_out] with w_i = prod_l (bit_l(i) ? r_l : 1 - r_l), i.e.
+// eight u8 x u8 -> s32 products accumulated in one 128 x 32 tile (column sums < 2^24, S < 2^16 p: still one Montgomery
+// row).  The CUDA-core version does 7 fixed-multiplicand folds per output and is multiplier-bound at 0.40 of HBM.
+struct MultiFoldTcArgs {
+    TabRef in, out;
+    uint64_t n_out;
+    uint8_t mats[8][1024];  // B operand of weight w_i: byte n of w_i 2^(8 k + 32) mod p at (k / 16) * 512 + n * 16 + k % 16
+};
+constexpr int TCM_NS = 3, TCM_UNIT = 16 * 2048, TCM_THREADS = 128;
+constexpr int TCM_SMEM = TCM_NS * TCM_UNIT + 8192 + 128;
+template <class F>
+__global__ void __launch_bounds__(TCM_THREADS, 2) k_multifold_tc(const __grid_constant__ MultiFoldTcArgs a) {
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    const uint32_t r = threadIdx.x, wq = r >> 5, lane = r & 31u;
+    const uint32_t st0 = smem_u32(tc_sm), mats = st0 + TCM_NS * TCM_UNIT;
+    const uint32_t b_full = mats + 8192, b_mma = b_full + TCM_NS * 8, b_empty = b_mma + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_sm + TCM_NS * TCM_UNIT + 8192 + (TCM_NS + 4) * 8);
+    for (uint32_t i = r; i < 8192 / 16; i += TCM_THREADS) reinterpret_cast<uint4*>(tc_sm + TCM_NS * TCM_UNIT)[i] = reinterpret_cast<const uint4*>(a.mats)[i];
+    if (r == 0) {
+        for (int b = 0; b < TCM_NS + 4; ++b) mbar_init_u32(b_full + b * 8, b < TCM_NS + 2 ? 1u : 4u);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    if (r < 32) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint64_t tiles = a.n_out >> 7;
+    const uint32_t U = blockIdx.x < tiles ? (uint32_t)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    const bool tma_role = r == 0, mma_role = r == 32;
+    uint32_t t_q = 0, t_stage = 0, m_q = 0, m_stage = 0, m_par = 0;
+    auto issue_tma = [&]() {
+        const uint64_t j0 = ((uint64_t)blockIdx.x + (uint64_t)t_q * gridDim.x) * 128;
+        const uint32_t dst = st0 + t_stage * TCM_UNIT, bar = b_full + t_stage * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TCM_UNIT) : "memory");
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+            const uint4* g0 = a.in.base + (uint64_t)i * a.n_out + j0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + i * 4096u), "l"(g0), "r"(2048u), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + i * 4096u + 2048u), "l"(g0 + a.in.stride), "r"(2048u), "r"(bar) : "memory");
+        }
+        ++t_q;
+        t_stage = t_stage + 1 == TCM_NS ? 0u : t_stage + 1;
+    };
+    auto issue_mma = [&]() {
+        const uint32_t ts = m_q & 1u;
+        mbar_wait_u32(b_full + m_stage * 8, m_par);
+        if (m_q >= 2) mbar_wait_u32(b_empty + ts * 8, ((m_q >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem + ts * 32u, a0 = st0 + m_stage * TCM_UNIT;
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) umma_i8(d, umma_desc(a0 + i * 4096u, 2048, 128), umma_desc(mats + i * 1024u, 512, 128), TC_IDESC_U8_M128_N32, i ? 1u : 0u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_mma + ts * 8) : "memory");
+        ++m_q;
+        if (++m_stage == TCM_NS) {
+            m_stage = 0;
+            m_par ^= 1u;
+        }
+    };
+    if (tma_role) {
+        for (uint32_t k = 0; k < TCM_NS && k < U; ++k) issue_tma();
+    }
+    if (mma_role && U) issue_mma();
+    for (uint32_t q = 0; q < U; ++q) {
+        const uint32_t ts = q & 1u;
+        if (mma_role && q + 1 < U) issue_mma();
+        mbar_wait_u32(b_mma + ts * 8, (q >> 1) & 1u);
+        tc_fence_after();
+        uint32_t c[32], s[10];
+        tmem_ld32(tmem + ts * 32u + ((wq * 32u) << 16), c);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(b_empty + ts * 8);
+        if (tma_role && q + TCM_NS < U) issue_tma();
+        tcg_assemble(c, s);
+        st_fe(a.out, ((uint64_t)blockIdx.x + (uint64_t)q * gridDim.x) * 128 + r, tc_mont_row<F>(s));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (r < 32) tmem_dealloc(tmem, 64);
 }
 
 // ---- one round as one launch: folds on the tensor cores; for >= 3 factors the sums of products too ----

@@ -1253,6 +1253,28 @@ int32_t multi_fold(zkb_ctx* c, const Table& src, const Fe* rs, uint32_t k, Table
     ZK_TRY(alloc_table(c, src.n >> first, &w));
     for (uint32_t i = 0; i < k;) {
         const uint32_t kk = k - i >= 3 ? 3 : k - i;
+        if (kk == 3 && c->tc_enabled && n >= (1ull << 17)) {
+            // the bound entry is a linear combination of 8 inputs with weights prod_l (bit_l ? r_l : 1 - r_l): tensor cores
+            auto ta = std::make_unique<MultiFoldTcArgs>();
+            ta->in = i == 0 ? src.ref() : w.ref();
+            ta->out = w.ref();
+            ta->n_out = n >> 3;
+            Fe omr[3];
+            for (int l = 0; l < 3; ++l) omr[l] = c->H.sub(c->tcm.c[32], rs[i + l]);
+            for (int x = 0; x < 8; ++x) {
+                Fe wgt = (x & 4) ? rs[i] : omr[0];
+                wgt = c->H.mul(wgt, (x & 2) ? rs[i + 1] : omr[1]);
+                wgt = c->H.mul(wgt, (x & 1) ? rs[i + 2] : omr[2]);
+                c->tcm.make_weight(c->H, wgt, ta->mats[x]);
+            }
+            prof_begin(c, ZKB_K_FOLD_TABLES, 32.0 * (double)n + 32.0 * (double)(n >> 3));
+            const uint64_t tiles = (n >> 3) >> 7;
+            c->K->multifold_tc(*ta, (int)(tiles < (uint64_t)(2 * c->sm_count) ? tiles : (uint64_t)(2 * c->sm_count)), c->stream);
+            ZK_TRY(check_launch(c, "k_multifold_tc"));
+            n >>= 3;
+            i += 3;
+            continue;
+        }
         MultiFoldArgs fa;
         std::memset(&fa, 0, sizeof fa);
         fa.in = i == 0 ? src.ref() : w.ref();
