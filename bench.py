@@ -20,6 +20,8 @@ Further legs in the same JSON line (each with its own clocks record and parity s
   target       north-star target shape: ONE product of 3 MLEs at 2^28 variables on one B200
   plain_n20    BASELINE configs[0]: sum_check::prove + verify at n = 20, core vs whole-table Keccak, CPU port beside it
   gkr, gkr_uniform   BASELINE configs[2] (reference-legal tree / as written with general wiring)
+  kzg          SURVEY 8f-3: the input-layer commitment (multilinear KZG over BLS12-381 G1) at 2^20 inputs
+  ntt, merkle  SURVEY 8f-4: fft/src/fft.rs at 2^24 coefficients, merkle_tree/src/merkle_tree.rs at depth 20
   config3      BASELINE configs[3] (N >= 2): SumPoly of 2 products x 3 factors at 28 variables sharded over the GPUs
   mle_sweep    BASELINE configs[4]: partial_evaluate / evaluate from 2^16 to 2^30 entries
 `--impl reference` times the CPU port alone (rank 0 only) on the same workload description.
@@ -839,6 +841,91 @@ def gkr_uniform_leg(z, args):
                         "extension (the reference's fixed wiring cannot express uniform layers); pinned input; KZG excluded" % (L, lg, lg)}
 
 
+def kzg_leg(z, args):
+    """SURVEY 8f-3: the input-layer commitment of gkr_protocol::prove (gkr_protocol.rs:92-118) at the configs[2] input size:
+    multilinear KZG over BLS12-381 G1 (pcs/src/kzg_pcs/kzg.rs:17-95), taus as an input.  Host wall clock around the C-ABI
+    calls, table resident; parity is the test suite's job (tests/test_gpu_kzg.py against oracle/kzg_ref.py, which is pinned to
+    the reference's known answers)."""
+    import random
+
+    n = args.kzg_log_inputs
+    fid = 2
+    p = z.engine.MODULI[fid]
+    rng = random.Random(11)
+    out = {"workload": f"multilinear KZG of a random {n}-variable MLE over BLS12-381 (G1 side): setup from the taus, commit, open, get_proof "
+                       "(one quotient commitment per variable)", "n_vars": n}
+    with z.Context(fid, 0, 1) as ctx:
+        m = z.MultilinearPoly.generate(ctx, SEED + 9, 0, n)
+        taus = [rng.randrange(p) for _ in range(n)]
+        t0 = time.perf_counter()
+        k = z.kzg.KZG(m, taus)
+        t1 = time.perf_counter()
+        c1 = k.commit(m)  # first call builds the fixed-base tables
+        t2 = time.perf_counter()
+        c2 = k.commit(m)
+        t3 = time.perf_counter()
+        r = [rng.randrange(p) for _ in range(n)]
+        v = k.open(r, m)
+        t4 = time.perf_counter()
+        pr = k.get_proof(v, r, m)
+        t5 = time.perf_counter()
+        out.update({"setup_ms": 1e3 * (t1 - t0), "commit_first_ms": 1e3 * (t2 - t1), "commit_ms": 1e3 * (t3 - t2), "open_ms": 1e3 * (t4 - t3),
+                    "get_proof_ms": 1e3 * (t5 - t4), "msm_points_per_s": (1 << n) / (t3 - t2), "commit_deterministic": c1 == c2,
+                    "quotients": len(pr)})
+        k.free()
+        m.free()
+    return out
+
+
+def fft_merkle_leg(z, args):
+    """the NTT of fft/src/fft.rs and the Keccak Merkle tree of merkle_tree/src/merkle_tree.rs on device-resident data
+    (host wall clock around the C-ABI calls after a warm-up call; parity against the oracle is tests/test_gpu_fft_merkle.py, here
+    the round trip interpolate(evaluate(x)) == x at the timed size).  No CPU figure: the oracle restatement is pure Python."""
+    out = {}
+    with z.Context(0, 0, 1) as ctx:
+        n = args.ntt_log_n
+        t = z.MultilinearPoly.generate(ctx, SEED + 12, 0, n)
+        z.fft.ntt(t).free()
+        ctx.sync()
+        t0 = time.perf_counter()
+        ev = z.fft.ntt(t)
+        ctx.sync()
+        t1 = time.perf_counter()
+        back = z.fft.ntt(ev, inverse=True)
+        ctx.sync()
+        t2 = time.perf_counter()
+        ok = (back - t).sum_halves() == [0, 0]
+        passes = 1 + max(0, -(-(n - 9) // 6))
+        out["ntt"] = {"workload": f"fft_evaluate / fft_interpolate of 2^{n} BN254 Fr coefficients, device-resident", "log_n": n,
+                      "evaluate_ms": 1e3 * (t1 - t0), "interpolate_ms": 1e3 * (t2 - t1), "passes": passes,
+                      "GBps_streamed": passes * 64.0 * (1 << n) / (t1 - t0) / 1e9, "butterflies_per_s": (n << (n - 1)) / (t1 - t0),
+                      "roundtrip_is_identity": ok}
+        for m in (t, ev, back):
+            m.free()
+        d = args.merkle_depth
+        import numpy as np
+        rng = np.random.default_rng(3)
+        raw = rng.integers(0, 1 << 62, size=(1 << d, 4), dtype=np.uint64)  # any 248-bit values < p as Montgomery limbs
+        raw[:, 3] &= (1 << 56) - 1
+        L = z.engine.lib()
+        h = z.engine.C.c_uint64()
+
+        def build():
+            z.engine._ck(ctx, L.zkb_merkle_build(ctx.handle, z.engine._p(raw), 1 << d, d, z.engine.C.byref(h)))
+
+        build()
+        L.zkb_merkle_free(ctx.handle, h.value)
+        t0 = time.perf_counter()
+        build()
+        t1 = time.perf_counter()
+        root = np.zeros((1, 4), dtype=np.uint64)
+        z.engine._ck(ctx, L.zkb_merkle_root(ctx.handle, h.value, z.engine._p(root)))
+        L.zkb_merkle_free(ctx.handle, h.value)
+        out["merkle"] = {"workload": f"MerkleTree::new_with_inputs, depth {d}, 2^{d} inputs from host memory (32 MiB H2D included)", "depth": d,
+                         "build_ms": 1e3 * (t1 - t0), "hashes": (2 << d) - 1, "hashes_per_s": ((2 << d) - 1) / (t1 - t0)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -850,6 +937,9 @@ def main():
     ap.add_argument("--gkr-log-inputs", type=int, default=21, help="0 = skip the GKR tree leg")
     ap.add_argument("--gkr-uniform-log-gates", type=int, default=20, help="0 = skip the uniform-layer GKR leg")
     ap.add_argument("--gkr-uniform-layers", type=int, default=16)
+    ap.add_argument("--ntt-log-n", type=int, default=24, help="NTT / Merkle leg (SURVEY 8f-4); 0 = skip")
+    ap.add_argument("--merkle-depth", type=int, default=20)
+    ap.add_argument("--kzg-log-inputs", type=int, default=20, help="input-layer commitment leg (multilinear KZG, BLS12-381); 0 = skip")
     ap.add_argument("--target-n-vars", type=int, default=28, help="north-star target leg (1 x 3 factors); 0 = skip")
     ap.add_argument("--config3-n-vars", type=int, default=28, help="configs[3] leg at N >= 2 (2 x 3 factors, global variables); 0 = skip")
     ap.add_argument("--mle-sweep-hi", type=int, default=30, help="largest per-GPU log2 size of the configs[4] sweep; 0 = skip")
@@ -883,6 +973,10 @@ def main():
                     line["gkr"] = gkr_leg(b.z, args)
                 if args.gkr_uniform_log_gates > 0:
                     line["gkr_uniform"] = gkr_uniform_leg(b.z, args)
+                if args.kzg_log_inputs > 0:
+                    line["kzg"] = kzg_leg(b.z, args)
+                if args.ntt_log_n > 0:
+                    line.update(fft_merkle_leg(b.z, args))
             print(json.dumps(line))
     if b.sampler:
         b.sampler.stop()

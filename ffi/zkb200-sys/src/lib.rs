@@ -15,6 +15,7 @@ pub type zkb_mle = u64;
 pub type zkb_sp = u64;
 pub type zkb_circ = u64;
 pub type zkb_kzg = u64;
+pub type zkb_merkle = u64;
 
 pub const ZKB_OK: i32 = 0;
 pub const ZKB_ERR_BAD_ARG: i32 = -1;
@@ -120,6 +121,16 @@ extern "C" {
     pub fn zkb_kzg_commit(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, out: *mut u8) -> i32;
     pub fn zkb_kzg_open(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, opening_values: *const u64, n: u32, out: *mut u64) -> i32;
     pub fn zkb_kzg_get_proof(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, opened_value: *const u64, opening_values: *const u64, n: u32, out: *mut u8) -> i32;
+    pub fn zkb_fft_evaluate(ctx: *mut zkb_ctx, coeffs_mont: *const u64, n: u64, evals_mont: *mut u64) -> i32;
+    pub fn zkb_fft_interpolate(ctx: *mut zkb_ctx, evals_mont: *const u64, n: u64, coeffs_mont: *mut u64) -> i32;
+    pub fn zkb_mle_ntt(ctx: *mut zkb_ctx, input: zkb_mle, inverse: i32, out: *mut zkb_mle) -> i32;
+    pub fn zkb_merkle_build(ctx: *mut zkb_ctx, inputs_mont: *const u64, n_inputs: u64, depth: u32, out: *mut zkb_merkle) -> i32;
+    pub fn zkb_merkle_free(ctx: *mut zkb_ctx, t: zkb_merkle) -> i32;
+    pub fn zkb_merkle_root(ctx: *mut zkb_ctx, t: zkb_merkle, out: *mut u64) -> i32;
+    pub fn zkb_merkle_nodes(ctx: *mut zkb_ctx, t: zkb_merkle, level: u32, first: u64, count: u64, out_mont: *mut u64) -> i32;
+    pub fn zkb_merkle_update_leaf(ctx: *mut zkb_ctx, t: zkb_merkle, leaf_id: u64, data: *const u64, is_hash: i32) -> i32;
+    pub fn zkb_merkle_create_proof(ctx: *mut zkb_ctx, t: zkb_merkle, data: *const u64, leaf_id: u64, sibling_hashes: *mut u64, sides: *mut u8) -> i32;
+    pub fn zkb_merkle_verify(ctx: *mut zkb_ctx, t: zkb_merkle, data: *const u64, sibling_hashes: *const u64, sides: *const u8, n: u32, ok: *mut i32) -> i32;
     pub fn zkb_bench_modmul(ctx: *mut zkb_ctx, variant: i32, iters: u32, modmuls_per_s: *mut f64) -> i32;
     pub fn zkb_bench_imad(ctx: *mut zkb_ctx, mode: i32, iters: u32, ops_per_s: *mut f64) -> i32;
 }

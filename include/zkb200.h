@@ -40,6 +40,7 @@ typedef uint64_t zkb_mle;  /* opaque handle of a device-resident MultilinearPoly
 typedef uint64_t zkb_sp;   /* opaque handle of a device-resident SumPoly        */
 typedef uint64_t zkb_circ; /* opaque handle of a device-resident Circuit        */
 typedef uint64_t zkb_kzg;  /* opaque handle of a multilinear-KZG setup (G1 side)   */
+typedef uint64_t zkb_merkle; /* opaque handle of a Keccak Merkle tree on the device */
 
 typedef enum {
     ZKB_OK = 0,
@@ -304,6 +305,38 @@ int32_t zkb_kzg_commit(zkb_ctx* ctx, zkb_kzg k, zkb_mle poly, uint8_t out[96]);
 int32_t zkb_kzg_open(zkb_ctx* ctx, zkb_kzg k, zkb_mle poly, const uint64_t* opening_values, uint32_t n, uint64_t out[4]);
 int32_t zkb_kzg_get_proof(zkb_ctx* ctx, zkb_kzg k, zkb_mle poly, const uint64_t opened_value[4], const uint64_t* opening_values, uint32_t n,
                           uint8_t* out);
+
+/* ------------------------------------------------ NTT: fft/src/fft.rs
+ * zkb_fft_evaluate     fft_evaluate (:31-41): evals[j] = sum_i coeffs[i] w^(i j), w = F::get_root_of_unity(n) (ark-ff: the field's
+ *                      two-adic root squared down to order n), natural order in and out; n not a power of two:
+ *                      ZKB_ERR_NOT_POW2 ("Length must be a power of 2", :34); n above the field's two-adic order (2^28 for
+ *                      BN254 Fr, 2^32 for BLS12-381 Fr, 2 for BN254 Fq): ZKB_ERR_UNSUPPORTED (the reference unwraps None, :38)
+ * zkb_fft_interpolate  fft_interpolate (:43-60): the inverse transform (w^-1, then n^-1); the coefficient vector comes back
+ *                      at full length n (UnivariatePoly::new does not trim)
+ * zkb_mle_ntt          the same transform on a device-resident table (inverse != 0: interpolate) */
+int32_t zkb_fft_evaluate(zkb_ctx* ctx, const uint64_t* coeffs_mont, uint64_t n, uint64_t* evals_mont);
+int32_t zkb_fft_interpolate(zkb_ctx* ctx, const uint64_t* evals_mont, uint64_t n, uint64_t* coeffs_mont);
+int32_t zkb_mle_ntt(zkb_ctx* ctx, zkb_mle in, int32_t inverse, zkb_mle* out);
+
+/* ------------------------------------------------ Keccak Merkle tree: merkle_tree/src/merkle_tree.rs
+ * Nodes are field elements (Montgomery limbs at the ABI); compute_hash(x) = Keccak256(fq_vec_to_bytes([x])) and
+ * hash_pair(l, r) = Keccak256(bytes(l) || bytes(r)), both mapped back with from_le_bytes_mod_order (:201-214).
+ * zkb_merkle_build         MerkleTree::new (:31-50, n_inputs = 0) / new_with_inputs (:52-84): leaves[i] = compute_hash(input_i),
+ *                          the other leaves are zero (not hashed); "Too many inputs for tree depth" -> ZKB_ERR_BAD_ARG
+ * zkb_merkle_root          get_root_hash (:134-136)
+ * zkb_merkle_nodes         `count` nodes of `level` from `first` (level 0 = the leaves, level depth = the root)
+ * zkb_merkle_update_leaf   update_leaf + recompute_path (:86-132); "Invalid leaf ID" -> ZKB_ERR_BAD_ARG
+ * zkb_merkle_create_proof  create_proof (:138-183): depth sibling hashes and their sides (0 = Left, 1 = Right);
+ *                          "Data does not match the leaf hash" / "Invalid leaf ID" -> ZKB_ERR_BAD_ARG
+ * zkb_merkle_verify        verify (:185-199): ok = 1 iff the path hashes to the stored root */
+int32_t zkb_merkle_build(zkb_ctx* ctx, const uint64_t* inputs_mont, uint64_t n_inputs, uint32_t depth, zkb_merkle* out);
+int32_t zkb_merkle_free(zkb_ctx* ctx, zkb_merkle t);
+int32_t zkb_merkle_root(zkb_ctx* ctx, zkb_merkle t, uint64_t out[4]);
+int32_t zkb_merkle_nodes(zkb_ctx* ctx, zkb_merkle t, uint32_t level, uint64_t first, uint64_t count, uint64_t* out_mont);
+int32_t zkb_merkle_update_leaf(zkb_ctx* ctx, zkb_merkle t, uint64_t leaf_id, const uint64_t data[4], int32_t is_hash);
+int32_t zkb_merkle_create_proof(zkb_ctx* ctx, zkb_merkle t, const uint64_t data[4], uint64_t leaf_id, uint64_t* sibling_hashes, uint8_t* sides);
+int32_t zkb_merkle_verify(zkb_ctx* ctx, zkb_merkle t, const uint64_t data[4], const uint64_t* sibling_hashes, const uint8_t* sides, uint32_t n,
+                          int32_t* ok);
 
 /* Device-timed multiplier throughput (fills the IMAD-roofline denominator).
  * variant: 0/1 = IMAD.WIDE multiplier with 1/2 independent chains per thread, 2/3 = 32-bit lo/hi

@@ -217,6 +217,17 @@ void l_bench_mul(int variant, Fe* out, uint32_t iters, int grid, cudaStream_t s)
     else if (variant == 2) k_bench_mul<FT, 1, true><<<grid, BLOCK, 0, s>>>(out, iters, seed);
     else k_bench_mul<FT, 2, true><<<grid, BLOCK, 0, s>>>(out, iters, seed);
 }
+void l_ntt_twiddles(TabRef lo, uint32_t lo_bits, TabRef hi, uint64_t n_hi, const NttPows& pw, int grid, cudaStream_t s) {
+    k_ntt_twiddles<FT><<<grid, BLOCK, 0, s>>>(lo, lo_bits, hi, n_hi, pw);
+}
+void l_ntt_pass(const NttArgs& a, int grid, cudaStream_t s) { k_ntt_pass<FT><<<grid, BLOCK, 0, s>>>(a); }
+void l_merkle_leaves(const Fe* inputs, uint64_t n_inputs, Fe* leaves, uint64_t n_leaves, int grid, cudaStream_t s) {
+    k_merkle_leaves<FT><<<grid, BLOCK, 0, s>>>(inputs, n_inputs, leaves, n_leaves);
+}
+void l_merkle_level(const Fe* prev, Fe* next, uint64_t n_next, int grid, cudaStream_t s) { k_merkle_level<FT><<<grid, BLOCK, 0, s>>>(prev, next, n_next); }
+void l_merkle_path(Fe* tree, uint32_t depth, uint64_t leaf_id, const Fe& data, int is_hash, int mode, Fe* siblings, unsigned int* status, cudaStream_t s) {
+    k_merkle_path<FT><<<1, 32, 0, s>>>(tree, depth, leaf_id, data, is_hash, mode, siblings, status);
+}
 void h_add(const Fe& a, const Fe& b, Fe& r) { r = Field<FT>::add(a, b); }
 void h_sub(const Fe& a, const Fe& b, Fe& r) { r = Field<FT>::sub(a, b); }
 void h_mul(const Fe& a, const Fe& b, Fe& r) { r = Field<FT>::mul(a, b); }
@@ -229,7 +240,7 @@ void h_modulus(Fe& p) {
 const FieldKernels TABLE = {
     FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_eval_tc, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_multifold_tc, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
-    l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
+    l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, l_ntt_twiddles, l_ntt_pass, l_merkle_leaves, l_merkle_level, l_merkle_path, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };
 }  // namespace
 

@@ -1982,6 +1982,8 @@ __global__ void __launch_bounds__(BLOCK) k_gkr_wiring(const GkrWiringArgs a) {
 // Register-resident multiplier throughput (fills the IMAD-roofline number the
 // driver does not measure): each thread runs `iters` dependent products on
 // ILP independent chains.
+#include "ntt_merkle.cuh"
+
 template <class F, int ILP, bool SPLIT>
 __global__ void __launch_bounds__(BLOCK) k_bench_mul(Fe* out, uint32_t iters, Fe seed) {
     Fe x[ILP], y = seed;

@@ -48,6 +48,12 @@ struct FieldKernels {
     void (*gkr_w_wiring)(const GkrWWiringArgs& a, int grid, cudaStream_t s);
     void (*layer_eval_w)(TabRef in, TabRef out, const uint8_t* ops, const uint32_t* in1, const uint32_t* in2, uint64_t n_gates, int grid, cudaStream_t s);
     void (*bench_mul)(int variant, Fe* out, uint32_t iters, int grid, cudaStream_t s);
+    // fft/src/fft.rs and merkle_tree/src/merkle_tree.rs (ntt_merkle.cuh)
+    void (*ntt_twiddles)(TabRef lo, uint32_t lo_bits, TabRef hi, uint64_t n_hi, const NttPows& pw, int grid, cudaStream_t s);
+    void (*ntt_pass)(const NttArgs& a, int grid, cudaStream_t s);
+    void (*merkle_leaves)(const Fe* inputs, uint64_t n_inputs, Fe* leaves, uint64_t n_leaves, int grid, cudaStream_t s);
+    void (*merkle_level)(const Fe* prev, Fe* next, uint64_t n_next, int grid, cudaStream_t s);
+    void (*merkle_path)(Fe* tree, uint32_t depth, uint64_t leaf_id, const Fe& data, int is_hash, int mode, Fe* siblings, unsigned int* status, cudaStream_t s);
     // host-side arithmetic on Montgomery residues (fr.cuh compiled for the host)
     void (*h_add)(const Fe& a, const Fe& b, Fe& r);
     void (*h_sub)(const Fe& a, const Fe& b, Fe& r);

@@ -270,6 +270,12 @@ struct KzgState {
     std::vector<G1Affine*> basis;  // level k: 2^(n_vars - k) points; level 0 = g1 * eq(taus, .)
 };
 
+// Keccak Merkle tree (merkle_tree/src/merkle_tree.rs:24-29): leaves then levels in one device buffer of Montgomery residues
+struct MerkleState {
+    uint32_t depth = 0;
+    Fe* tree = nullptr;
+};
+
 struct zkb_transcript {
     TranscriptImpl impl;
 };
@@ -308,6 +314,7 @@ struct zkb_ctx {
     std::unordered_map<uint64_t, std::unique_ptr<SumPolyState>> sps;
     std::unordered_map<uint64_t, std::unique_ptr<CircuitState>> circs;
     std::unordered_map<uint64_t, std::unique_ptr<KzgState>> kzgs;
+    std::unordered_map<uint64_t, std::unique_ptr<MerkleState>> merkles;
     G1Affine* g1_table = nullptr;  // 32 x 256 multiples of the generator (fixed-base windows), made on first use
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -650,21 +657,26 @@ uint64_t gather_threshold_n(const zkb_ctx* c, const SumPolyState* sp) {
     return 1ull << 14;
 }
 int32_t sp_gather(zkb_ctx* c, SumPolyState* sp) {
+    // ONE all-gather for all tables (the shards are a few KiB by now: the call's latency is what counts): every rank sends
+    // [table][plane][nl] and receives the same block of every rank
     const int T = (int)sp->src.size();
     const uint64_t nl = sp->cur_n, G = (uint64_t)c->world;
-    ZK_TRY(ensure_stage(c, (size_t)(G + 1) * nl * 32));
+    const uint64_t blk = (uint64_t)T * 2 * nl;  // uint4 per rank
+    ZK_TRY(ensure_stage(c, (size_t)(G + 1) * blk * 16));
     uint4* send = (uint4*)c->stage;
-    uint4* recv = send + 2 * nl;
-    sp->gath.resize(T);
+    uint4* recv = send + blk;
     for (int t = 0; t < T; ++t) {
         Table& cur = sp->cur(t);
-        ZK_CUDA(c, cudaMemcpyAsync(send, cur.base, nl * 16, cudaMemcpyDeviceToDevice, c->stream));
-        ZK_CUDA(c, cudaMemcpyAsync(send + nl, cur.base + cur.stride, nl * 16, cudaMemcpyDeviceToDevice, c->stream));
-        ZK_NCCL(c, g_nccl.AllGather(send, recv, (size_t)nl * 32, ncclUint8, c->comm, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(send + (uint64_t)t * 2 * nl, cur.base, nl * 16, cudaMemcpyDeviceToDevice, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(send + (uint64_t)t * 2 * nl + nl, cur.base + cur.stride, nl * 16, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    ZK_NCCL(c, g_nccl.AllGather(send, recv, (size_t)blk * 16, ncclUint8, c->comm, c->stream));
+    sp->gath.resize(T);
+    for (int t = 0; t < T; ++t) {
         Table g;
         ZK_TRY(alloc_table(c, nl * G, &g));
-        TabRef gr{recv, nl};
-        c->K->interleave_shards(gr, 2 * nl, g.ref(), nl, (uint32_t)c->log2world, grid_for(c, nl * G, 8), c->stream);
+        TabRef gr{recv + (uint64_t)t * 2 * nl, nl};
+        c->K->interleave_shards(gr, blk, g.ref(), nl, (uint32_t)c->log2world, grid_for(c, nl * G, 8), c->stream);
         ZK_TRY(check_launch(c, "k_interleave_shards"));
         sp->gath[t] = g;
     }
@@ -1997,6 +2009,7 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     if (c->dt_rounds) cudaFreeHost(c->dt_rounds);
     cudaFree(c->d_relay);
     cudaFree(c->d_cpow8);
+    for (auto& kv : c->merkles) cudaFree(kv.second->tree);
     cudaStreamDestroy(c->stream);
     delete c;
     return ZKB_OK;
@@ -3205,6 +3218,204 @@ int32_t zkb_kzg_get_proof(zkb_ctx* c, zkb_kzg h, zkb_mle poly, const uint64_t op
     cudaFreeAsync(d, c->stream);
     free_table(c, &work);
     free_table(c, &q);
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------ fft/src/fft.rs
+namespace {
+// ark-ff: TWO_ADIC_ROOT_OF_UNITY = GENERATOR^((p - 1) / 2^TWO_ADICITY); get_root_of_unity(n) squares it TWO_ADICITY - log n times.
+// Generators and two-adicities of ark-bn254 0.5.0 Fr (5, 28), Fq (3, 1) and ark-bls12-381 0.5.0 Fr (7, 32).
+int32_t root_of_unity(zkb_ctx* c, int log_n, Fe* omega) {
+    static const uint32_t gen[3] = {5, 3, 7};
+    static const int adicity[3] = {28, 1, 32};
+    const int s = adicity[c->field];
+    if (log_n > s) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "the field has no root of unity of that order");
+    Fe e = c->H.modulus();  // (p - 1) >> s: p is odd, so p - 1 clears bit 0 and the shift drops the s zero bits
+    e.l[0] &= ~1u;
+    for (int k = 0; k < s; ++k) {
+        for (int i = 0; i < 7; ++i) e.l[i] = (e.l[i] >> 1) | (e.l[i + 1] << 31);
+        e.l[7] >>= 1;
+    }
+    const Fe g = c->H.from_u64(gen[c->field]);
+    Fe r = c->H.one();
+    for (int i = 255; i >= 0; --i) {
+        r = c->H.mul(r, r);
+        if ((e.l[i / 32] >> (i % 32)) & 1) r = c->H.mul(r, g);
+    }
+    for (int k = log_n; k < s; ++k) r = c->H.mul(r, r);
+    *omega = r;
+    return ZKB_OK;
+}
+// y[j] = sum_i x_i w^(i j) (inverse: w^-1 and a final n^-1), natural order in and out (fft.rs:6-60)
+int32_t ntt_table(zkb_ctx* c, const Table& src, bool inverse, Table* out) {
+    const uint64_t n = src.n;
+    const int log_n = ilog2_u64(n);
+    Fe omega;
+    ZK_TRY(root_of_unity(c, log_n, &omega));
+    if (n == 1) return multi_fold(c, src, nullptr, 0, out);
+    if (inverse) omega = c->H.inv(omega);
+    NttPows pw;
+    pw.w[0] = omega;
+    for (int i = 1; i < 32; ++i) pw.w[i] = c->H.mul(pw.w[i - 1], pw.w[i - 1]);
+    const uint32_t lo_bits = (uint32_t)(log_n - 1 < 12 ? log_n - 1 : 12);
+    const uint64_t n_hi = (n >> 1) >> lo_bits;
+    Table w_lo, w_hi, dst;
+    ZK_TRY(alloc_table(c, 1ull << lo_bits, &w_lo));
+    ZK_TRY(alloc_table(c, n_hi, &w_hi));
+    ZK_TRY(alloc_table(c, n, &dst));
+    c->K->ntt_twiddles(w_lo.ref(), lo_bits, w_hi.ref(), n_hi, pw, grid_for(c, (1ull << lo_bits) + n_hi, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_ntt_twiddles"));
+    NttArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.in = src.ref();
+    a.data = dst.ref();
+    a.log_n = (uint32_t)log_n;
+    a.w_lo = w_lo.ref();
+    a.w_hi = w_hi.ref();
+    a.lo_bits = lo_bits;
+    a.scale = c->H.inv(c->H.from_u64(n));
+    for (int s0 = 0; s0 < log_n;) {
+        const int g = s0 == 0 ? (log_n < NTT_TILE_LOG ? log_n : NTT_TILE_LOG) : (log_n - s0 < 6 ? log_n - s0 : 6);
+        a.s0 = (uint32_t)s0;
+        a.g = (uint32_t)g;
+        a.do_scale = inverse && s0 + g == log_n;
+        const uint64_t tiles = n >> (s0 == 0 ? g : NTT_TILE_LOG);
+        prof_begin(c, ZKB_K_OTHER, 64.0 * (double)n);
+        c->K->ntt_pass(a, (int)(tiles < (uint64_t)c->sm_count * 8 ? tiles : (uint64_t)c->sm_count * 8), c->stream);
+        ZK_TRY(check_launch(c, "k_ntt_pass"));
+        s0 += g;
+    }
+    free_table(c, &w_lo);
+    free_table(c, &w_hi);
+    *out = dst;
+    return ZKB_OK;
+}
+int32_t fft_host(zkb_ctx* c, const uint64_t* in, uint64_t n, uint64_t* out, bool inverse) {
+    if (!c || !in || !out) return ZKB_ERR_BAD_ARG;
+    if (!is_pow2(n)) ZK_FAIL(c, ZKB_ERR_NOT_POW2, "Length must be a power of 2");
+    Table t, r;
+    ZK_TRY(upload_aos(c, in, n, 0, 1, n, 0, &t));
+    int32_t st = ntt_table(c, t, inverse, &r);
+    free_table(c, &t);
+    ZK_TRY(st);
+    st = download_aos(c, r, out, 0);
+    free_table(c, &r);
+    return st;
+}
+}  // namespace
+int32_t zkb_fft_evaluate(zkb_ctx* c, const uint64_t* coeffs, uint64_t n, uint64_t* evals) { return fft_host(c, coeffs, n, evals, false); }
+int32_t zkb_fft_interpolate(zkb_ctx* c, const uint64_t* evals, uint64_t n, uint64_t* coeffs) { return fft_host(c, evals, n, coeffs, true); }
+int32_t zkb_mle_ntt(zkb_ctx* c, zkb_mle in, int32_t inverse, zkb_mle* out) {
+    Table* t = c ? find_mle(c, in) : nullptr;
+    if (!t || !out) return ZKB_ERR_BAD_ARG;
+    Table r;
+    ZK_TRY(ntt_table(c, *t, inverse != 0, &r));
+    *out = put_mle(c, r);
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------ merkle_tree/src/merkle_tree.rs
+namespace {
+MerkleState* find_merkle(zkb_ctx* c, zkb_merkle h) {
+    if (!c) return nullptr;
+    auto it = c->merkles.find(h);
+    return it == c->merkles.end() ? nullptr : it->second.get();
+}
+// compute_hash / hash_pair on the host (:201-214)
+Fe merkle_hash_host(const HostField& H, const Fe& a, const Fe* b) {
+    Keccak256 k;
+    Fe ca = H.from_mont(a);
+    k.update(reinterpret_cast<const uint8_t*>(ca.l), 32);
+    if (b) {
+        Fe cb = H.from_mont(*b);
+        k.update(reinterpret_cast<const uint8_t*>(cb.l), 32);
+    }
+    uint8_t dg[32];
+    k.finalize_reset(dg);
+    return H.from_le_bytes_mod_order(dg);
+}
+}  // namespace
+int32_t zkb_merkle_build(zkb_ctx* c, const uint64_t* inputs, uint64_t n_inputs, uint32_t depth, zkb_merkle* out) {
+    if (!c || !out || (n_inputs && !inputs)) return ZKB_ERR_BAD_ARG;
+    if (depth == 0 || depth > 32) ZK_FAIL(c, ZKB_ERR_BAD_ARG, "merkle tree depth must be 1..32");
+    const uint64_t n_leaves = 1ull << depth;
+    if (n_inputs > n_leaves) ZK_FAIL(c, ZKB_ERR_BAD_ARG, "Too many inputs for tree depth");
+    auto ms = std::make_unique<MerkleState>();
+    ms->depth = depth;
+    ZK_CUDA(c, cudaMalloc((void**)&ms->tree, sizeof(Fe) * ((2ull << depth) - 1)));
+    Fe* d_in = nullptr;
+    if (n_inputs) {
+        ZK_CUDA(c, cudaMallocAsync((void**)&d_in, sizeof(Fe) * n_inputs, c->stream));
+        ZK_CUDA(c, cudaMemcpyAsync(d_in, inputs, sizeof(Fe) * n_inputs, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->K->merkle_leaves(d_in, n_inputs, ms->tree, n_leaves, grid_for(c, n_leaves, 8), c->stream);
+    ZK_TRY(check_launch(c, "k_merkle_leaves"));
+    for (uint32_t level = 0; level < depth; ++level) {
+        const uint64_t n_next = n_leaves >> (level + 1);
+        c->K->merkle_level(ms->tree + merkle_level_off(depth, level), ms->tree + merkle_level_off(depth, level + 1), n_next, grid_for(c, n_next, 8), c->stream);
+        ZK_TRY(check_launch(c, "k_merkle_level"));
+    }
+    if (d_in) cudaFreeAsync(d_in, c->stream);
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));  // the caller's input buffer is free again
+    const uint64_t h = c->next_handle++;
+    c->merkles[h] = std::move(ms);
+    *out = h;
+    return ZKB_OK;
+}
+int32_t zkb_merkle_free(zkb_ctx* c, zkb_merkle h) {
+    MerkleState* ms = find_merkle(c, h);
+    if (!ms) return ZKB_ERR_BAD_ARG;
+    cudaFree(ms->tree);
+    c->merkles.erase(h);
+    return ZKB_OK;
+}
+int32_t zkb_merkle_nodes(zkb_ctx* c, zkb_merkle h, uint32_t level, uint64_t first, uint64_t count, uint64_t* out) {
+    MerkleState* ms = find_merkle(c, h);
+    if (!ms || !out || level > ms->depth || first + count > (1ull << (ms->depth - level))) return ZKB_ERR_BAD_ARG;
+    ZK_CUDA(c, cudaMemcpyAsync(out, ms->tree + merkle_level_off(ms->depth, level) + first, sizeof(Fe) * count, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ZKB_OK;
+}
+int32_t zkb_merkle_root(zkb_ctx* c, zkb_merkle h, uint64_t out[4]) {
+    MerkleState* ms = find_merkle(c, h);
+    if (!ms || !out) return ZKB_ERR_BAD_ARG;
+    return zkb_merkle_nodes(c, h, ms->depth, 0, 1, out);
+}
+int32_t zkb_merkle_update_leaf(zkb_ctx* c, zkb_merkle h, uint64_t leaf_id, const uint64_t data[4], int32_t is_hash) {
+    MerkleState* ms = find_merkle(c, h);
+    if (!ms || !data) return ZKB_ERR_BAD_ARG;
+    if (leaf_id >= (1ull << ms->depth)) ZK_FAIL(c, ZKB_ERR_BAD_ARG, "Invalid leaf ID");
+    c->K->merkle_path(ms->tree, ms->depth, leaf_id, fe_from_u64x4(data), is_hash, 0, nullptr, nullptr, c->stream);
+    ZK_TRY(check_launch(c, "k_merkle_path"));
+    return ZKB_OK;
+}
+int32_t zkb_merkle_create_proof(zkb_ctx* c, zkb_merkle h, const uint64_t data[4], uint64_t leaf_id, uint64_t* sibling_hashes, uint8_t* sides) {
+    MerkleState* ms = find_merkle(c, h);
+    if (!ms || !data || !sibling_hashes || !sides) return ZKB_ERR_BAD_ARG;
+    if (leaf_id >= (1ull << ms->depth)) ZK_FAIL(c, ZKB_ERR_BAD_ARG, "Invalid leaf ID");
+    Fe* d_sib = c->d_res;  // 64 elements: depth <= 32
+    c->K->merkle_path(ms->tree, ms->depth, leaf_id, fe_from_u64x4(data), 0, 1, d_sib, c->d_ticket, c->stream);
+    ZK_TRY(check_launch(c, "k_merkle_path"));
+    unsigned int status = 0;
+    ZK_CUDA(c, cudaMemcpyAsync(&status, c->d_ticket, sizeof status, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaMemcpyAsync(sibling_hashes, d_sib, sizeof(Fe) * ms->depth, cudaMemcpyDeviceToHost, c->stream));
+    ZK_CUDA(c, cudaMemsetAsync(c->d_ticket, 0, sizeof(unsigned int), c->stream));
+    ZK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (status) ZK_FAIL(c, ZKB_ERR_BAD_ARG, "Data does not match the leaf hash");
+    for (uint32_t level = 0; level < ms->depth; ++level) sides[level] = ((leaf_id >> level) & 1) ? 0 : 1;  // even index: the sibling is on the Right (:160-164)
+    return ZKB_OK;
+}
+int32_t zkb_merkle_verify(zkb_ctx* c, zkb_merkle h, const uint64_t data[4], const uint64_t* sibling_hashes, const uint8_t* sides, uint32_t n, int32_t* ok) {
+    MerkleState* ms = find_merkle(c, h);
+    if (!ms || !data || !ok || (n && (!sibling_hashes || !sides))) return ZKB_ERR_BAD_ARG;
+    uint64_t root[4];
+    ZK_TRY(zkb_merkle_root(c, h, root));
+    Fe cur = merkle_hash_host(c->H, fe_from_u64x4(data), nullptr);
+    for (uint32_t i = 0; i < n; ++i) {
+        const Fe sib = fe_from_u64x4(sibling_hashes + 4 * i);
+        cur = sides[i] == 0 ? merkle_hash_host(c->H, sib, &cur) : merkle_hash_host(c->H, cur, &sib);  // Left: (sibling, current), :190-193
+    }
+    *ok = c->H.eq(cur, fe_from_u64x4(root)) ? 1 : 0;
     return ZKB_OK;
 }
 

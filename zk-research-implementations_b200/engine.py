@@ -135,6 +135,16 @@ def lib() -> C.CDLL:
         "zkb_kzg_commit": (i32, [vp, u64, u64, vp]),
         "zkb_kzg_open": (i32, [vp, u64, u64, u64p, u32, u64p]),
         "zkb_kzg_get_proof": (i32, [vp, u64, u64, u64p, u64p, u32, vp]),
+        "zkb_fft_evaluate": (i32, [vp, u64p, u64, u64p]),
+        "zkb_fft_interpolate": (i32, [vp, u64p, u64, u64p]),
+        "zkb_mle_ntt": (i32, [vp, u64, i32, u64p]),
+        "zkb_merkle_build": (i32, [vp, u64p, u64, u32, u64p]),
+        "zkb_merkle_free": (i32, [vp, u64]),
+        "zkb_merkle_root": (i32, [vp, u64, u64p]),
+        "zkb_merkle_nodes": (i32, [vp, u64, u32, u64, u64, u64p]),
+        "zkb_merkle_update_leaf": (i32, [vp, u64, u64, u64p, i32]),
+        "zkb_merkle_create_proof": (i32, [vp, u64, u64p, u64, u64p, vp]),
+        "zkb_merkle_verify": (i32, [vp, u64, u64p, u64p, vp, u32, i32p]),
         "zkb_bench_modmul": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
         "zkb_bench_imad": (i32, [vp, i32, u32, C.POINTER(C.c_double)]),
     }
