@@ -63,18 +63,20 @@ def macs_per_quad(P: int, D: int) -> int:
     each sum one product of D factors = (D-2) full products + one lazy product.  With the tensor-core path a fold costs one
     Montgomery row, and for >= 3 factors the last (lazy) product of every sum is a Gram-matrix block on the tensor cores."""
     if tc_folds(D):
-        return P * (2 * D * MACS_FOLD_TC + D * ((D - 2) * MACS_FULL + (MACS_LAZY if D == 2 else 0)))
+        if D == 3:  # Gram accumulation: one raw (64-multiply) and two Montgomery partial products per quad, no lazy product
+            return P * (2 * D * MACS_FOLD_TC + MACS_LAZY + 2 * MACS_FULL)
+        return P * (2 * D * MACS_FOLD_TC + D * ((D - 2) * MACS_FULL + MACS_LAZY))
     return P * (2 * D * MACS_FOLD + D * ((D - 2) * MACS_FULL + MACS_LAZY))
 
 
 def macs_per_pair_round0(P: int, D: int) -> int:
     """k_sc_eval: D+1 points of a product of D factors per pair position.  For D = 3 the product of the first two
     factors is a quadratic in t, interpolated from three full products (kernels.cuh RoundAcc::add_product).  Tensor-core
-    path: D = 2 is a pure Gram matrix (no CUDA-core multiply), D = 3 keeps the three full products."""
+    path: D = 2 is a pure Gram matrix (no CUDA-core multiply), D = 3 keeps four raw 64-multiply products."""
     if D == 1:
         return 0
     if tc_folds(D):
-        return 0 if D == 2 else P * 3 * MACS_FULL
+        return 0 if D == 2 else P * 4 * MACS_LAZY  # D = 3: four raw products of the first two factors
     if D == 3:
         return P * (3 * MACS_FULL + 4 * MACS_LAZY)
     return P * (D + 1) * ((D - 2) * MACS_FULL + MACS_LAZY)

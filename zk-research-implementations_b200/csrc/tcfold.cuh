@@ -708,6 +708,124 @@ struct GramAcc {
     }
 };
 
+// GramAcc2: the same accumulator with UNREDUCED products among the A rows.  A raw 512-bit product T = x y of two residues
+// costs 64 wide multiplies instead of the 136 of a Montgomery product; written as 64 byte rows (low half L, high half H,
+// T = L + 2^256 H) it enters the contraction like any other value, and the two missing divisions by R = 2^256 are done once,
+// at the very end: sum_j T_j c_j R^-2 = redc(redc(G(L, c))) + redc(G(H, c)).  The tile is [A: 4 slots of 32 bytes][B: lo, hi]
+// = 24 KiB per warpgroup; GROUPS accumulator tiles (64 columns each) take turns on the same A buffer, the B rows of a
+// push are shared by its groups.  Warp w of the warpgroup owns accumulator rows 32 w .. 32 w + 31 = A slot w.
+template <class F, int GROUPS>
+struct GramAcc2 {
+    typedef Field<F> Fd;
+    static constexpr int tile_bytes = 12 * 2048;
+    static constexpr int sums_words = GROUPS * 4 * 2 * 17;
+    static constexpr int bytes_per_wg = tile_bytes + sums_words * 4 + GROUPS * 4 * 2 * 32 + 64;
+    uint32_t tile, b_full, b_free, tmem, r, wq, lane, rows, steps;
+    uint32_t* sums;
+    Fe* blk;  // [GROUPS][4][2]: the reduced block sums after finish()
+    bool mma_role;
+    __device__ __forceinline__ void init(uint8_t* base_wg, uint32_t tmem_cols, uint32_t wg_, uint32_t mma_warp) {
+        r = threadIdx.x & 127u;
+        wq = (threadIdx.x >> 5) & 3u;
+        lane = threadIdx.x & 31u;
+        tile = smem_u32(base_wg);
+        sums = reinterpret_cast<uint32_t*>(base_wg + tile_bytes);
+        blk = reinterpret_cast<Fe*>(base_wg + tile_bytes + sums_words * 4);
+        b_full = smem_u32(base_wg + tile_bytes + sums_words * 4 + GROUPS * 4 * 2 * 32);
+        b_free = b_full + 8;
+        tmem = tmem_cols;
+        mma_role = lane == 0 && wq == mma_warp;
+        rows = steps = 0;
+        for (uint32_t i = r; i < (uint32_t)sums_words; i += 128) sums[i] = 0;
+        if (r == 0) {
+            mbar_init_u32(b_full, 128u);
+            mbar_init_u32(b_free, 1u);
+            fence_barrier_init();
+        }
+        wg_sync(wg_);
+    }
+    __device__ __forceinline__ void put(uint32_t piece, const uint32_t* v) {
+        const uint32_t a0 = tile + piece * 2048u + r * 16u;
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + 2048u), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+    }
+    // the A buffer (and, for the first group of a push, the B rows) may be written again
+    __device__ __forceinline__ void wait_free() {
+        if (steps) mbar_wait_u32(b_free, (steps - 1u) & 1u);
+    }
+    __device__ __forceinline__ void put_a(uint32_t slot, const Fe& v) { put(2 * slot, v.l); }
+    // the raw product x * y (x, y < 2^256) into slots `slot` (low half) and `slot + 1` (high half)
+    __device__ __forceinline__ void put_raw(uint32_t slot, const Fe& x, const Fe& y) {
+        Wide t = Fd::wide_zero();
+        Fd::mac_wide(t, x, y);
+        put(2 * slot, t.l);
+        put(2 * slot + 2, t.l + 8);
+    }
+    __device__ __forceinline__ void put_b(const Fe& lo, const Fe& hi) {
+        put(8, lo.l);
+        put(10, hi.l);
+    }
+    // every thread of the warpgroup has written its row: accumulate the tile into group g
+    __device__ __forceinline__ void commit(uint32_t g, uint32_t wg_) {
+        fence_proxy_async();
+        mbar_arrive_u32(b_full);
+        if (mma_role) {
+            mbar_wait_u32(b_full, steps & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (uint32_t k4 = 0; k4 < 4; ++k4)
+                umma_i8(tmem + g * 64u, umma_desc(tile + k4 * 512u, 128, 2048), umma_desc(tile + 8u * 2048u + k4 * 512u, 128, 2048), TC_IDESC_GRAM64,
+                        (rows | k4) ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_free) : "memory");
+        }
+        ++steps;
+        if (g == GROUPS - 1) {
+            rows += 128u;
+            if (rows == TCG_DRAIN_ROWS) drain(wg_);
+        }
+    }
+    __device__ __forceinline__ void drain(uint32_t wg_) {
+        if (!rows) return;
+        mbar_wait_u32(b_free, (steps - 1u) & 1u);  // the last commit covers every MMA before it; the tile is free: scratch
+        tc_fence_after();
+        uint32_t* scratch = reinterpret_cast<uint32_t*>(sums) - (tile_bytes / 4) + wq * (32 * 12);  // inside the A buffer
+#pragma unroll
+        for (uint32_t g = 0; g < (uint32_t)GROUPS; ++g) {
+            tcg_block_add(tmem + g * 64u + ((wq * 32u) << 16), scratch, lane, sums + ((g * 4 + wq) * 2) * 17);
+            tcg_block_add(tmem + g * 64u + 32u + ((wq * 32u) << 16), scratch, lane, sums + ((g * 4 + wq) * 2 + 1) * 17);
+        }
+        tc_fence_before();
+        wg_sync(wg_);
+        rows = 0;
+    }
+    // blk[g][w][part] = G(A slot w of group g, part of B) R^-1 mod p, canonical; valid for every thread of the warpgroup
+    __device__ __forceinline__ void finish(uint32_t wg_) {
+        drain(wg_);
+        if (lane < 2u * GROUPS) {
+            const uint32_t g = lane >> 1, part = lane & 1u;
+            Wide w;
+#pragma unroll
+            for (int i = 0; i < 17; ++i) w.l[i] = sums[((g * 4 + wq) * 2 + part) * 17 + i];
+            blk[(g * 4 + wq) * 2 + part] = Fd::reduce_wide(w);
+        }
+        wg_sync(wg_);
+        if (r == 0) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_full) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_free) : "memory");
+        }
+    }
+    // one more division by R (for the low half of a raw product)
+    __device__ __forceinline__ static Fe redc(const Fe& x) {
+        Fe one = Fd::zero();
+        one.l[0] = 1;
+        return Fd::mul(x, one);
+    }
+    // sum_j T_j c_j for the raw product in slots (s, s + 1) of group g against B part `part`, as a Montgomery residue
+    __device__ __forceinline__ Fe raw_sum(uint32_t g, uint32_t s, uint32_t part) const {
+        return Fd::add(redc(blk[(g * 4 + s) * 2 + part]), blk[(g * 4 + s + 1) * 2 + part]);
+    }
+};
+
 // ---- fold rounds of products of >= 3 factors: round_pass_tc with the sums through GramAcc ----
 template <int D, int NPTS>
 struct TcGramRoundSmem {
@@ -718,14 +836,14 @@ struct TcGramRoundSmem {
     static constexpr int bars_per_wg = (NS + 2 * NT) * 8;
     static constexpr int tmem_off = bars_off + 2 * bars_per_wg;
     static constexpr int gram_off = bars_off + 256;
-    static constexpr int gram_per_wg = (GramAcc<Bn254Fr, NPTS - 1>::bytes_per_wg + 127) / 128 * 128;
+    static constexpr int gram_per_wg = (GramAcc2<Bn254Fr, 1>::bytes_per_wg + 127) / 128 * 128;
     static constexpr int bytes = gram_off + 2 * gram_per_wg;
     static constexpr int tmem_cols = 256;  // per CTA: per warpgroup 2 x 32 fold columns + 64 Gram columns
 };
 template <class F, int D, int NPTS>
 __device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products, uint64_t n_out,
                                                    uint8_t* smb, uint32_t tmem_cta, Fe* out) {
-    static_assert(BLOCK == 256 && D >= 3, "two warpgroups per CTA");
+    static_assert(BLOCK == 256 && D == 3 && NPTS == 4, "two warpgroups per CTA; one raw and two reduced partial products fill the 128 accumulator rows");
     typedef Field<F> Fd;
     typedef TcGramRoundSmem<D, NPTS> L;
     typedef Slots<NPTS, true> S;
@@ -747,7 +865,7 @@ __device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in
         fence_barrier_init();
     }
     const bool tma_role = lane == 0 && wq == ((2u * wg) & 3u), mma_role = lane == 0 && wq == ((2u * wg + 1u) & 3u);
-    GramAcc<F, K> gram;
+    GramAcc2<F, 1> gram;
     gram.init(smb + L::gram_off + wg * L::gram_per_wg, tmem + 64u, wg, (2u * wg + 2u) & 3u);  // (its wg_sync publishes the barriers too)
     uint64_t t_tile = first;
     uint32_t t_u = 0, t_stage = 0, m_q = 0, m_stage = 0, m_par = 0;
@@ -792,7 +910,9 @@ __device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in
     for (uint32_t tk = 0; tk < my_tiles; ++tk) {
         const uint64_t j = (first + (uint64_t)tk * tstride) * 128 + r;
         for (int p = 0; p < n_products; ++p) {
-            Fe m[K], lo, hi;
+            // A rows of this position: the RAW product lo0 * lo1 (point 0, slots 0-1) and the reduced products at the points
+            // 2 and 3 (slots 2, 3); B rows: the folded pair of the last factor
+            Fe m[K], y0, lo, hi;
 #pragma unroll 1
             for (int f = 0; f < D; ++f) {
 #pragma unroll
@@ -813,7 +933,7 @@ __device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in
                     dst = tc_fold_finish<F>(c);
                     st_fe(outp[p * D + f], h ? j + half : j, dst);
                 }
-                if (f < D - 1) {  // partial products of the first D - 1 factors at the points 0, 2, 3, ..
+                if (f < D - 1) {  // the first two factors at the points 0, 2, 3
                     Fe cur = lo;
                     const Fe d = Fd::sub(hi, lo);
 #pragma unroll
@@ -821,14 +941,32 @@ __device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in
                         if (k == 1) cur = Fd::add(hi, d);
                         else if (k > 1) cur = Fd::add(cur, d);
                         if (f == 0) m[k] = cur;
+                        else if (k == 0) y0 = cur;
                         else m[k] = Fd::mul(m[k], cur);
                     }
                 }
             }
-            gram.push(m, lo, hi, wg);
+            gram.wait_free();
+            gram.put_raw(0, m[0], y0);
+            gram.put_a(2, m[1]);
+            gram.put_a(3, m[2]);
+            gram.put_b(lo, hi);
+            gram.commit(0, wg);
         }
     }
-    gram.finish(out, 1, wg);
+    gram.finish(wg);
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = Fd::zero();
+    if (r == 0) {  // s(t) = (1 - t) G(., lo) + t G(., hi)
+        out[0] = gram.raw_sum(0, 0, 0);
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const Fe gl = gram.blk[(k + 1) * 2], d = Fd::sub(gram.blk[(k + 1) * 2 + 1], gl);
+            Fe v = gl;
+            for (int i = 0; i < k + 1; ++i) v = Fd::add(v, d);
+            out[k] = v;
+        }
+    }
     if (r == 0) {
 #pragma unroll
         for (int b = 0; b < NS + 2 * NT; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_full + b * 8) : "memory");
@@ -843,9 +981,9 @@ struct TcGramEvalSmem {
     static constexpr int NBUF = 2;
     static constexpr int stage_bytes = NBUF * 4 * BLOCK * 16;
     static constexpr int gram_off = stage_bytes;
-    static constexpr int gram_per_wg = (GramAcc<Bn254Fr, NPTS>::bytes_per_wg + 127) / 128 * 128;
+    static constexpr int gram_per_wg = (GramAcc2<Bn254Fr, 2>::bytes_per_wg + 127) / 128 * 128;
     static constexpr int bytes = gram_off + 2 * gram_per_wg;
-    static constexpr int tmem_cols = 128;  // per CTA: 64 Gram columns per warpgroup
+    static constexpr int tmem_cols = 256;  // per CTA: two 64-column Gram accumulators per warpgroup
 };
 template <class F, int D, int NPTS>
 __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval_gram(const __grid_constant__ ScArgs a) {
@@ -864,8 +1002,8 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval_gram(const __grid_constant
     const uint64_t first = (uint64_t)blockIdx.x * 2 + wg, tstride = (uint64_t)gridDim.x * 2;
     const uint32_t my_tiles = first < tiles ? (uint32_t)((tiles - first + tstride - 1) / tstride) : 0u;
     const int T = a.n_products * D;
-    GramAcc<F, NPTS> gram;
-    gram.init(tc_sm + L::gram_off + wg * L::gram_per_wg, s_tmem + wg * 64u, wg, wg);
+    GramAcc2<F, 2> gram;
+    gram.init(tc_sm + L::gram_off + wg * L::gram_per_wg, s_tmem + wg * 128u, wg, wg);
     uint4* my = reinterpret_cast<uint4*>(tc_sm) + threadIdx.x;
     // flattened prefetch sequence: (tile, table)
     uint32_t p_tile = 0;
@@ -899,27 +1037,39 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_eval_gram(const __grid_constant
     };
     for (uint32_t tk = 0; tk < my_tiles; ++tk) {
         for (int p = 0; p < a.n_products; ++p) {
-            Fe m[NPTS];
-            {
-                Fe lo0, hi0, lo1, hi1;
-                take(lo0, hi0);
-                take(lo1, hi1);
-                m[0] = Fd::mul(lo0, lo1);
-                m[1] = Fd::mul(hi0, hi1);
-                Fe e = Fd::mul(Fd::sub(hi0, lo0), Fd::sub(hi1, lo1));  // q(infinity)
-                e = Fd::dbl(e);                                          // the constant second difference
-                Fe dd = Fd::add(Fd::sub(m[1], m[0]), e);                 // q(2) - q(1)
-                m[2] = Fd::add(m[1], dd);
-                dd = Fd::add(dd, e);
-                m[3] = Fd::add(m[2], dd);
-            }
-            Fe lo2, hi2;
+            // q(t) = (lo0 + t d0)(lo1 + t d1) at t = 0..3 as RAW products (64 wide multiplies each instead of three Montgomery
+            // products and second differences): points 0, 1 go to accumulator group 0, points 2, 3 to group 1
+            Fe lo0, hi0, lo1, hi1, lo2, hi2;
+            take(lo0, hi0);
+            take(lo1, hi1);
+            gram.wait_free();
+            gram.put_raw(0, lo0, lo1);
+            gram.put_raw(2, hi0, hi1);
             take(lo2, hi2);
-            gram.push(m, lo2, hi2, wg);
+            gram.put_b(lo2, hi2);
+            gram.commit(0, wg);
+            const Fe d0 = Fd::sub(hi0, lo0), d1 = Fd::sub(hi1, lo1);
+            const Fe a2 = Fd::add(hi0, d0), b2 = Fd::add(hi1, d1);
+            const Fe a3 = Fd::add(a2, d0), b3 = Fd::add(b2, d1);
+            gram.wait_free();
+            gram.put_raw(0, a2, b2);
+            gram.put_raw(2, a3, b3);
+            gram.commit(1, wg);
         }
     }
     Fe out[NPTS];
-    gram.finish(out, 0, wg);
+    gram.finish(wg);
+#pragma unroll
+    for (int k = 0; k < NPTS; ++k) out[k] = Fd::zero();
+    if (r == 0) {  // s(t) = (1 - t) G(q_t, lo2) + t G(q_t, hi2)
+#pragma unroll
+        for (int k = 0; k < NPTS; ++k) {
+            const Fe gl = gram.raw_sum(k >> 1, 2 * (k & 1), 0), d = Fd::sub(gram.raw_sum(k >> 1, 2 * (k & 1), 1), gl);
+            Fe v = gl;
+            for (int i = 0; i < k; ++i) v = Fd::add(v, d);
+            out[k] = v;
+        }
+    }
     cp_async_wait<0>();
     finish_round<F, NPTS>(out, a.fin);
     tc_fence_before();
