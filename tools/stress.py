@@ -14,7 +14,8 @@ rng = random.Random(5)
 ctx = z.Context(fid, 0, z.MODE_FULL)
 S, T = z.sum_check_protocol, z.fiat_shamir.Transcript
 cases = []
-for P, D, n in ((1, 2, 4), (1, 2, 11), (1, 2, 14), (2, 2, 12), (1, 3, 10), (1, 2, 17), (2, 3, 13)):
+# (the shapes from 2^17 entries up run their large rounds on the tensor cores: TMA / MMA / TMEM pipelines, Gram drains)
+for P, D, n in ((1, 2, 4), (1, 2, 11), (1, 2, 14), (2, 2, 12), (1, 3, 10), (1, 2, 17), (2, 3, 13), (1, 2, 19), (1, 3, 18), (2, 2, 18), (2, 3, 17)):
     tabs = [O.synth_table(fid, 1000 + n, t, n) for t in range(P * D)]
     ref = O.gkr_sumcheck_prove(O.Transcript(fid), 1, P, D, tabs)
     mont = [z.engine.to_mont(fid, t) for t in tabs]
