@@ -513,6 +513,7 @@ class Bench:
             "largest_round": big,
             "fold_engine": ("tcgen05.mma kind::i8 (u8 x u8 -> s32 in TMEM, operands by TMA bulk copy; csrc/tcfold.cuh): bit-identical to the "
                             "CUDA-core fold" if tc_folds(D_) else "CUDA cores (fixed-multiplicand Montgomery product)"),
+            "tensor_cores": dict(zip(("enabled", "persistent_kernel"), ctx.tensor_cores())),
             "imad": {"wide_macs_per_quad": macs_per_quad(P_, D_), "bytes_per_quad": 96 * P_ * D_ * 2,
                      "measured_imad_wide_x_per_s": imad, "measured": "zkb_bench_imad in this run"},
             "kernels": {k: {"launches": v[0], "ms_per_step": v[1] / args.steps, "GBps": v[2] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0}

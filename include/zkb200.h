@@ -101,6 +101,10 @@ int32_t zkb_ctx_set_gather_threshold(zkb_ctx* ctx, uint32_t log2_local_entries);
 /* Rounds whose tables have at most 2^log2_entries entries run inside ONE persistent cooperative kernel that
  * exchanges round sums / challenges with the host transcript through a mailbox in mapped host memory
  * (no launch per round).  0 disables it (one launch per round).  Default 40 (always). */
+/* Tensor-core paths (csrc/tcfold.cuh): *enabled = 1 unless ZKB200_NO_TC was set when the ctx was created; *persistent = 1 if
+ * the persistent round kernel uses them too (two of its CTAs per SM were found co-resident by the creation-time probe;
+ * otherwise the large rounds of the persistent kernel stay on the CUDA cores and only the per-round launches use them). */
+int32_t zkb_ctx_tensor_cores(const zkb_ctx* ctx, int32_t* enabled, int32_t* persistent);
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* ctx, uint32_t log2_entries);
 /* Once all tables of a sumcheck fit in `smem_bytes` of shared memory (default and maximum 200 KiB) the remaining
  * rounds run in a single-CTA kernel that keeps the tables on chip; 0 disables it. */

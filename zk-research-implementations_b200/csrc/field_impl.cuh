@@ -42,7 +42,7 @@ bool l_sc_fold_eval(int kind, int D, int npts, const ScArgs& a, int grid, cudaSt
 bool l_sc_eval_tc(int kind, int D, int npts, const ScArgs& a, int grid, cudaStream_t s) {
 #define X(NP) \
     if (kind == KIND_PROD && D == 2 && npts == NP) { \
-        static bool once = (cudaFuncSetAttribute(k_sc_eval_tc<FT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCG_SMEM), true); \
+        static bool once = (cudaFuncSetAttribute(k_sc_eval_tc<FT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCG_SMEM), cudaFuncSetAttribute(k_sc_eval_tc<FT, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true); \
         (void)once; \
         k_sc_eval_tc<FT, NP><<<grid, BLOCK, TCG_SMEM, s>>>(a); \
         return true; \
@@ -51,7 +51,7 @@ bool l_sc_eval_tc(int kind, int D, int npts, const ScArgs& a, int grid, cudaStre
 #undef X
     if (kind == KIND_PROD && D == 3 && npts == 4) {
         constexpr int SM = TcGramEvalSmem<4>::bytes;
-        static bool once = (cudaFuncSetAttribute(k_sc_eval_gram<FT, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true);
+        static bool once = (cudaFuncSetAttribute(k_sc_eval_gram<FT, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), cudaFuncSetAttribute(k_sc_eval_gram<FT, 3, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
         (void)once;
         k_sc_eval_gram<FT, 3, 4><<<grid, BLOCK, SM, s>>>(a);
         return true;
@@ -62,7 +62,7 @@ bool l_sc_fold_eval_tc(int kind, int D, int npts, const ScArgsTc& a, int grid, c
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         constexpr int SM = TcFoldEvalCfg<DD, NP>::smem; \
-        static bool once = (cudaFuncSetAttribute(k_sc_fold_eval_tc<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
+        static bool once = (cudaFuncSetAttribute(k_sc_fold_eval_tc<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), cudaFuncSetAttribute(k_sc_fold_eval_tc<FT, K, DD, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true); \
         (void)once; \
         k_sc_fold_eval_tc<FT, K, DD, NP><<<grid, BLOCK, SM, s>>>(a); \
         return true; \
@@ -77,7 +77,7 @@ int l_sc_tail(int kind, int D, int npts, bool tc, const TailArgs& a, int grid, c
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
         constexpr int SM = TailSmemTc<NP>::bytes; \
-        static bool once = (cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), true); \
+        static bool once = (cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM), cudaFuncSetAttribute(k_sc_tail<FT, K, DD, NP, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true); \
         (void)once; \
         k_sc_tail<FT, K, DD, NP, true><<<grid, BLOCK, SM, s>>>(a); \
         return (int)cudaGetLastError(); \
@@ -158,7 +158,7 @@ void l_multifold(int k, const MultiFoldArgs& a, int grid, cudaStream_t s) {
     else k_multifold<FT, 1><<<grid, BLOCK, 0, s>>>(a);
 }
 void l_multifold_tc(const MultiFoldTcArgs& a, int grid, cudaStream_t s) {
-    static bool once = (cudaFuncSetAttribute(k_multifold_tc<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCM_SMEM), true);
+    static bool once = (cudaFuncSetAttribute(k_multifold_tc<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCM_SMEM), cudaFuncSetAttribute(k_multifold_tc<FT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
     (void)once;
     k_multifold_tc<FT><<<grid, TCM_THREADS, TCM_SMEM, s>>>(a);
 }

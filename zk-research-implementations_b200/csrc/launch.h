@@ -67,6 +67,7 @@ const FieldKernels* field_kernels_bn254_fr();
 const FieldKernels* field_kernels_bn254_fq();
 const FieldKernels* field_kernels_bls12_381_fr();
 void launch_gather_elems(const GatherArgs& a, cudaStream_t s);
+int launch_tc_probe(unsigned int* counter, unsigned int* failed, int grid, int smem, long long timeout_clocks, cudaStream_t s);  // cudaError_t
 void launch_bench_imad(int mode, uint64_t* out, uint32_t iters, int grid, cudaStream_t s);
 
 }  // namespace zkb

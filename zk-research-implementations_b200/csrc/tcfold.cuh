@@ -1192,6 +1192,34 @@ __global__ void __launch_bounds__(BLOCK, 2) k_sc_fold_eval_tc(const __grid_const
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(tmem, L::tmem_cols);
 }
+
+// ---- co-residency probe.  The tensor-core variant of the persistent kernel is a plain launch of 2 CTAs per SM that wait for
+// each other (cudaLaunchCooperativeKernel refuses it: the occupancy calculator answers 1 for kernels that allocate tensor
+// memory).  This kernel takes the same resources (shared memory, 128 TMEM columns, 256 threads) and reports whether all
+// CTAs of the grid were resident at the same time; the host runs it once per context and keeps the persistent kernel on the
+// CUDA cores if they were not.
+static __global__ void __launch_bounds__(BLOCK, 2) k_tc_probe(unsigned int* counter, unsigned int* failed, long long timeout_clocks) {
+    extern __shared__ __align__(128) uint8_t tc_sm[];
+    __shared__ uint32_t s_tmem;
+    if (threadIdx.x < 32) tmem_alloc(&s_tmem, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (threadIdx.x == 0) {
+        tc_sm[0] = 1;  // (the dynamic allocation is what matters)
+        atomicAdd(counter, 1u);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < gridDim.x) {
+            if (clock64() - t0 > timeout_clocks) {
+                *failed = 1u;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(s_tmem, 128);
+}
 #endif  // __CUDACC__
 
 }  // namespace zkb

@@ -329,6 +329,7 @@ struct zkb_ctx {
     TcMatsBuilder tcm;
     Fe* d_cpow8 = nullptr;
     bool tc_enabled = true;
+    bool tc_tail_ok = false;    // two CTAs per SM of the tensor-core persistent kernel are co-resident (probed at creation)
     // persistent round kernel
     TailMailbox* mb = nullptr;   // mapped pinned host memory
     TailRelay* d_relay = nullptr;
@@ -991,7 +992,7 @@ struct RoundDriver {
         if (big && stop_n < MID_N) stop_n = MID_N;
         a.stop_n = stop_n;
         // tensor-core folds when every round of this launch is throughput-bound (its last round writes stop_n entries)
-        const bool tc = big && !first_eval && stop_n >= MID_N && tc_round_ok(c, sp->kind, sp->kD, sp->npts, stop_n, 4);
+        const bool tc = big && !first_eval && stop_n >= MID_N && c->tc_tail_ok && tc_round_ok(c, sp->kind, sp->kD, sp->npts, stop_n, 4);
         if (tc) {
             a.cpow8 = c->d_cpow8;
             c->tcm.make(c->H, r, &a.mats0);
@@ -1904,6 +1905,18 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
     if (cudaMalloc((void**)&c->d_cpow8, sizeof(Fe) * 33) != cudaSuccess) return ZKB_ERR_CUDA;
     if (cudaMemcpy(c->d_cpow8, c->tcm.c, sizeof(Fe) * 33, cudaMemcpyHostToDevice) != cudaSuccess) return ZKB_ERR_CUDA;
     c->tc_enabled = getenv("ZKB200_NO_TC") == nullptr;
+    if (c->tc_enabled) {  // co-residency probe for the plain-launched persistent variant (tcfold.cuh k_tc_probe)
+        unsigned int* d = c->d_ticket;  // zero between launches; [1] does not exist: use d_res as the failure word
+        unsigned int* failed = reinterpret_cast<unsigned int*>(c->d_res);
+        cudaMemsetAsync(failed, 0, sizeof(unsigned int), c->stream);
+        const int e = launch_tc_probe(d, failed, 2 * c->sm_count, TailSmemTc<4>::bytes, 100000000ll, c->stream);  // ~50 ms
+        unsigned int f = 1;
+        if (e == 0 && cudaMemcpyAsync(&f, failed, sizeof f, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess)
+            c->tc_tail_ok = f == 0;
+        else
+            cudaGetLastError();
+        cudaMemsetAsync(d, 0, sizeof(unsigned int), c->stream);
+    }
     // Under Nsight Compute every launch is made synchronous, so a kernel that waits for the host's next
     // challenge can never be answered: profile with one launch per round (the same round_pass code).
     extern char** environ;
@@ -2072,6 +2085,12 @@ int32_t zkb_ctx_comm_init(zkb_ctx* c, int32_t rank, int32_t world, const uint8_t
     c->world = world;
     c->log2world = ilog2_u64((uint64_t)world);
     c->use_shm = getenv("ZKB200_NO_SHM") == nullptr && c->shm.open(unique_id, rank, world);
+    return ZKB_OK;
+}
+int32_t zkb_ctx_tensor_cores(const zkb_ctx* c, int32_t* enabled, int32_t* persistent) {
+    if (!c || !enabled || !persistent) return ZKB_ERR_BAD_ARG;
+    *enabled = c->tc_enabled ? 1 : 0;
+    *persistent = c->tc_enabled && c->tc_tail_ok ? 1 : 0;
     return ZKB_OK;
 }
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* c, uint32_t log2_entries) {

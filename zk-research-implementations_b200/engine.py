@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
         "zkb_kzg_commit": (i32, [vp, u64, u64, vp]),
         "zkb_kzg_open": (i32, [vp, u64, u64, u64p, u32, u64p]),
         "zkb_kzg_get_proof": (i32, [vp, u64, u64, u64p, u64p, u32, vp]),
+        "zkb_ctx_tensor_cores": (i32, [vp, i32p, i32p]),
         "zkb_fft_evaluate": (i32, [vp, u64p, u64, u64p]),
         "zkb_fft_interpolate": (i32, [vp, u64p, u64, u64p]),
         "zkb_mle_ntt": (i32, [vp, u64, i32, u64p]),
@@ -259,6 +260,12 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    def tensor_cores(self):
+        """(enabled, persistent): see zkb_ctx_tensor_cores."""
+        a, b = C.c_int32(), C.c_int32()
+        _ck(self, lib().zkb_ctx_tensor_cores(self._h, C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
 
     def sync(self) -> None:
         _ck(self, lib().zkb_ctx_sync(self._h))
