@@ -43,7 +43,7 @@ def prove(zkb, ctx, fid, tabs, P, D):
 
 
 @pytest.mark.parametrize("fid,p", FIELDS)
-@pytest.mark.parametrize("P,D,n", [(1, 2, 18), (2, 2, 18), (1, 3, 18), (2, 3, 18)])
+@pytest.mark.parametrize("P,D,n", [(1, 2, 18), (2, 2, 18), (1, 3, 18), (2, 3, 18), (3, 2, 17), (5, 3, 17)])
 def test_tc_proof_equals_oracle_and_cuda_cores(zkb, ctx_pairs, oracle, fid, p, P, D, n):
     tc, cc = ctx_pairs(fid)
     seed = 0xB2007C00 + 16 * P + D

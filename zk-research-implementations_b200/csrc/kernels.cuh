@@ -568,28 +568,19 @@ template <int KIND, int D>
 struct Staged {
     static constexpr bool value = KIND == KIND_XYZ || D <= 2;
 };
-// BULK: products of >= 3 factors stage through per-WARP buffers filled by TMA bulk copies.  A unit is one fold of one
-// table for the warp's 32 positions: 4 segments (2 elements x 2 limb planes) of 512 bytes; BULK_BUFS units in flight.
+// UNITS: products of >= 3 factors take their tables one fold at a time (round_pass_async3): a unit is one fold of one table,
+// 4 vectors per thread (2 elements x 2 limb planes); UnitBufs units are in flight per thread.
 template <int KIND, int D>
 struct Bulk {
-#ifdef ZKB_BULK_OFF  // (kbench only: the unstaged path of round 1, for comparison)
-    static constexpr bool value = false;
-#else
     static constexpr bool value = KIND == KIND_PROD && D >= 3;
-#endif
 };
 template <int NPTS>
 struct BulkBufs {
     static constexpr int value = NPTS <= 4 ? 3 : 2;  // bounded by 2 CTAs/SM next to the parked accumulators
 };
-constexpr int BULK_UNIT_VECS = 4 * 32;  // uint4 per unit and warp (2 KiB)
-#ifndef ZKB_BULK_TMA
-#define ZKB_BULK_TMA 0
-#endif
-constexpr bool BULK_USE_TMA = ZKB_BULK_TMA != 0;  // 1: per-warp TMA bulk copies; 0: per-thread cp.async slots (measured faster)
 template <int NPTS>
-struct BulkWarpBytes {  // per warp: the unit buffers (+ with TMA one mbarrier per buffer, padded to 32 bytes)
-    static constexpr int value = BulkBufs<NPTS>::value * BULK_UNIT_VECS * 16 + (BULK_USE_TMA ? 32 : 0);
+struct BulkWarpBytes {  // per warp: 32 threads x 4 vectors x 16 bytes per unit buffer
+    static constexpr int value = BulkBufs<NPTS>::value * 4 * 32 * 16;
 };
 template <int KIND, int D, int NPTS>
 struct FoldSmem {
@@ -601,110 +592,17 @@ template <int KIND, int D, int NPTS>
 struct TailSmem {  // the persistent kernel may start with the evaluation pass, which stages through 64 KiB
     static constexpr int bytes = FoldSmem<KIND, D, NPTS>::bytes > STAGE_BYTES ? FoldSmem<KIND, D, NPTS>::bytes : STAGE_BYTES;
 };
-// The >= 3-factor round pass: same arithmetic as round_pass, table reads through per-warp TMA bulk copies.
-// Warp w owns positions [jw, jw + 32) of each grid-stride iteration; unit sequence per iteration: for every table, the
-// "lo" fold (entries j, j + n_out) then the "hi" fold (entries j + half, j + half + n_out).  Production runs exactly
-// BULK_BUFS units ahead of consumption: right after the warp has moved unit u from shared memory into registers,
-// lane 0 refills the same buffer with unit u + BULK_BUFS, whose coordinates follow from the consumer's loop counters
-// (no separate producer state in registers).  The warp's buffers and mbarriers are addressed from one 32-bit base.
 __device__ __forceinline__ Fe lds_fe(unsigned int a_lo, unsigned int a_hi) {
     Fe r;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]) : "r"(a_lo));
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]) : "r"(a_hi));
     return r;
 }
-template <class F, int D, int NPTS>
-__device__ __forceinline__ void round_pass_bulk(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
-                                                uint64_t n_out, const FixedMul& rt, uint4* stage, uint4* accs, Fe* out) {
-    typedef Field<F> Fd;
-    constexpr int NB = BulkBufs<NPTS>::value;
-    constexpr unsigned int UNIT = BULK_UNIT_VECS * 16;  // bytes per unit
-    const unsigned int lane = threadIdx.x & 31;
-    const uint64_t half = n_out >> 1;
-    const uint64_t step = (uint64_t)gridDim.x * BLOCK;
-    const uint64_t jw0 = (uint64_t)blockIdx.x * BLOCK + (threadIdx.x & ~31u);  // the warp's first position
-    const int units = 2 * n_products * D;                                      // units per iteration
-    const unsigned int wb = smem_u32(stage) + (threadIdx.x >> 5) * BulkWarpBytes<NPTS>::value;
-    const unsigned int bars = wb + NB * UNIT;
-    auto issue = [&](uint64_t pj, int pu, unsigned int buf) {  // one lane: unit pu of the iteration at pj -> buffer buf
-        const uint64_t left = half - pj;
-        const unsigned int bytes = (unsigned int)(left < 32 ? left : 32) * 16u;
-        const TabRef& t = in[pu >> 1];
-        const uint4* g0 = t.base + pj + ((pu & 1) ? half : 0);
-        const uint4* g1 = g0 + t.stride;
-        const unsigned int dst = wb + buf * UNIT, bar = bars + buf * 8;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(g0), "r"(bytes), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 512u), "l"(g1), "r"(bytes), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 1024u), "l"(g0 + n_out), "r"(bytes), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 1536u), "l"(g1 + n_out), "r"(bytes), "r"(bar) : "memory");
-    };
-    if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + b * 8) : "memory");
-        fence_barrier_init();
-        fence_proxy_async();
-        if (jw0 < half) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) issue(jw0, b, b);  // units 0 .. NB-1 (units >= 6 > NB)
-        }
-    }
-    __syncwarp();
-    unsigned int cb = 0, phases = 0;  // buffer to consume next; bit b = parity to wait for on buffer b
-    RoundAcc<F, D, NPTS, true, true> acc;
-    acc.init(accs);
-    for (uint64_t jw = jw0; jw < half; jw += step) {
-        const uint64_t j = jw + lane;
-        const bool active = j < half;  // only the last warp of a tiny table is ragged
-        for (int p = 0; p < n_products; ++p) {
-            Fe m[NPTS - 1];
-#pragma unroll
-            for (int f = 0; f < D; ++f) {
-                Fe lo, hi;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    {
-                        const unsigned int bar = bars + cb * 8, par = (phases >> cb) & 1u;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "ZKB_W_%=:\n\t"
-                            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                            "@!p bra ZKB_W_%=;\n\t}" ::"r"(bar), "r"(par) : "memory");
-                    }
-                    const unsigned int src = wb + cb * UNIT + lane * 16u;
-                    const Fe x0 = lds_fe(src, src + 512u), x1 = lds_fe(src + 1024u, src + 1536u);
-                    __syncwarp();  // every lane has its operands in registers: the buffer may be refilled
-                    phases ^= 1u << cb;
-                    {
-                        int pu = 2 * (p * D + f) + h + NB;
-                        uint64_t pj = jw;
-                        if (pu >= units) {
-                            pu -= units;
-                            pj += step;
-                        }
-                        if (lane == 0 && pj < half) issue(pj, pu, cb);
-                    }
-                    cb = cb + 1 == NB ? 0u : cb + 1;
-                    Fe& dst = h ? hi : lo;
-                    dst = Fd::fold_fixed(x0, x1, rt);
-                    if (active) st_fe(outp[p * D + f], h ? j + half : j, dst);
-                }
-                if (active) acc.factor(f, lo, hi, m);
-            }
-        }
-    }
-    acc.finish(out);
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bars + b * 8) : "memory");
-    }
-    __syncwarp();
-}
 
-// Same unit pipeline with per-THREAD cp.async (LDGSTS) slots instead of per-warp bulk copies: slot layout
-// stage[buf][vec][thread]; a slot is private to its thread, so cp.async.wait_group is the only synchronisation.
-// Measured on B200 (2^28, 1 x 3): the bulk version 30.4 ms per proof in this kernel, this one see DESIGN.md section 6.
+// The >= 3-factor round pass for the sizes the tensor-core path does not take (below 2^16 entries): a unit is one fold of one
+// table; NB units are in flight through per-THREAD cp.async (LDGSTS) slots, stage[buf][vec][thread] -- a slot is private to its
+// thread, so cp.async.wait_group is the only synchronisation -- and the product is taken one factor at a time (RoundAcc::factor).
+// (A per-warp TMA bulk-copy version of the same pipeline measured 5 % slower and was dropped.)
 template <class F, int D, int NPTS>
 __device__ __forceinline__ void round_pass_async3(const TabRef* __restrict__ in, const TabRef* __restrict__ outp, int n_products,
                                                   uint64_t n_out, const FixedMul& rt, uint4* stage, uint4* accs, Fe* out) {
@@ -782,8 +680,7 @@ __device__ __forceinline__ void round_pass(const TabRef* __restrict__ in, const 
     uint4* my = stage + threadIdx.x;
     uint4* accs = stage + FoldSmem<KIND, D, NPTS>::stage_bytes / 16 + threadIdx.x;  // accumulators after the staging buffers
     if constexpr (Bulk<KIND, D>::value) {
-        if constexpr (BULK_USE_TMA) round_pass_bulk<F, D, NPTS>(in, outp, n_products, n_out, rt, stage, accs, out);
-        else round_pass_async3<F, D, NPTS>(in, outp, n_products, n_out, rt, stage, accs, out);
+        round_pass_async3<F, D, NPTS>(in, outp, n_products, n_out, rt, stage, accs, out);
         return;
     }
     uint64_t pj = j0;

@@ -609,106 +609,7 @@ __device__ __forceinline__ void tcg_block_add(uint32_t taddr, uint32_t* scratch,
     __syncwarp();
 }
 
-template <class F, int K>
-struct GramAcc {
-    typedef Field<F> Fd;
-    static constexpr int A_PIECES = 2 * K, PIECES = 2 * K + 4;
-    static constexpr int tile_bytes = PIECES * 2048;
-    static constexpr int sums_words = K * 2 * 17, scratch_words = K * 32 * 12;
-    static constexpr int bytes_per_wg = tile_bytes + (sums_words + scratch_words) * 4 + 64;
-    static_assert(K >= 2 && K <= 4, "the A operand spans 8 pieces from its base; 128 accumulator rows");
-    uint32_t tile, b_full, b_free, tmem, r, wq, lane, rows, pushes;
-    uint32_t *sums, *scratch;
-    bool mma_role;
-    __device__ __forceinline__ void init(uint8_t* base_wg, uint32_t tmem_cols, uint32_t wg_, uint32_t mma_warp) {
-        r = threadIdx.x & 127u;
-        wq = (threadIdx.x >> 5) & 3u;
-        lane = threadIdx.x & 31u;
-        tile = smem_u32(base_wg);
-        sums = reinterpret_cast<uint32_t*>(base_wg + tile_bytes);
-        scratch = sums + sums_words;
-        b_full = smem_u32(base_wg + tile_bytes + (sums_words + scratch_words) * 4);
-        b_free = b_full + 8;
-        tmem = tmem_cols;
-        mma_role = lane == 0 && wq == mma_warp;
-        rows = pushes = 0;
-        for (uint32_t i = r; i < (uint32_t)sums_words; i += 128) sums[i] = 0;
-        if (r == 0) {
-            mbar_init_u32(b_full, 128u);
-            mbar_init_u32(b_free, 1u);
-            fence_barrier_init();
-        }
-        wg_sync(wg_);
-    }
-    __device__ __forceinline__ void put(uint32_t piece, const Fe& v) {
-        const uint32_t a0 = tile + piece * 2048u + r * 16u;
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(v.l[3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + 2048u), "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7]) : "memory");
-    }
-    // the 128 threads of the warpgroup together: one row each
-    __device__ __forceinline__ void push(const Fe* m, const Fe& lo, const Fe& hi, uint32_t wg_) {
-        if (pushes) mbar_wait_u32(b_free, (pushes - 1u) & 1u);  // the MMAs of the previous push have read the tile
-#pragma unroll
-        for (int k = 0; k < K; ++k) put(2 * k, m[k]);
-        put(A_PIECES, lo);
-        put(A_PIECES + 2, hi);
-        fence_proxy_async();
-        mbar_arrive_u32(b_full);
-        if (mma_role) {
-            mbar_wait_u32(b_full, pushes & 1u);
-            tc_fence_after();
-#pragma unroll
-            for (uint32_t k4 = 0; k4 < 4; ++k4)
-                umma_i8(tmem, umma_desc(tile + k4 * 512u, 128, 2048), umma_desc(tile + A_PIECES * 2048u + k4 * 512u, 128, 2048), TC_IDESC_GRAM64,
-                        (rows | k4) ? 1u : 0u);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b_free) : "memory");
-        }
-        rows += 128u;
-        ++pushes;
-        if (rows == TCG_DRAIN_ROWS) drain(wg_);
-    }
-    __device__ __forceinline__ void drain(uint32_t wg_) {
-        if (!rows) return;
-        mbar_wait_u32(b_free, (pushes - 1u) & 1u);  // the commit of the last push covers every MMA before it
-        tc_fence_after();
-        if (wq < (uint32_t)K) {
-            tcg_block_add(tmem + ((wq * 32u) << 16), scratch + wq * (32 * 12), lane, sums + (wq * 2) * 17);
-            tcg_block_add(tmem + 32u + ((wq * 32u) << 16), scratch + wq * (32 * 12), lane, sums + (wq * 2 + 1) * 17);
-        }
-        tc_fence_before();
-        wg_sync(wg_);
-        rows = 0;
-    }
-    // out[k] = (1 - t_k) G(m_k, lo) + t_k G(m_k, hi) in lane 0 of warp k of this warpgroup, zero elsewhere; t_k = first_t
-    // for k = 0 and k + skip afterwards (skip = 1: the points 0, 2, 3, .. of a round whose s(1) comes from the claim)
-    __device__ __forceinline__ void finish(Fe* out, int skip, uint32_t wg_) {
-        drain(wg_);
-#pragma unroll
-        for (int k = 0; k < K; ++k) out[k] = Fd::zero();
-        if (wq < (uint32_t)K && lane == 0) {
-            Wide wl, wh;
-#pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                wl.l[i] = sums[(wq * 2) * 17 + i];
-                wh.l[i] = sums[(wq * 2 + 1) * 17 + i];
-            }
-            const Fe gl = Fd::reduce_wide(wl), gh = Fd::reduce_wide(wh), d = Fd::sub(gh, gl);
-            Fe v = gl;
-            const uint32_t t = wq == 0 ? 0u : wq + (uint32_t)skip;
-            for (uint32_t i = 0; i < t; ++i) v = Fd::add(v, d);
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                if ((uint32_t)k == wq) out[k] = v;
-        }
-        wg_sync(wg_);
-        if (r == 0) {
-            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_full) : "memory");
-            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b_free) : "memory");
-        }
-    }
-};
-
-// GramAcc2: the same accumulator with UNREDUCED products among the A rows.  A raw 512-bit product T = x y of two residues
+// GramAcc2: the accumulator, with UNREDUCED products among the A rows.  A raw 512-bit product T = x y of two residues
 // costs 64 wide multiplies instead of the 136 of a Montgomery product; written as 64 byte rows (low half L, high half H,
 // T = L + 2^256 H) it enters the contraction like any other value, and the two missing divisions by R = 2^256 are done once,
 // at the very end: sum_j T_j c_j R^-2 = redc(redc(G(L, c))) + redc(G(H, c)).  The tile is [A: 4 slots of 32 bytes][B: lo, hi]
