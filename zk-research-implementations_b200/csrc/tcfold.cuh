@@ -12,6 +12,12 @@
 // column sums (< 2^22 each) into 9 limbs, run ONE 32-bit Montgomery row (division by 2^32: 8 wide multiplies instead
 // of the 82 of Field::fold_fixed) and subtract p once: the result is the canonical residue, bit-identical to the
 // CUDA-core fold.
+//
+// Contents: tcgen05 / TMEM / UMMA-descriptor primitives; tc_fold_finish (column sums -> canonical residue); k_tc_fold (the
+// stand-alone check, tools/tcfold.cu); round_pass_tc (fused round pass, 2 factors; used by k_sc_fold_eval_tc and k_sc_tail<TC>);
+// k_sc_eval_tc (round 0 of 2 factors as one Gram matrix); GramAcc2 + round_pass_tc_gram + k_sc_eval_gram (3 factors: raw
+// partial products through Gram tiles); k_multifold_tc (evaluate); k_tc_probe (co-residency of the plain-launched persistent
+// kernel).  DESIGN.md section 6a has the derivations and the measurements.
 #pragma once
 // (included by kernels.cuh after the round-pass building blocks and before the persistent kernel)
 
