@@ -38,6 +38,10 @@ for mode, shapes in () if GKR_ONLY else ((z.MODE_FULL, [(1, 1), (1, 2), (1, 3), 
         a.scale(r).free()
         s1, s2 = z.MultilinearPoly.generate(ctx, 6, 2, n // 2), z.MultilinearPoly.generate(ctx, 6, 3, n // 2)
         z.MultilinearPoly.tensor_add_mul_polynomials(s1, s2, z.Operation.Mul).free()
+        z.fft.ntt(a).free()  # fft/src/fft.rs
+        mt = z.merkle_tree.MerkleTree(ctx, 12, [rng.randrange(p) for _ in range(1 << 12)])  # merkle_tree/src/merkle_tree.rs
+        mt.update_leaf(5, 77, False)
+        mt.free()
         S.prove(a)  # plain sumcheck (absorbs the table)
         for t in (a, b, s1, s2):
             t.free()
@@ -61,4 +65,15 @@ wp = z.gkr_protocol.RawWiredGkrProver(w, inp[:G])
 wp.prove()
 assert wp.verify()
 ctx.close()
+if not GKR_ONLY:  # input-layer commitment (pcs/src/kzg_pcs/kzg.rs), BLS12-381
+    kctx = z.Context(z.BLS12_381_FR, 0, z.MODE_FULL)
+    q = z.engine.MODULI[z.BLS12_381_FR]
+    m = z.MultilinearPoly.generate(kctx, 9, 0, 14)
+    k = z.kzg.KZG(m, [rng.randrange(q) for _ in range(14)])
+    k.commit(m)
+    pt = [rng.randrange(q) for _ in range(14)]
+    k.get_proof(k.open(pt, m), pt, m)
+    k.free()
+    m.free()
+    kctx.close()
 print("all kernels launched")
