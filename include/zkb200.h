@@ -101,6 +101,10 @@ int32_t zkb_ctx_set_gather_threshold(zkb_ctx* ctx, uint32_t log2_local_entries);
 /* Rounds whose tables have at most 2^log2_entries entries run inside ONE persistent cooperative kernel that
  * exchanges round sums / challenges with the host transcript through a mailbox in mapped host memory
  * (no launch per round).  0 disables it (one launch per round).  Default 40 (always). */
+/* Host only (no ctx, no GPU): the two byte matrices the tensor-core fold uses for a challenge r (Montgomery limbs in): out[0..1024)
+ * for the (1 - r) rows, out[1024..2048) for the r rows; byte n of T_k = (1 - r) 2^(8 k + 32) mod p resp. r 2^(8 k + 32) mod p at
+ * (k / 16) * 512 + n * 16 + k % 16 (csrc/tcfold.cuh).  Exposed so that the construction can be checked without a device. */
+int32_t zkb_tc_fold_matrices(int32_t field_id, const uint64_t r_mont[4], uint8_t out[2048]);
 /* Tensor-core paths (csrc/tcfold.cuh): *enabled = 1 unless ZKB200_NO_TC was set when the ctx was created; *persistent = 1 if
  * the persistent round kernel uses them too (two of its CTAs per SM were found co-resident by the creation-time probe;
  * otherwise the large rounds of the persistent kernel stay on the CUDA cores and only the per-round launches use them). */

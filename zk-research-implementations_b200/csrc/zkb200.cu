@@ -2423,6 +2423,17 @@ int32_t zkb_fe_from_mont(int32_t field_id, const uint64_t* mont, uint64_t* canon
     return ZKB_OK;
 }
 
+int32_t zkb_tc_fold_matrices(int32_t field_id, const uint64_t r_mont[4], uint8_t out[2048]) {
+    if (!r_mont || !out || field_id < 0 || field_id > 2) return ZKB_ERR_BAD_ARG;
+    const FieldKernels* K = field_id == 0 ? field_kernels_bn254_fr() : (field_id == 1 ? field_kernels_bn254_fq() : field_kernels_bls12_381_fr());
+    const HostField H = HostField::make(K);
+    TcMatsBuilder b;
+    b.init(H);
+    TcFoldMats m;
+    b.make(H, fe_from_u64x4(r_mont), &m);
+    std::memcpy(out, m.b, 2048);
+    return ZKB_OK;
+}
 int32_t zkb_fe_reduce_wide(int32_t field_id, const uint64_t* wide, uint64_t* out, size_t n) {
     const FieldKernels* K = kernels_for(field_id);
     if (!K || (!wide && n) || (!out && n)) return ZKB_ERR_BAD_ARG;

@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
         "zkb_kzg_open": (i32, [vp, u64, u64, u64p, u32, u64p]),
         "zkb_kzg_get_proof": (i32, [vp, u64, u64, u64p, u64p, u32, vp]),
         "zkb_ctx_tensor_cores": (i32, [vp, i32p, i32p]),
+        "zkb_tc_fold_matrices": (i32, [i32, u64p, vp]),
         "zkb_fft_evaluate": (i32, [vp, u64p, u64, u64p]),
         "zkb_fft_interpolate": (i32, [vp, u64p, u64, u64p]),
         "zkb_mle_ntt": (i32, [vp, u64, i32, u64p]),
