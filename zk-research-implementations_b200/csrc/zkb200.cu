@@ -316,6 +316,8 @@ struct zkb_ctx {
     std::unordered_map<uint64_t, std::unique_ptr<KzgState>> kzgs;
     std::unordered_map<uint64_t, std::unique_ptr<MerkleState>> merkles;
     G1Affine* g1_table = nullptr;  // 32 x 256 multiples of the generator (fixed-base windows), made on first use
+    cudaStream_t kzg_streams[4] = {nullptr, nullptr, nullptr, nullptr};  // side streams of get_proof (made on first use)
+    cudaEvent_t kzg_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1, log2world = 0;
@@ -1772,13 +1774,14 @@ MsmPlan msm_plan(uint64_t n) {
     return pl;
 }
 // sum_i bases[i] * scalars[i] -> 96 canonical affine bytes in d_out (device).  scalars: a Montgomery Fr table.
-int32_t msm_run(zkb_ctx* c, const Table& scalars, const G1Affine* bases, uint64_t n, uint8_t* d_out) {
+// (st: the stream the whole MSM runs on, scratch included -- the quotient commitments of get_proof run on side streams)
+int32_t msm_run(zkb_ctx* c, const Table& scalars, const G1Affine* bases, uint64_t n, uint8_t* d_out, cudaStream_t st) {
     if (n <= 256) {
         G1Jac* scratch = nullptr;
-        ZK_CUDA(c, cudaMallocAsync((void**)&scratch, sizeof(G1Jac) * 256, c->stream));
-        k_msm_small<<<1, 256, 0, c->stream>>>(scalars.ref(), bases, (uint32_t)n, scratch, d_out);
+        ZK_CUDA(c, cudaMallocAsync((void**)&scratch, sizeof(G1Jac) * 256, st));
+        k_msm_small<<<1, 256, 0, st>>>(scalars.ref(), bases, (uint32_t)n, scratch, d_out);
         ZK_TRY(check_launch(c, "k_msm_small"));
-        cudaFreeAsync(scratch, c->stream);
+        cudaFreeAsync(scratch, st);
         return ZKB_OK;
     }
     const MsmPlan pl = msm_plan(n);
@@ -1791,38 +1794,38 @@ int32_t msm_run(zkb_ctx* c, const Table& scalars, const G1Affine* bases, uint64_
     size_t tmp_bytes = 0;
     int key_bits = (int)pl.c;
     while ((1u << (key_bits - (int)pl.c)) < pl.windows) ++key_bits;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)m, 0, key_bits, c->stream);
-    ZK_CUDA(c, cudaMallocAsync((void**)&keys, m * 4, c->stream));
-    ZK_CUDA(c, cudaMallocAsync((void**)&vals, m * 4, c->stream));
-    ZK_CUDA(c, cudaMallocAsync((void**)&keys2, m * 4, c->stream));
-    ZK_CUDA(c, cudaMallocAsync((void**)&vals2, m * 4, c->stream));
-    ZK_CUDA(c, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, c->stream));
-    ZK_CUDA(c, cudaMallocAsync((void**)&start, (size_t)nb * 8, c->stream));  // start[nb], end[nb]
-    ZK_CUDA(c, cudaMallocAsync((void**)&heavy, ((size_t)nb + 1) * 4, c->stream));  // count, then the list
-    ZK_CUDA(c, cudaMallocAsync((void**)&buckets, sizeof(G1Jac) * nb, c->stream));
-    ZK_CUDA(c, cudaMallocAsync((void**)&parts, sizeof(G1Jac) * pl.windows * pl.chunks, c->stream));
-    ZK_CUDA(c, cudaMallocAsync((void**)&wsum, sizeof(G1Jac) * pl.windows, c->stream));
-    ZK_CUDA(c, cudaMemsetAsync(start, 0, (size_t)nb * 8, c->stream));
-    ZK_CUDA(c, cudaMemsetAsync(heavy, 0, 4, c->stream));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)m, 0, key_bits, st);
+    ZK_CUDA(c, cudaMallocAsync((void**)&keys, m * 4, st));
+    ZK_CUDA(c, cudaMallocAsync((void**)&vals, m * 4, st));
+    ZK_CUDA(c, cudaMallocAsync((void**)&keys2, m * 4, st));
+    ZK_CUDA(c, cudaMallocAsync((void**)&vals2, m * 4, st));
+    ZK_CUDA(c, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+    ZK_CUDA(c, cudaMallocAsync((void**)&start, (size_t)nb * 8, st));  // start[nb], end[nb]
+    ZK_CUDA(c, cudaMallocAsync((void**)&heavy, ((size_t)nb + 1) * 4, st));  // count, then the list
+    ZK_CUDA(c, cudaMallocAsync((void**)&buckets, sizeof(G1Jac) * nb, st));
+    ZK_CUDA(c, cudaMallocAsync((void**)&parts, sizeof(G1Jac) * pl.windows * pl.chunks, st));
+    ZK_CUDA(c, cudaMallocAsync((void**)&wsum, sizeof(G1Jac) * pl.windows, st));
+    ZK_CUDA(c, cudaMemsetAsync(start, 0, (size_t)nb * 8, st));
+    ZK_CUDA(c, cudaMemsetAsync(heavy, 0, 4, st));
     uint32_t* end = start + nb;
-    k_msm_digits<<<grid_for(c, n, 8), BLOCK, 0, c->stream>>>(scalars.ref(), n, pl, keys, vals);
+    k_msm_digits<<<grid_for(c, n, 8), BLOCK, 0, st>>>(scalars.ref(), n, pl, keys, vals);
     ZK_TRY(check_launch(c, "k_msm_digits"));
-    if (cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)m, 0, key_bits, c->stream) != cudaSuccess)
+    if (cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)m, 0, key_bits, st) != cudaSuccess)
         ZK_FAIL(c, ZKB_ERR_CUDA, "msm: radix sort failed");
-    k_msm_bounds<<<grid_for(c, m, 8), BLOCK, 0, c->stream>>>(keys2, m, start, end);
+    k_msm_bounds<<<grid_for(c, m, 8), BLOCK, 0, st>>>(keys2, m, start, end);
     ZK_TRY(check_launch(c, "k_msm_bounds"));
-    k_msm_buckets<<<(nb + 127) / 128, 128, 0, c->stream>>>(vals2, start, end, bases, pl, buckets, heavy + 1, heavy);
+    k_msm_buckets<<<(nb + 127) / 128, 128, 0, st>>>(vals2, start, end, bases, pl, buckets, heavy + 1, heavy);
     ZK_TRY(check_launch(c, "k_msm_buckets"));
-    k_msm_heavy<<<c->sm_count, 256, sizeof(G1Jac) * 256, c->stream>>>(vals2, start, end, bases, buckets, heavy + 1, heavy);
+    k_msm_heavy<<<c->sm_count, 256, sizeof(G1Jac) * 256, st>>>(vals2, start, end, bases, buckets, heavy + 1, heavy);
     ZK_TRY(check_launch(c, "k_msm_heavy"));
-    k_msm_window_chunks<<<(pl.windows * pl.chunks + 127) / 128, 128, 0, c->stream>>>(buckets, pl, parts);
+    k_msm_window_chunks<<<(pl.windows * pl.chunks + 127) / 128, 128, 0, st>>>(buckets, pl, parts);
     ZK_TRY(check_launch(c, "k_msm_window_chunks"));
-    k_msm_window_sum<<<pl.windows, 128, 0, c->stream>>>(parts, pl, wsum);
+    k_msm_window_sum<<<pl.windows, 128, 0, st>>>(parts, pl, wsum);
     ZK_TRY(check_launch(c, "k_msm_window_sum"));
-    k_msm_horner<<<1, 32, 0, c->stream>>>(wsum, pl, d_out);
+    k_msm_horner<<<1, 32, 0, st>>>(wsum, pl, d_out);
     ZK_TRY(check_launch(c, "k_msm_horner"));
     for (void* q : {(void*)keys, (void*)vals, (void*)keys2, (void*)vals2, tmp, (void*)start, (void*)heavy, (void*)buckets, (void*)parts, (void*)wsum})
-        cudaFreeAsync(q, c->stream);
+        cudaFreeAsync(q, st);
     return ZKB_OK;
 }
 int32_t kzg_require_field(zkb_ctx* c) {
@@ -2023,6 +2026,10 @@ int32_t zkb_ctx_destroy(zkb_ctx* c) {
     cudaFree(c->d_relay);
     cudaFree(c->d_cpow8);
     for (auto& kv : c->merkles) cudaFree(kv.second->tree);
+    for (int i = 0; i < 4; ++i) {
+        if (c->kzg_streams[i]) cudaStreamDestroy(c->kzg_streams[i]);
+        if (c->kzg_ev[i]) cudaEventDestroy(c->kzg_ev[i]);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
     return ZKB_OK;
@@ -3203,7 +3210,7 @@ int32_t zkb_kzg_commit(zkb_ctx* c, zkb_kzg h, zkb_mle poly, uint8_t out[96]) {
     if (t->n != (1ull << it->second->n_vars)) ZK_FAIL(c, ZKB_ERR_LENGTH_MISMATCH, "invalid polynomial or lagrange basis");  // kzg.rs:135-137
     uint8_t* d = nullptr;
     ZK_CUDA(c, cudaMallocAsync((void**)&d, 96, c->stream));
-    ZK_TRY(msm_run(c, *t, it->second->basis[0], t->n, d));
+    ZK_TRY(msm_run(c, *t, it->second->basis[0], t->n, d, c->stream));
     ZK_CUDA(c, cudaMemcpyAsync(out, d, 96, cudaMemcpyDeviceToHost, c->stream));
     ZK_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFreeAsync(d, c->stream);
@@ -3227,15 +3234,29 @@ int32_t zkb_kzg_get_proof(zkb_ctx* c, zkb_kzg h, zkb_mle poly, const uint64_t op
     if (n > ks->n_vars) ZK_FAIL(c, ZKB_ERR_ARITY, "Invalid number of values");
     uint8_t* d = nullptr;
     ZK_CUDA(c, cudaMallocAsync((void**)&d, 96 * (size_t)(n ? n : 1), c->stream));
+    // The n quotient commitments are independent of each other (only the remainder chain is sequential), and a small MSM
+    // is latency: a single-warp window combination and a few CTAs of bucket sums.  Every level gets its own slice of one
+    // quotient table and its MSM runs on one of four side streams behind an event, so the serial tails overlap.
+    for (int i = 0; i < 4; ++i) {
+        if (!c->kzg_streams[i]) ZK_CUDA(c, cudaStreamCreateWithFlags(&c->kzg_streams[i], cudaStreamNonBlocking));
+        if (!c->kzg_ev[i]) ZK_CUDA(c, cudaEventCreateWithFlags(&c->kzg_ev[i], cudaEventDisableTiming));
+    }
     Table cur = *t, work, q;
     ZK_TRY(alloc_table(c, t->n / 2, &work));
-    ZK_TRY(alloc_table(c, t->n / 2, &q));
+    ZK_TRY(alloc_table(c, t->n, &q));  // level k (half_k entries) at offset n - 2 half_k: the slices tile [0, n)
+    cudaEvent_t ready = nullptr;
+    ZK_CUDA(c, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     for (uint32_t k = 0; k < n; ++k) {
         const uint64_t half = cur.n / 2;
-        q.n = half;
-        k_kzg_quotient<<<grid_for(c, half, 8), BLOCK, 0, c->stream>>>(cur.ref(), q.ref(), half);  // kzg.rs:152-163
+        Table qk = q;
+        qk.base = q.base + (t->n - 2 * half);
+        qk.n = half;
+        k_kzg_quotient<<<grid_for(c, half, 8), BLOCK, 0, c->stream>>>(cur.ref(), qk.ref(), half);  // kzg.rs:152-163
         ZK_TRY(check_launch(c, "k_kzg_quotient"));
-        ZK_TRY(msm_run(c, q, ks->basis[k + 1], half, d + 96 * (size_t)k));                          // :80-83 on the folded basis
+        cudaStream_t side = c->kzg_streams[k & 3];
+        ZK_CUDA(c, cudaEventRecord(ready, c->stream));
+        ZK_CUDA(c, cudaStreamWaitEvent(side, ready, 0));
+        ZK_TRY(msm_run(c, qk, ks->basis[k + 1], half, d + 96 * (size_t)k, side));                    // :80-83 on the folded basis
         FixedMul rt;                                                                               // remainder: partial_evaluate(0, z_k), :146-150
         c->fmb.make(c->H, fe_from_u64x4(opening_values + 4 * k), &rt);
         c->K->fold(cur.ref(), work.ref(), half, (uint32_t)ilog2_u64(half), rt, grid_for(c, half, 8), c->stream);
@@ -3243,6 +3264,11 @@ int32_t zkb_kzg_get_proof(zkb_ctx* c, zkb_kzg h, zkb_mle poly, const uint64_t op
         cur = work;
         cur.n = half;
     }
+    for (int i = 0; i < 4; ++i) {  // the main stream continues after every side stream
+        ZK_CUDA(c, cudaEventRecord(c->kzg_ev[i], c->kzg_streams[i]));
+        ZK_CUDA(c, cudaStreamWaitEvent(c->stream, c->kzg_ev[i], 0));
+    }
+    cudaEventDestroy(ready);
     ZK_CUDA(c, cudaMemcpyAsync(out, d, 96 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     ZK_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFreeAsync(d, c->stream);
