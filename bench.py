@@ -332,6 +332,8 @@ class Bench:
 
         def __enter__(self):
             try:
+                if len(os.sched_getaffinity(0)) < 2:  # the other threads of this rank (NCCL proxy, sampler) need a core too
+                    raise OSError("single core")
                 self.old = (os.sched_getscheduler(0), os.sched_getparam(0))
                 os.sched_setscheduler(0, os.SCHED_FIFO, os.sched_param(10))
                 Bench._HostPriority.policy = "SCHED_FIFO during the timed proofs"
