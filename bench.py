@@ -769,10 +769,12 @@ def gkr_leg(z, args):
         prover = z.gkr_protocol.RawGkrProver(circ, buf)
         for _ in range(2):
             prover.prove()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            prover.prove()
-        return prover, (time.perf_counter() - t0) * 1e3 / reps
+        with Bench._HostPriority():
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                prover.prove()
+            ms_ = (time.perf_counter() - t0) * 1e3 / reps
+        return prover, ms_
 
     _, ms_pageable = run(inputs)
     pinned = torch.from_numpy(inputs.view(np.int64)).pin_memory()  # keep the tensor alive: the prover reads its memory
