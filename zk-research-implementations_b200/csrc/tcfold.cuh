@@ -357,6 +357,9 @@ __device__ __forceinline__ void round_pass_tc(const TabRef* __restrict__ in, con
             }
         }
     }
+    // The folded entries were stored through the generic proxy; the next round of the persistent kernel reads them (in this
+    // or another CTA, after the grid-wide hand-shake) with TMA, i.e. through the async proxy: order the two proxies.
+    asm volatile("fence.proxy.async;" ::: "memory");
     acc.finish(out);
     wg_sync(wg);  // nobody of this warpgroup still waits on a barrier
     if (r == 0) {
@@ -861,6 +864,7 @@ __device__ __forceinline__ void round_pass_tc_gram(const TabRef* __restrict__ in
             gram.commit(0, wg);
         }
     }
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of the folded tables before later TMA reads (see round_pass_tc)
     gram.finish(wg);
 #pragma unroll
     for (int k = 0; k < K; ++k) out[k] = Fd::zero();
