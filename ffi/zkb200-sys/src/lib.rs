@@ -123,6 +123,7 @@ extern "C" {
     pub fn zkb_kzg_get_proof(ctx: *mut zkb_ctx, k: zkb_kzg, poly: zkb_mle, opened_value: *const u64, opening_values: *const u64, n: u32, out: *mut u8) -> i32;
     pub fn zkb_tc_fold_matrices(field_id: i32, r_mont: *const u64, out: *mut u8) -> i32;
     pub fn zkb_ctx_tensor_cores(ctx: *const zkb_ctx, enabled: *mut i32, persistent: *mut i32) -> i32;
+    pub fn zkb_ctx_small_cluster_max(ctx: *const zkb_ctx, ctas: *mut i32) -> i32;
     pub fn zkb_fft_evaluate(ctx: *mut zkb_ctx, coeffs_mont: *const u64, n: u64, evals_mont: *mut u64) -> i32;
     pub fn zkb_fft_interpolate(ctx: *mut zkb_ctx, evals_mont: *const u64, n: u64, coeffs_mont: *mut u64) -> i32;
     pub fn zkb_mle_ntt(ctx: *mut zkb_ctx, input: zkb_mle, inverse: i32, out: *mut zkb_mle) -> i32;

@@ -110,8 +110,12 @@ int32_t zkb_tc_fold_matrices(int32_t field_id, const uint64_t r_mont[4], uint8_t
  * otherwise the large rounds of the persistent kernel stay on the CUDA cores and only the per-round launches use them). */
 int32_t zkb_ctx_tensor_cores(const zkb_ctx* ctx, int32_t* enabled, int32_t* persistent);
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* ctx, uint32_t log2_entries);
-/* Once all tables of a sumcheck fit in `smem_bytes` of shared memory (default and maximum 200 KiB) the remaining
- * rounds run in a single-CTA kernel that keeps the tables on chip; 0 disables it. */
+/* CTAs of the largest thread-block cluster the on-chip kernel (next entry) is launched with: 16 on a B200 unless
+ * ZKB200_CLUSTER_MAX (a power of two, 1 = single CTA) was set when the ctx was created or the device cannot place it. */
+int32_t zkb_ctx_small_cluster_max(const zkb_ctx* ctx, int32_t* ctas);
+/* Once all tables of a sumcheck fit in `smem_bytes` of shared memory per CTA (default and maximum 200 KiB) the remaining
+ * rounds run in ONE launch that keeps the tables on chip -- a single CTA, or a thread-block cluster of up to 16 CTAs with
+ * the tables sharded over their shared memories (16 x the size); 0 disables it. */
 int32_t zkb_ctx_set_small_threshold(zkb_ctx* ctx, uint32_t smem_bytes);
 /* Device-side Fiat-Shamir transcript (default OFF, ZKB200_DT=1 in the environment turns it on).  In the
  * on-chip kernel above, for round polynomials of degree <= 2 (the GKR layer sumcheck and products of two factors),

@@ -99,17 +99,51 @@ int l_sc_tail(int kind, int D, int npts, bool tc, const TailArgs& a, int grid, c
 }
 int l_sc_small(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s) {
     const int T = a.n_tables;
-    const size_t smem = (size_t)T * a.n_in * 32;
+    const int nc = a.nc > 1 ? a.nc : 1;
+    const size_t smem = (size_t)T * (a.n_in / nc) * 32;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(nc);
+    cfg.blockDim = dim3(SMALL_BLOCK);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nc;
+    attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = nc > 1 ? 1 : 0;
 #define X(K, DD, NP) \
     if (kind == K && D == DD && npts == NP) { \
-        static bool once = (cudaFuncSetAttribute(k_sc_small<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM_MAX), true); \
+        static bool once = (cudaFuncSetAttribute(k_sc_small<FT, K, DD, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM_MAX), \
+                            cudaFuncSetAttribute(k_sc_small<FT, K, DD, NP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), true); \
         (void)once; \
-        k_sc_small<FT, K, DD, NP><<<1, SMALL_BLOCK, smem, s>>>(a); \
-        return (int)cudaGetLastError(); \
+        return (int)cudaLaunchKernelEx(&cfg, k_sc_small<FT, K, DD, NP>, a); \
     }
     ZKB_SC_CASES(X)
 #undef X
     return -1;
+}
+// largest cluster (<= SMALL_MAX_CLUSTER CTAs, each with the full shared-memory budget) this device can place
+int l_sc_small_max_cluster() {
+    auto kern = k_sc_small<FT, KIND_PROD, 2, 3>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int nc = SMALL_MAX_CLUSTER; nc > 1; nc >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3(nc);
+        cfg.blockDim = dim3(SMALL_BLOCK);
+        cfg.dynamicSmemBytes = SMALL_SMEM_MAX;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = nc;
+        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1) return nc;
+        cudaGetLastError();
+    }
+    return 1;
 }
 int l_sc_occupancy(int fused, int kind, int D, int npts) {
     int nb = 0;
@@ -238,7 +272,7 @@ void h_modulus(Fe& p) {
 }
 
 const FieldKernels TABLE = {
-    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_eval_tc, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_multifold_tc, l_fold,      l_aos_to_planar, l_planar_to_aos,
+    FT::ID,      l_sc_eval,   l_sc_fold_eval, l_sc_eval_tc, l_sc_fold_eval_tc, l_sc_tail, l_sc_small, l_sc_small_max_cluster, l_sc_occupancy, l_fold_tables, l_final_bind, l_multifold, l_multifold_tc, l_fold,      l_aos_to_planar, l_planar_to_aos,
     l_interleave, l_generate, l_vec_op,       l_axpby,        l_tensor,      l_layer_eval, l_add_mul_i, l_eq_split,     l_gkr_phase1,
     l_gkr_phase2, l_gkr_wiring, l_gkr_w_phase1, l_gkr_w_phase2, l_gkr_w_wiring, l_layer_eval_w, l_bench_mul, l_ntt_twiddles, l_ntt_pass, l_merkle_leaves, l_merkle_level, l_merkle_path, h_add,         h_sub,          h_mul,         h_to_mont,   h_from_mont,     h_modulus,
 };

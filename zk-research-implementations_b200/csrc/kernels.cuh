@@ -946,12 +946,15 @@ __device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, Fixed
                     *reinterpret_cast<volatile unsigned int*>(&a.relay->abort) = status;
                 }
             }
-            if (threadIdx.x == 0) {
+            if (threadIdx.x < 32) {
+                // all lanes of warp 0 poll together (one broadcast read): a spin by a single lane leaves the warp split, and
+                // its next shuffles were measured to take ~10 us (k_sc_small's cluster messages)
                 const volatile unsigned int* seq = reinterpret_cast<const volatile unsigned int*>(&a.relay->seq);
                 const volatile unsigned int* ab = reinterpret_cast<const volatile unsigned int*>(&a.relay->abort);
                 unsigned int aborted = 0;
                 while (*seq != want && !(aborted = *ab)) __nanosleep(32);
-                s_abort = aborted;
+                aborted = __shfl_sync(0xffffffffu, aborted, 0);
+                if (threadIdx.x == 0) s_abort = aborted;
                 __threadfence();
             }
             __syncthreads();
@@ -1017,7 +1020,13 @@ __device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, Fixed
 // not throughput, matters here), CTA reduction, mailbox exchange with the host transcript.
 // With first_eval the kernel also produces round 0 (all NPTS points), so a whole GKR phase on a
 // small layer is one launch.
+// Tables of up to 16 x that size run the same way in ONE THREAD-BLOCK CLUSTER of nc = 2..16 CTAs: CTA c keeps the
+// entries j = c (mod nc) of every table in its shared memory (the multi-GPU layout of zkb200.cu: the two entries of a
+// pair differ in the top index bit, so they live in the same CTA), every CTA polls the mailbox for the challenge, and
+// the CTAs' partial sums meet in CTA 0's shared memory (distributed shared memory stores + one arrival counter, no
+// cluster barrier per round).  Once a CTA holds a single entry per table, CTA 0 collects them and finishes alone.
 constexpr int SMALL_BLOCK = 512;
+constexpr int SMALL_MAX_CLUSTER = 16;
 constexpr int SMALL_SMEM_MAX = 200 * 1024;
 
 // ---- device-side transcript.  With `enabled`, k_sc_small derives every challenge itself: warp 0
@@ -1108,7 +1117,25 @@ struct SmallArgs {
     unsigned int base_seq;
     long long timeout_clocks;
     DtArgs dt;          // device-side Fiat-Shamir transcript (NPTS == 3 shapes)
+    int nc;             // CTAs of the launch (one thread-block cluster; 1 = a single CTA): see k_sc_small
 };
+
+// ---- thread-block cluster helpers (k_sc_small with nc > 1)
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of the same shared-memory object in CTA `rank` of the cluster (distributed shared memory)
+template <class T>
+__device__ __forceinline__ T* cluster_map(T* p, uint32_t rank) {
+    uint64_t out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t)(uintptr_t)p), "r"(rank));
+    return (T*)(uintptr_t)out;
+}
 
 // integrand at t = 0, (1), 2, .. for one pair position, accumulated with modular adds
 template <class F, int KIND, int D, int NPTS, bool SKIP1>
@@ -1159,20 +1186,33 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
     __shared__ Fe s_r;
     __shared__ unsigned int s_status;
     __shared__ Fe s_red[SMALL_BLOCK / 32][MAXPTS];
+    // Cluster messages carry a checksum over payload and message number instead of being fenced (a cluster-scope fence is
+    // MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR + CCTL.IVALL, ~0.3 us per hop: tools/clustertest.cu): the reader re-reads until the
+    // checksum matches.
+    __shared__ Fe s_part[SMALL_MAX_CLUSTER][MAXPTS];       // CTA 0: the other CTAs' partial sums of the current round
+    __shared__ unsigned int s_pchk[SMALL_MAX_CLUSTER][2];  // CTA 0: their checksums (msg_checksum)
+    __shared__ __align__(64) uint32_t s_cmsg[16];          // CTAs 1..: the mailbox line as CTA 0 read it (same layout as the host's)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.n_tables;
-    const uint32_t cap = a.n_in;
+    const uint32_t NC0 = a.nc > 1 ? (uint32_t)a.nc : 1u;
+    const uint32_t crank = NC0 > 1 ? cluster_cta_rank() : 0u;
+    uint32_t nc = NC0;                 // CTAs still working (1 after CTA 0 collected the tables)
+    const uint32_t cap = a.n_in / NC0;  // entries per table in this CTA
     const int KD = KIND == KIND_XYZ ? 3 : D;
     for (uint32_t idx = tid; idx < (uint32_t)T * cap; idx += SMALL_BLOCK) {
-        const uint32_t t = idx / cap, j = idx - t * cap;
-        tab[(size_t)(2 * t) * cap + j] = a.in[t].base[j];
-        tab[(size_t)(2 * t + 1) * cap + j] = a.in[t].base[a.in[t].stride + j];
+        const uint32_t t = idx / cap, l = idx - t * cap;
+        const uint32_t j = l * NC0 + crank;
+        tab[(size_t)(2 * t) * cap + l] = a.in[t].base[j];
+        tab[(size_t)(2 * t + 1) * cap + l] = a.in[t].base[a.in[t].stride + j];
     }
     if (tid == 0) {
         s_r = a.r0;
         s_status = 1;
     }
+    if (tid < 16) s_cmsg[tid] = tid == 8 ? a.base_seq : 0u;  // (no challenge has this number: they start at base_seq + 1)
+    if (tid < 2 * SMALL_MAX_CLUSTER) s_pchk[tid >> 1][tid & 1] = 0u;
     __syncthreads();
+    if (NC0 > 1) cluster_sync_all();  // every CTA of the cluster runs (and CTA 0's counter is set) before any remote access
     auto ld = [&](int t, uint32_t j) { return fe_from_smem(tab + (size_t)(2 * t) * cap + j, tab + (size_t)(2 * t + 1) * cap + j); };
     auto st = [&](int t, uint32_t j, const Fe& v) {
         tab[(size_t)(2 * t) * cap + j] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
@@ -1290,12 +1330,60 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
             for (int p = 0; p < n; ++p) {
                 Fe v = lane < SMALL_BLOCK / 32 ? s_red[lane][p] : Fd::zero();
                 v = warp_sum<F>(v);
-                if (lane == 0) {
-                    s_ev[p] = v;
-                    if (!dt) a.mb->evals[p] = v;
-                }
+                if (lane == 0) s_ev[p] = v;
             }
-            if (dt) {
+            if (nc > 1) {  // the cluster's sums meet in CTA 0
+                __syncwarp();
+                const unsigned int seq = a.base_seq + pubs + 1;
+                if (crank != 0) {
+                    if (lane == 0) {
+                        unsigned int c0, c1;
+                        msg_checksum(s_ev, n, seq, &c0, &c1);
+                        Fe* rp = cluster_map(&s_part[crank][0], 0);
+                        for (int p = 0; p < n; ++p) rp[p] = s_ev[p];
+                        volatile unsigned int* rc = cluster_map(&s_pchk[crank][0], 0);
+                        rc[0] = c0;
+                        rc[1] = c1;
+                    }
+                } else {
+                    {  // lane c waits for CTA c's message; the loop is warp-uniform (a divergent spin before the
+                       // shuffles of warp_sum measured 10 us: the warp stayed split)
+                        const bool mine = lane >= 1 && lane < (int)NC0;
+                        const volatile uint32_t* w = reinterpret_cast<const volatile uint32_t*>(&s_part[mine ? lane : 0][0]);
+                        const volatile unsigned int* ck = &s_pchk[mine ? lane : 0][0];
+                        const long long t0 = clock64();
+                        bool ok = !mine;
+                        while (!__all_sync(0xffffffffu, ok)) {
+                            unsigned int x = seq * 0x9E3779B9u, y = seq ^ 0x85EBCA6Bu;
+                            for (int k = 0; k < n * 8; ++k) {
+                                const unsigned int wv = w[k];
+                                x ^= wv;
+                                y = ((y << 5) | (y >> 27)) + wv;
+                            }
+                            ok = ok || (x == ck[0] && y == ck[1]);
+                            if (clock64() - t0 > a.timeout_clocks) {
+                                if (lane == 0) {
+                                    s_status = 3;
+                                    a.mb->dev_error = 1;
+                                    __threadfence_system();
+                                }
+                                break;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    for (int p = 0; p < n; ++p) {
+                        Fe v = lane == 0 ? s_ev[p] : (lane < (int)NC0 ? s_part[lane][p] : Fd::zero());
+                        v = warp_sum<F>(v);
+                        if (lane == 0) s_ev[p] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            if (!dt && crank == 0 && lane == 0)
+                for (int p = 0; p < n; ++p) a.mb->evals[p] = s_ev[p];
+            if (crank != 0) {
+            } else if (dt) {
                 __syncwarp();
                 dt_step(n == NPTS);
             } else if (lane == 0) {  // no system fence: the host validates the checksum (FinishArgs::chk)
@@ -1310,7 +1398,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
         if (dt) dt_post();
         ++pubs;
     };
-    uint32_t m = a.n_in;
+    uint32_t m = cap;  // entries per table in this CTA (all of them without a cluster)
     if (a.first_eval) {  // round 0: all NPTS points of the unbound tables
         Fe acc[NPTS];
 #pragma unroll
@@ -1328,12 +1416,16 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
             }
         }
         publish(acc, NPTS);
+        if (s_status != 1) return;
     }
     for (unsigned int chal = a.first_eval ? 1u : 0u;; ++chal) {
         if (chal > 0 && !dt) {  // challenge number `chal` from the host mailbox
             if (warp == 0) {
+                // cluster: only CTA 0 reads the host's mailbox (reads of one host line by several CTAs serialise on PCIe:
+                // measured 3 us per polling CTA and round) and passes the line on to the other CTAs' shared memories
+                const bool from_host = crank == 0;
                 const unsigned int want = a.base_seq + chal;
-                const volatile uint32_t* line = reinterpret_cast<const volatile uint32_t*>(a.mb);
+                const volatile uint32_t* line = from_host ? reinterpret_cast<const volatile uint32_t*>(a.mb) : reinterpret_cast<const volatile uint32_t*>(s_cmsg);
                 const long long t0 = clock64();
                 uint32_t word = 0;
                 unsigned int status = 0;
@@ -1350,10 +1442,15 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
                 if (lane < 8) s_r.l[lane] = word;
                 if (lane == 0) {
                     s_status = status;
-                    if (status == 3) {
+                    if (status == 3 && from_host) {
                         a.mb->dev_error = 1;
                         __threadfence_system();
                     }
+                }
+                if (nc > 1 && from_host) {  // as read (number and checksum included); anything but a challenge becomes an abort
+                    const uint32_t fw = lane == 9 && status != 1 ? 1u : word;
+                    for (uint32_t cc = 1; cc < NC0; ++cc)
+                        if (lane < 16) *reinterpret_cast<volatile uint32_t*>(cluster_map(&s_cmsg[lane], cc)) = fw;
                 }
             }
             __syncthreads();
@@ -1368,6 +1465,68 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
         }
         __syncthreads();
         m = n_out;
+        if (nc > 1 && m == 1) {
+            // one entry per table and CTA left: CTA 0 collects them (entry c of a table comes from CTA c; staged behind
+            // the entries CTA 0 itself still reads, cap >= 2 NC0) and finishes the remaining log2(NC0) rounds alone
+            const unsigned int gseq = ~(a.base_seq + pubs + 1);  // (not the number of a round message)
+            if (crank != 0) {
+                if (tid == 0) {
+                    uint4* rt = cluster_map(tab, 0);
+                    unsigned int x = gseq * 0x9E3779B9u, y = gseq ^ 0x85EBCA6Bu;
+                    for (int t = 0; t < T; ++t)
+                        for (int h = 0; h < 2; ++h) {
+                            const uint4 v = tab[(size_t)(2 * t + h) * cap];
+                            rt[(size_t)(2 * t + h) * cap + NC0 + crank] = v;
+                            const unsigned int wv[4] = {v.x, v.y, v.z, v.w};
+                            for (int k = 0; k < 4; ++k) {
+                                x ^= wv[k];
+                                y = ((y << 5) | (y >> 27)) + wv[k];
+                            }
+                        }
+                    volatile unsigned int* rc = cluster_map(&s_pchk[crank][0], 0);
+                    rc[0] = x;
+                    rc[1] = y;
+                }
+                return;
+            }
+            if (warp == 0) {  // lane c waits for CTA c's entries (warp-uniform loop, see publish)
+                const bool mine = lane >= 1 && lane < (int)NC0;
+                const volatile unsigned int* ck = &s_pchk[mine ? lane : 0][0];
+                const long long t0 = clock64();
+                bool ok = !mine;
+                while (!__all_sync(0xffffffffu, ok)) {
+                    unsigned int x = gseq * 0x9E3779B9u, y = gseq ^ 0x85EBCA6Bu;
+                    for (int t = 0; t < T; ++t)
+                        for (int h = 0; h < 2; ++h) {
+                            const volatile uint32_t* w = reinterpret_cast<const volatile uint32_t*>(tab + (size_t)(2 * t + h) * cap + NC0 + (mine ? lane : 0));
+                            for (int k = 0; k < 4; ++k) {
+                                const unsigned int wv = w[k];
+                                x ^= wv;
+                                y = ((y << 5) | (y >> 27)) + wv;
+                            }
+                        }
+                    ok = ok || (x == ck[0] && y == ck[1]);
+                    if (clock64() - t0 > a.timeout_clocks) {
+                        if (lane == 0) {
+                            s_status = 3;
+                            a.mb->dev_error = 1;
+                            __threadfence_system();
+                        }
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_status != 1) return;
+            for (uint32_t idx = tid; idx < (uint32_t)T * (NC0 - 1); idx += SMALL_BLOCK) {
+                const uint32_t t = idx / (NC0 - 1), cc = 1 + idx % (NC0 - 1);
+                tab[(size_t)(2 * t) * cap + cc] = tab[(size_t)(2 * t) * cap + NC0 + cc];
+                tab[(size_t)(2 * t + 1) * cap + cc] = tab[(size_t)(2 * t + 1) * cap + NC0 + cc];
+            }
+            __syncthreads();
+            nc = 1;
+            m = NC0;
+        }
         if (m == 1) {  // bound values
             if (tid < T) {
                 const Fe v = ld(tid, 0);
@@ -1395,6 +1554,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_sc_small(const __grid_constant_
             }
         }
         publish(acc, NPTS - 1);
+        if (s_status != 1) return;
     }
 }
 

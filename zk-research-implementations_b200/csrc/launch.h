@@ -22,6 +22,7 @@ struct FieldKernels {
     int (*sc_tail)(int kind, int D, int npts, bool tc, const TailArgs& a, int grid, cudaStream_t s);
     // single-CTA shared-memory kernel for small tables; returns a cudaError_t, or -1 if not instantiated
     int (*sc_small)(int kind, int D, int npts, const SmallArgs& a, cudaStream_t s);
+    int (*sc_small_max_cluster)();  // largest thread-block cluster of k_sc_small the device places (1 = none)
     // resident CTAs per SM for that instantiation (0 = unsupported); fused: 0 = k_sc_eval, 1 = k_sc_fold_eval, 2 = k_sc_tail,
     // 3 = k_sc_fold_eval_tc, 4 = k_sc_tail<TC>, 5 = k_sc_eval_tc / k_sc_eval_gram
     int (*sc_occupancy)(int fused, int kind, int D, int npts);

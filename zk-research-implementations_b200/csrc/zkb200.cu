@@ -331,6 +331,7 @@ struct zkb_ctx {
     TcMatsBuilder tcm;
     Fe* d_cpow8 = nullptr;
     bool tc_enabled = true;
+    int cluster_max = 1;        // CTAs of the largest thread-block cluster k_sc_small is launched with (ZKB200_CLUSTER_MAX caps it; 1 = single CTA)
     bool tc_tail_ok = false;    // two CTAs per SM of the tensor-core persistent kernel are co-resident (probed at creation)
     // persistent round kernel
     TailMailbox* mb = nullptr;   // mapped pinned host memory
@@ -546,7 +547,8 @@ int32_t collect(zkb_ctx* c, int npts, bool sharded, const FinishArgs& f, Fe* out
 int sc_occ(zkb_ctx* c, int fused, int kind, int D, int npts);
 // Tensor-core folds for a round pass whose smallest output tables have n_out_min entries: throughput-bound sizes only
 // (a tile is 128 quad positions; below 2^16 entries the TMA -> MMA -> TMEM pipeline is latency, not bandwidth).
-constexpr uint64_t TC_MIN_N_OUT = 1ull << 16;
+// smallest round (entries written per table) the tensor-core kernels take; ZKB200_TC_MIN_LOG2 overrides (tuning)
+static const uint64_t TC_MIN_N_OUT = 1ull << (getenv("ZKB200_TC_MIN_LOG2") ? std::atoi(getenv("ZKB200_TC_MIN_LOG2")) : 15);
 bool tc_round_ok(zkb_ctx* c, int kind, int D, int npts, uint64_t n_out_min, int fused) {
     return c->tc_enabled && tc_shape(kind, D, npts) && n_out_min >= TC_MIN_N_OUT && ((n_out_min >> 1) & 127u) == 0 && sc_occ(c, fused, kind, D, npts) > 0;
 }
@@ -648,12 +650,25 @@ int32_t sp_ensure_work(zkb_ctx* c, SumPolyState* sp) {
 // Local table size at which the shards are gathered (C2).  Automatic: as soon as the REPLICATED table fits the on-chip
 // kernel, so the rounds after the gather are one k_sc_small launch; with the per-round NCCL fallback (no shared
 // memory between the ranks' hosts) every sharded round is a launch and an all-reduce, so gather early instead.
+// Largest table (entries) one CTA of k_sc_small holds for `tables` tables / the largest its cluster holds.
+uint64_t small_cap_cta(const zkb_ctx* c, size_t tables) {
+    if (!c->small_bytes || !tables) return 0;
+    const uint64_t budget = c->small_bytes < (uint32_t)SMALL_SMEM_MAX ? c->small_bytes : (uint32_t)SMALL_SMEM_MAX;
+    uint64_t n = 1;
+    while (2 * n * tables * 32 <= budget) n *= 2;
+    return n >= 2 ? n : 0;
+}
+// (the device-side transcript, an opt-in experiment, exists for the single-CTA kernel only)
+inline int small_cluster_ctas(const zkb_ctx* c) { return c->dt_enabled ? 1 : c->cluster_max; }
+uint64_t small_cap_cluster(const zkb_ctx* c, size_t tables) {
+    const uint64_t n = small_cap_cta(c, tables), k = (uint64_t)small_cluster_ctas(c);
+    // (a CTA of a cluster keeps >= 2 x cluster entries per table: the collection step of k_sc_small stages behind them)
+    return n >= 2 * k ? n * k : n;
+}
 uint64_t gather_threshold_n(const zkb_ctx* c, const SumPolyState* sp) {
     if (c->gather_log2) return 1ull << c->gather_log2;
     if (c->use_shm && c->small_bytes && sp->rest.empty() && !sp->sel.empty()) {
-        const uint64_t budget = c->small_bytes < (uint32_t)SMALL_SMEM_MAX ? c->small_bytes : (uint32_t)SMALL_SMEM_MAX;
-        uint64_t n = 1;
-        while (2 * n * sp->sel.size() * 32 <= budget) n *= 2;
+        const uint64_t n = small_cap_cluster(c, sp->sel.size());
         const uint64_t g = n >> c->log2world;
         if (g >= 2) return g;
     }
@@ -772,13 +787,16 @@ int32_t sp_bind_and_next(zkb_ctx* c, SumPolyState* sp, const Fe& r, Fe* evals, F
     const bool tc = tc_round_ok(c, sp->kind, sp->kD, sp->npts, n_out, 3);
     const int grid = grid_for(c, n_out / 2, sc_occ(c, tc ? 3 : 1, sp->kind, sp->kD, sp->npts));
     ZK_TRY(prep_finish(c, grid, sp->npts - 1, sp->sharded, &a.fin));
-    prof_begin(c, ZKB_K_SC_FOLD_EVAL, 96.0 * (double)sp->sel.size() * (double)n_out);
     if (tc) {
         ScArgsTc at;
         at.s = a;
         c->tcm.make(c->H, r, &at.mats);
+        prof_begin(c, ZKB_K_SC_FOLD_EVAL, 96.0 * (double)sp->sel.size() * (double)n_out);  // after the host arithmetic: the interval is the launch
         if (!c->K->sc_fold_eval_tc(sp->kind, sp->kD, sp->npts, at, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval_tc: shape not instantiated");
-    } else if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
+    } else {
+        prof_begin(c, ZKB_K_SC_FOLD_EVAL, 96.0 * (double)sp->sel.size() * (double)n_out);
+        if (!c->K->sc_fold_eval(sp->kind, sp->kD, sp->npts, a, grid, c->stream)) ZK_FAIL(c, ZKB_ERR_UNSUPPORTED, "sc_fold_eval: shape not instantiated");
+    }
     ZK_TRY(check_launch(c, "k_sc_fold_eval"));
     if (sp->state == 0) sp->state = 1;
     sp->cur_n = n_out;
@@ -816,7 +834,11 @@ int32_t sp_final_values(zkb_ctx* c, SumPolyState* sp, Fe* vals) {
 //     challenges through the host mailbox);
 //   * tables that fit in shared memory: the single-CTA kernel k_sc_small, which can also
 //     produce round 0 itself, so a small sumcheck is exactly one launch.
-constexpr uint64_t MID_N = 1ull << 17;
+// table size below which the rounds are latency-bound (CUDA-core launch of the persistent kernel, or the on-chip kernel
+// k_sc_small where its cluster holds the tables: 2^15 entries for two tables); ZKB200_MID_LOG2 overrides (tuning).
+// Measured at 2^24 x 2 tables: tensor-core launch down to 2^17 + CUDA-core launch to 2^15 + k_sc_small 1.063 ms; tensor-core
+// launch down to 2^15 + k_sc_small 1.037 ms (a launch boundary costs more than two 18 us rounds).
+static const uint64_t MID_N = 1ull << (getenv("ZKB200_MID_LOG2") ? std::atoi(getenv("ZKB200_MID_LOG2")) : 15);
 struct RoundDriver {
     zkb_ctx* c;
     SumPolyState* sp;
@@ -856,10 +878,7 @@ struct RoundDriver {
     }
     uint64_t small_cap() const {  // largest table (entries) k_sc_small takes for this shape
         if (!c->small_bytes || sp->sharded || !sp->rest.empty()) return 0;
-        uint64_t budget = c->small_bytes < (uint32_t)SMALL_SMEM_MAX ? c->small_bytes : (uint32_t)SMALL_SMEM_MAX;
-        uint64_t n = 1;
-        while (2 * n * sp->sel.size() * 32 <= budget) n *= 2;
-        return n >= 2 ? n : 0;
+        return small_cap_cluster(c, sp->sel.size());
     }
     bool small_ok() const { return sp->cur_n >= 2 && sp->cur_n <= small_cap(); }
     uint64_t gather_n() const { return gather_threshold_n(c, sp); }
@@ -934,7 +953,10 @@ struct RoundDriver {
         // Device transcript: the sponge as it stands now (after the challenge r was drawn, or before round 0) moves
         // to the kernel; the host keeps its own copy and replays every round behind the device.
         dt = false;
-        if (tr && c->dt_enabled && c->dt_rounds && sp->npts == 3 && (first_eval || claim) && ilog2_u64(sp->cur_n) + 1 <= DT_MAX_ROUNDS &&
+        const uint64_t cta_cap = small_cap_cta(c, sp->sel.size());
+        int nc = 1;
+        while (cta_cap && sp->cur_n / (uint64_t)nc > cta_cap && nc < small_cluster_ctas(c)) nc *= 2;
+        if (tr && c->dt_enabled && c->dt_rounds && nc == 1 && sp->npts == 3 && (first_eval || claim) && ilog2_u64(sp->cur_n) + 1 <= DT_MAX_ROUNDS &&
             tr->hasher.snapshot(a.dt.st, &a.dt.fill_words)) {
             dt = true;
             a.dt.enabled = 1;
@@ -949,6 +971,7 @@ struct RoundDriver {
         a.n_tables = (int)sp->sel.size();
         a.n_products = sp->kP;
         a.n_in = (uint32_t)sp->cur_n;
+        a.nc = nc;
         a.first_eval = first_eval ? 1 : 0;
         a.r0 = r;
         a.mb = c->mb;
@@ -987,13 +1010,13 @@ struct RoundDriver {
         begin_mailbox();
         a.base_seq = base;
         a.timeout_clocks = 6000000000ll;  // ~3 s
-        // Throughput-bound rounds (tables > 2^17 entries) and latency-bound rounds run as two launches of the same
+        // Rounds above MID_N entries and the latency-bound rounds below run as two launches of the same
         // kernel, so that each launch (and its profile entry) belongs to one regime.
         stop_n = sp->sharded ? gather_n() : small_cap();
         const bool big = sp->cur_n > MID_N;
         if (big && stop_n < MID_N) stop_n = MID_N;
         a.stop_n = stop_n;
-        // tensor-core folds when every round of this launch is throughput-bound (its last round writes stop_n entries)
+        // tensor-core folds when every round of this launch is large enough for them (its last round writes stop_n entries)
         const bool tc = big && !first_eval && stop_n >= MID_N && c->tc_tail_ok && tc_round_ok(c, sp->kind, sp->kD, sp->npts, stop_n, 4);
         if (tc) {
             a.cpow8 = c->d_cpow8;
@@ -1920,6 +1943,16 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
             cudaGetLastError();
         cudaMemsetAsync(d, 0, sizeof(unsigned int), c->stream);
     }
+    {
+        const char* e = getenv("ZKB200_CLUSTER_MAX");
+        int want = e ? std::atoi(e) : SMALL_MAX_CLUSTER;
+        if (want > SMALL_MAX_CLUSTER) want = SMALL_MAX_CLUSTER;
+        c->cluster_max = 1;
+        if (want > 1) {
+            const int have = c->K->sc_small_max_cluster();
+            while (c->cluster_max * 2 <= want && c->cluster_max * 2 <= have) c->cluster_max *= 2;
+        }
+    }
     // Under Nsight Compute every launch is made synchronous, so a kernel that waits for the host's next
     // challenge can never be answered: profile with one launch per round (the same round_pass code).
     extern char** environ;
@@ -2068,7 +2101,7 @@ int32_t zkb_ctx_profile_read(zkb_ctx* c, int32_t k, uint64_t* launches, double* 
 const char* zkb_kernel_name(int32_t k) {
     static const char* names[ZKB_K_COUNT] = {"k_sc_eval", "k_sc_fold_eval", "k_fold_tables", "k_final_bind", "k_fold",
                                              "k_aos_to_planar/k_planar_to_aos", "k_gkr_phase1/2", "other", "k_sc_tail", "k_sc_small",
-                                             "k_sc_tail (tables <= 2^17)"};
+                                             "k_sc_tail (latency-bound launch)"};
     return (k >= 0 && k < ZKB_K_COUNT) ? names[k] : "?";
 }
 
@@ -2098,6 +2131,11 @@ int32_t zkb_ctx_tensor_cores(const zkb_ctx* c, int32_t* enabled, int32_t* persis
     if (!c || !enabled || !persistent) return ZKB_ERR_BAD_ARG;
     *enabled = c->tc_enabled ? 1 : 0;
     *persistent = c->tc_enabled && c->tc_tail_ok ? 1 : 0;
+    return ZKB_OK;
+}
+int32_t zkb_ctx_small_cluster_max(const zkb_ctx* c, int32_t* ctas) {
+    if (!c || !ctas) return ZKB_ERR_BAD_ARG;
+    *ctas = c->cluster_max;
     return ZKB_OK;
 }
 int32_t zkb_ctx_set_tail_threshold(zkb_ctx* c, uint32_t log2_entries) {

@@ -136,6 +136,7 @@ def lib() -> C.CDLL:
         "zkb_kzg_open": (i32, [vp, u64, u64, u64p, u32, u64p]),
         "zkb_kzg_get_proof": (i32, [vp, u64, u64, u64p, u64p, u32, vp]),
         "zkb_ctx_tensor_cores": (i32, [vp, i32p, i32p]),
+        "zkb_ctx_small_cluster_max": (i32, [vp, i32p]),
         "zkb_tc_fold_matrices": (i32, [i32, u64p, vp]),
         "zkb_fft_evaluate": (i32, [vp, u64p, u64, u64p]),
         "zkb_fft_interpolate": (i32, [vp, u64p, u64, u64p]),
@@ -267,6 +268,12 @@ class Context:
         a, b = C.c_int32(), C.c_int32()
         _ck(self, lib().zkb_ctx_tensor_cores(self._h, C.byref(a), C.byref(b)))
         return bool(a.value), bool(b.value)
+
+    def small_cluster_max(self) -> int:
+        """CTAs of the largest cluster the on-chip round kernel uses: see zkb_ctx_small_cluster_max."""
+        a = C.c_int32()
+        _ck(self, lib().zkb_ctx_small_cluster_max(self._h, C.byref(a)))
+        return a.value
 
     def sync(self) -> None:
         _ck(self, lib().zkb_ctx_sync(self._h))
