@@ -549,8 +549,12 @@ int sc_occ(zkb_ctx* c, int fused, int kind, int D, int npts);
 // (a tile is 128 quad positions; below 2^16 entries the TMA -> MMA -> TMEM pipeline is latency, not bandwidth).
 // smallest round (entries written per table) the tensor-core kernels take; ZKB200_TC_MIN_LOG2 overrides (tuning)
 static const uint64_t TC_MIN_N_OUT = 1ull << (getenv("ZKB200_TC_MIN_LOG2") ? std::atoi(getenv("ZKB200_TC_MIN_LOG2")) : 15);
-bool tc_round_ok(zkb_ctx* c, int kind, int D, int npts, uint64_t n_out_min, int fused) {
-    return c->tc_enabled && tc_shape(kind, D, npts) && n_out_min >= TC_MIN_N_OUT && ((n_out_min >> 1) & 127u) == 0 && sc_occ(c, fused, kind, D, npts) > 0;
+// ... and the smallest the PERSISTENT tensor-core launch continues to once it runs (ZKB200_TC_TAIL_MIN_LOG2): a launch
+// boundary (~35 us) costs more than its small rounds lose against the CUDA-core launch (15 vs 16 us per round), so it
+// runs down to wherever the on-chip kernel / the gather of the shards takes over (a tile is 128 quad positions: >= 2^9).
+static const uint64_t TC_TAIL_MIN_N_OUT = 1ull << (getenv("ZKB200_TC_TAIL_MIN_LOG2") ? std::atoi(getenv("ZKB200_TC_TAIL_MIN_LOG2")) : 9);
+bool tc_round_ok(zkb_ctx* c, int kind, int D, int npts, uint64_t n_out_min, int fused, uint64_t floor_n = TC_MIN_N_OUT) {
+    return c->tc_enabled && tc_shape(kind, D, npts) && n_out_min >= floor_n && n_out_min >= 256 && ((n_out_min >> 1) & 127u) == 0 && sc_occ(c, fused, kind, D, npts) > 0;
 }
 int sc_occ(zkb_ctx* c, int fused, int kind, int D, int npts) {
     char key[64];
@@ -1014,10 +1018,17 @@ struct RoundDriver {
         // kernel, so that each launch (and its profile entry) belongs to one regime.
         stop_n = sp->sharded ? gather_n() : small_cap();
         const bool big = sp->cur_n > MID_N;
-        if (big && stop_n < MID_N) stop_n = MID_N;
-        a.stop_n = stop_n;
         // tensor-core folds when every round of this launch is large enough for them (its last round writes stop_n entries)
-        const bool tc = big && !first_eval && stop_n >= MID_N && c->tc_tail_ok && tc_round_ok(c, sp->kind, sp->kD, sp->npts, stop_n, 4);
+        bool tc = false;
+        if (big && !first_eval && c->tc_tail_ok) {
+            const uint64_t tstop = stop_n < TC_TAIL_MIN_N_OUT ? TC_TAIL_MIN_N_OUT : stop_n;
+            if (tc_round_ok(c, sp->kind, sp->kD, sp->npts, tstop, 4, TC_TAIL_MIN_N_OUT)) {
+                tc = true;
+                stop_n = tstop;
+            }
+        }
+        if (big && !tc && stop_n < MID_N) stop_n = MID_N;
+        a.stop_n = stop_n;
         if (tc) {
             a.cpow8 = c->d_cpow8;
             c->tcm.make(c->H, r, &a.mats0);
@@ -1943,6 +1954,7 @@ int32_t zkb_ctx_create(int32_t field_id, int32_t device, int32_t mode, zkb_ctx**
             cudaGetLastError();
         cudaMemsetAsync(d, 0, sizeof(unsigned int), c->stream);
     }
+    if (const char* e = getenv("ZKB200_GATHER_LOG2")) c->gather_log2 = (uint32_t)std::atoi(e);  // tuning: as zkb_ctx_set_gather_threshold
     {
         const char* e = getenv("ZKB200_CLUSTER_MAX");
         int want = e ? std::atoi(e) : SMALL_MAX_CLUSTER;
