@@ -672,7 +672,9 @@ uint64_t small_cap_cluster(const zkb_ctx* c, size_t tables) {
 uint64_t gather_threshold_n(const zkb_ctx* c, const SumPolyState* sp) {
     if (c->gather_log2) return 1ull << c->gather_log2;
     if (c->use_shm && c->small_bytes && sp->rest.empty() && !sp->sel.empty()) {
-        const uint64_t n = small_cap_cluster(c, sp->sel.size());
+        // (the single-CTA size, not the cluster's: gathering 16 x larger shards earlier was not faster at 2 GPUs, 1.12 vs
+        // 1.13 ms, and the all-gather of 8 ranks grows with it)
+        const uint64_t n = small_cap_cta(c, sp->sel.size());
         const uint64_t g = n >> c->log2world;
         if (g >= 2) return g;
     }
@@ -1017,17 +1019,21 @@ struct RoundDriver {
         // Rounds above MID_N entries and the latency-bound rounds below run as two launches of the same
         // kernel, so that each launch (and its profile entry) belongs to one regime.
         stop_n = sp->sharded ? gather_n() : small_cap();
-        const bool big = sp->cur_n > MID_N;
+        const uint64_t mid_n = sp->sharded && MID_N < (1ull << 17) ? (1ull << 17) : MID_N;
+        const bool big = sp->cur_n > mid_n;
         // tensor-core folds when every round of this launch is large enough for them (its last round writes stop_n entries)
         bool tc = false;
         if (big && !first_eval && c->tc_tail_ok) {
-            const uint64_t tstop = stop_n < TC_TAIL_MIN_N_OUT ? TC_TAIL_MIN_N_OUT : stop_n;
-            if (tc_round_ok(c, sp->kind, sp->kD, sp->npts, tstop, 4, TC_TAIL_MIN_N_OUT)) {
+            // sharded rounds (lock-step with the other ranks): the split of round 2's measured 8-GPU runs stays -- tensor cores
+            // down to 2^17 entries, the CUDA-core launch below
+            const uint64_t floor_n = sp->sharded ? (1ull << 17) : TC_TAIL_MIN_N_OUT;
+            const uint64_t tstop = stop_n < floor_n ? floor_n : stop_n;
+            if (tc_round_ok(c, sp->kind, sp->kD, sp->npts, tstop, 4, floor_n)) {
                 tc = true;
                 stop_n = tstop;
             }
         }
-        if (big && !tc && stop_n < MID_N) stop_n = MID_N;
+        if (big && !tc && stop_n < mid_n) stop_n = mid_n;
         a.stop_n = stop_n;
         if (tc) {
             a.cpow8 = c->d_cpow8;
