@@ -812,7 +812,7 @@ struct TailRelay {  // device memory: CTA 0 re-publishes the host's message for 
     unsigned int seq;
     unsigned int abort;
     unsigned int pad[2];
-    TcFoldMats mats;  // tensor-core variant: the byte matrices of the same challenge
+    Fe r;  // tensor-core variant: the challenge itself (every CTA builds the two byte matrices in its own shared memory)
 };
 struct TailArgs {
     TabRef in[MAXT];
@@ -917,20 +917,14 @@ __device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, Fixed
                     Fe r;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) r.l[k] = __shfl_sync(0xffffffffu, word, k);
-                    if (lane < 8) {
+                    if (TC) {
+                        // the challenge as it is: the byte matrices are 64 Montgomery products and 2 KiB that every CTA builds
+                        // for itself faster than one warp can build, publish and 296 CTAs re-read them (2.4 -> 0.6 us here)
+                        if (lane < 8) a.relay->r.l[lane] = word;
+                    } else if (lane < 8) {
                         Fe t = Fd::mul(r, a.cpow[lane]);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) a.relay->rt.t[lane][k] = t.l[k];
-                    }
-                    if (TC) {  // lane i: column i of both byte matrices, T1_i = (1 - r) 2^(8 i + 32), T2_i = r 2^(8 i + 32) mod p
-                        const Fe cp = a.cpow8[lane];
-                        const Fe t1 = Fd::mul(Fd::sub(a.cpow8[32], r), cp), t2 = Fd::mul(r, cp);
-                        uint8_t* m0 = a.relay->mats.b[0] + (lane / 16) * 512 + lane % 16;
-#pragma unroll
-                        for (int n = 0; n < 32; ++n) {
-                            m0[n * 16] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
-                            m0[1024 + n * 16] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
-                        }
                     }
                     __threadfence();
                     __syncwarp();
@@ -959,10 +953,23 @@ __device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, Fixed
             }
             __syncthreads();
             if (s_abort) return;
-            for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = __ldcg(&a.relay->rt.t[0][0] + w);
             if (TC) {
-                for (int w = threadIdx.x; w < 128; w += BLOCK)
-                    reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(stage) + TcRoundSmem<NPTS>::mats_off)[w] = __ldcg(reinterpret_cast<const uint4*>(&a.relay->mats) + w);
+                if (threadIdx.x < 32) {  // lane i: column i of both byte matrices, T1_i = (1 - r) 2^(8 i + 32), T2_i = r 2^(8 i + 32) mod p
+                    const int lane = threadIdx.x;
+                    Fe r;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r.l[k] = __ldcg(&a.relay->r.l[k]);
+                    const Fe cp = a.cpow8[lane];
+                    const Fe t1 = Fd::mul(Fd::sub(a.cpow8[32], r), cp), t2 = Fd::mul(r, cp);
+                    uint8_t* m0 = reinterpret_cast<uint8_t*>(stage) + TcRoundSmem<NPTS>::mats_off + (lane / 16) * 512 + lane % 16;
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) {
+                        m0[n * 16] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
+                        m0[1024 + n * 16] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
+                    }
+                }
+            } else {
+                for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = __ldcg(&a.relay->rt.t[0][0] + w);
             }
         }
         if (TC) fence_proxy_async();  // the matrices: generic-proxy writes, read by the tensor core through the async proxy
