@@ -812,7 +812,7 @@ struct TailRelay {  // device memory: CTA 0 re-publishes the host's message for 
     unsigned int seq;
     unsigned int abort;
     unsigned int pad[2];
-    Fe r;  // tensor-core variant: the challenge itself (every CTA builds the two byte matrices in its own shared memory)
+    __align__(64) uint32_t line[16];  // the host's mailbox line as CTA 0 read it: challenge [0..8), number [8], checksum [10]
 };
 struct TailArgs {
     TabRef in[MAXT];
@@ -913,25 +913,13 @@ __device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, Fixed
                     else if (clock64() - t0 > a.timeout_clocks) status = 3;
                 }
                 if (status == 1) {
+                    // The line goes on as it was read -- challenge, number and checksum: every CTA validates it the same way
+                    // (no fence, no second flag) and builds what it needs from the challenge itself: 64 (tensor cores) or 8
+                    // Montgomery products per CTA are cheaper than one warp building 2 KiB and 296 CTAs re-reading them
+                    // (relay 2.4 -> 0.4 us per round, ZKB200_TRACE=2).
                     if (lane == 0) a.mb->ts[0] = gtime();
-                    Fe r;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) r.l[k] = __shfl_sync(0xffffffffu, word, k);
-                    if (TC) {
-                        // the challenge as it is: the byte matrices are 64 Montgomery products and 2 KiB that every CTA builds
-                        // for itself faster than one warp can build, publish and 296 CTAs re-read them (2.4 -> 0.6 us here)
-                        if (lane < 8) a.relay->r.l[lane] = word;
-                    } else if (lane < 8) {
-                        Fe t = Fd::mul(r, a.cpow[lane]);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) a.relay->rt.t[lane][k] = t.l[k];
-                    }
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) {
-                        *reinterpret_cast<volatile unsigned int*>(&a.relay->seq) = want;
-                        a.mb->ts[1] = gtime();
-                    }
+                    if (lane < 16) __stcg(&a.relay->line[lane], word);
+                    if (lane == 0) a.mb->ts[1] = gtime();
                 } else if (lane == 0) {
                     if (status == 3) {
                         a.mb->dev_error = 1;
@@ -941,36 +929,46 @@ __device__ __forceinline__ void tail_body(const TailArgs& a, uint4* stage, Fixed
                 }
             }
             if (threadIdx.x < 32) {
-                // all lanes of warp 0 poll together (one broadcast read): a spin by a single lane leaves the warp split, and
+                // all lanes of warp 0 poll together (one 64-byte read): a spin by a single lane leaves the warp split, and
                 // its next shuffles were measured to take ~10 us (k_sc_small's cluster messages)
-                const volatile unsigned int* seq = reinterpret_cast<const volatile unsigned int*>(&a.relay->seq);
+                const int lane = threadIdx.x;
+                const volatile uint32_t* rl = reinterpret_cast<const volatile uint32_t*>(a.relay->line);
                 const volatile unsigned int* ab = reinterpret_cast<const volatile unsigned int*>(&a.relay->abort);
                 unsigned int aborted = 0;
-                while (*seq != want && !(aborted = *ab)) __nanosleep(32);
-                aborted = __shfl_sync(0xffffffffu, aborted, 0);
-                if (threadIdx.x == 0) s_abort = aborted;
-                __threadfence();
+                uint32_t word;
+                for (;;) {
+                    word = lane < 16 ? rl[lane] : 0u;
+                    const uint32_t seq = __shfl_sync(0xffffffffu, word, 8);
+                    const uint32_t chk = __shfl_sync(0xffffffffu, word, 10);
+                    const uint32_t x = __reduce_xor_sync(0xffffffffu, lane < 8 ? word : 0u);
+                    if (seq == want && (x ^ (want * 0x9E3779B9u)) == chk) break;
+                    if ((aborted = *ab)) break;
+                    __nanosleep(32);
+                }
+                if (lane == 0) s_abort = aborted;
+                __threadfence();  // (tables written by other CTAs in the previous round are read after this)
+                if (!aborted) {
+                    Fe r;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r.l[k] = __shfl_sync(0xffffffffu, word, k);
+                    if (TC) {  // lane i: column i of both byte matrices, T1_i = (1 - r) 2^(8 i + 32), T2_i = r 2^(8 i + 32) mod p
+                        const Fe cp = a.cpow8[lane];
+                        const Fe t1 = Fd::mul(Fd::sub(a.cpow8[32], r), cp), t2 = Fd::mul(r, cp);
+                        uint8_t* m0 = reinterpret_cast<uint8_t*>(stage) + TcRoundSmem<NPTS>::mats_off + (lane / 16) * 512 + lane % 16;
+#pragma unroll
+                        for (int n = 0; n < 32; ++n) {
+                            m0[n * 16] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
+                            m0[1024 + n * 16] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
+                        }
+                    } else if (lane < 8) {  // row i of the fixed-multiplicand table: r 2^(32 i + 64)
+                        const Fe t = Fd::mul(r, a.cpow[lane]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) s_rt.t[lane][k] = t.l[k];
+                    }
+                }
             }
             __syncthreads();
             if (s_abort) return;
-            if (TC) {
-                if (threadIdx.x < 32) {  // lane i: column i of both byte matrices, T1_i = (1 - r) 2^(8 i + 32), T2_i = r 2^(8 i + 32) mod p
-                    const int lane = threadIdx.x;
-                    Fe r;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) r.l[k] = __ldcg(&a.relay->r.l[k]);
-                    const Fe cp = a.cpow8[lane];
-                    const Fe t1 = Fd::mul(Fd::sub(a.cpow8[32], r), cp), t2 = Fd::mul(r, cp);
-                    uint8_t* m0 = reinterpret_cast<uint8_t*>(stage) + TcRoundSmem<NPTS>::mats_off + (lane / 16) * 512 + lane % 16;
-#pragma unroll
-                    for (int n = 0; n < 32; ++n) {
-                        m0[n * 16] = (uint8_t)(t1.l[n / 4] >> (8 * (n % 4)));
-                        m0[1024 + n * 16] = (uint8_t)(t2.l[n / 4] >> (8 * (n % 4)));
-                    }
-                }
-            } else {
-                for (int w = threadIdx.x; w < 64; w += BLOCK) (&s_rt.t[0][0])[w] = __ldcg(&a.relay->rt.t[0][0] + w);
-            }
         }
         if (TC) fence_proxy_async();  // the matrices: generic-proxy writes, read by the tensor core through the async proxy
         __syncthreads();
