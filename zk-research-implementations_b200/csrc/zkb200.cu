@@ -1019,14 +1019,16 @@ struct RoundDriver {
         // Rounds above MID_N entries and the latency-bound rounds below run as two launches of the same
         // kernel, so that each launch (and its profile entry) belongs to one regime.
         stop_n = sp->sharded ? gather_n() : small_cap();
-        const uint64_t mid_n = sp->sharded && MID_N < (1ull << 17) ? (1ull << 17) : MID_N;
+        static const uint64_t shard_mid = getenv("ZKB200_TC_SHARD_MIN_LOG2") ? MID_N : (1ull << 17);
+        const uint64_t mid_n = sp->sharded && MID_N < shard_mid ? shard_mid : MID_N;
         const bool big = sp->cur_n > mid_n;
         // tensor-core folds when every round of this launch is large enough for them (its last round writes stop_n entries)
         bool tc = false;
         if (big && !first_eval && c->tc_tail_ok) {
             // sharded rounds (lock-step with the other ranks): the split of round 2's measured 8-GPU runs stays -- tensor cores
             // down to 2^17 entries, the CUDA-core launch below
-            const uint64_t floor_n = sp->sharded ? (1ull << 17) : TC_TAIL_MIN_N_OUT;
+            static const uint64_t shard_floor = 1ull << (getenv("ZKB200_TC_SHARD_MIN_LOG2") ? std::atoi(getenv("ZKB200_TC_SHARD_MIN_LOG2")) : 17);
+            const uint64_t floor_n = sp->sharded ? shard_floor : TC_TAIL_MIN_N_OUT;
             const uint64_t tstop = stop_n < floor_n ? floor_n : stop_n;
             if (tc_round_ok(c, sp->kind, sp->kD, sp->npts, tstop, 4, floor_n)) {
                 tc = true;
